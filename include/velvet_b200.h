@@ -1,0 +1,264 @@
+/*
+ * velvet_b200.h -- C ABI of the B200-native XPBD cloth solver (drop-in for the hot path of
+ * vitalight/Velvet: VtClothSolverGPU::Simulate + SpatialHashGPU::Hash + VtBuffer).
+ *
+ * Two layers, both plain C (pointers + sizes + PODs, no C++/torch types):
+ *
+ *  1. The KERNEL SEAM: one entry point per free function that the reference's host code
+ *     (VtClothSolverGPU.hpp, SpatialHashGPU.hpp) calls into its .cu files.  Same argument order
+ *     and meaning as the reference declarations cited on each prototype; glm::vec3* becomes
+ *     float* (packed xyz, 12-byte stride), glm::mat4 becomes const float[16] column-major.
+ *     All pointers must be device-accessible (cudaMalloc / cudaMallocManaged).  Launches are
+ *     asynchronous on the seam stream (default: the legacy default stream, as in the reference).
+ *
+ *  2. The OBJECT SURFACE: an opaque handle mirroring class VtClothSolverGPU
+ *     (VtClothSolverGPU.hpp L23-231) and SpatialHashGPU (SpatialHashGPU.hpp L15-60): cloth
+ *     registration, constraint append, collider update, Simulate(), public sim buffers.
+ *     Simulate() on a handle runs the fused sm_100a pipeline (SoA float4 state, tile-fused
+ *     deterministic Jacobi iteration, own radix sort, one CUDA graph per frame).
+ *
+ * Error convention (reference: print + exit(EXIT_FAILURE), helper_cuda.h L566-579): every
+ * function returns 0 on success or a negative VelvetStatus and never exits; the message is
+ * available from velvet_last_error() (thread-local).
+ */
+#ifndef VELVET_B200_H
+#define VELVET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VELVET_API __declspec(dllexport)
+#else
+#define VELVET_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------ PODs (layout == reference) */
+
+/* Common.hpp L19-47, sizeof == 80. */
+typedef struct VtSimParams {
+    int32_t numSubsteps;           /* 0  */
+    int32_t numIterations;         /* 4  */
+    int32_t maxNumNeighbors;       /* 8  */
+    float maxSpeed;                /* 12 */
+    float gravity[3];              /* 16 */
+    float bendCompliance;          /* 28 */
+    float damping;                 /* 32 */
+    float relaxationFactor;        /* 36 */
+    float longRangeStretchiness;   /* 40 */
+    float collisionMargin;         /* 44 */
+    float friction;                /* 48 */
+    uint8_t enableSelfCollision;   /* 52 (C++ bool) */
+    uint8_t _pad[3];
+    int32_t interleavedHash;       /* 56 */
+    uint32_t numParticles;         /* 60 */
+    float particleDiameter;        /* 64 */
+    float deltaTime;               /* 68 */
+    float particleDiameterScalar;  /* 72 */
+    float hashCellSizeScalar;      /* 76 */
+} VtSimParams;
+
+/* Common.hpp L113-118 */
+typedef enum VtColliderType { VT_COLLIDER_SPHERE = 0, VT_COLLIDER_PLANE = 1, VT_COLLIDER_CUBE = 2 } VtColliderType;
+
+/* VtClothSolverGPU.cuh L8-18, sizeof == 196. */
+typedef struct VtSDFCollider {
+    int32_t type;              /* 0   */
+    float position[3];         /* 4   */
+    float scale[3];            /* 16  */
+    float deltaTime;           /* 28  */
+    float curTransform[9];     /* 32  mat3 column-major (upper-left of the model matrix) */
+    float invCurTransform[16]; /* 68  mat4 column-major */
+    float lastTransform[16];   /* 132 mat4 column-major */
+} VtSDFCollider;
+
+/* SpatialHashGPU.cuh L7-15, sizeof == 24. */
+typedef struct VtHashParams {
+    uint32_t numObjects;
+    uint32_t maxNumNeighbors;
+    float cellSpacing;
+    float cellSpacing2;
+    int32_t tableSize;
+    float particleDiameter2;
+} VtHashParams;
+
+typedef enum VelvetStatus {
+    VELVET_OK = 0,
+    VELVET_ERR_INVALID_ARGUMENT = -1,
+    VELVET_ERR_CUDA = -2,
+    VELVET_ERR_STATE = -3,
+    VELVET_ERR_UNSUPPORTED = -4
+} VelvetStatus;
+
+VELVET_API const char* velvet_last_error(void);
+VELVET_API int velvet_version(void);
+/* Fills *p with the reference's host-side defaults (Common.hpp L21-46). */
+VELVET_API int velvet_default_params(VtSimParams* p);
+
+/* ------------------------------------------------------------------ 1. kernel seam */
+
+/* VtClothSolverGPU.cuh L99 / .cu L23-28.  Copies the params; later seam calls use the copy. */
+VELVET_API int velvet_SetSimulationParams(const VtSimParams* hostParams);
+/* .cuh L101 / .cu L30-40 */
+VELVET_API int velvet_InitializePositions(float* positions, int start, int count, const float* modelMatrix16);
+/* .cuh L103-107 / .cu L42-63 */
+VELVET_API int velvet_PredictPositions(float* predicted, float* velocities, const float* positions, float deltaTime);
+/* .cuh L109-116 / .cu L65-115 */
+VELVET_API int velvet_SolveStretch(float* predicted, float* deltas, int* deltaCounts, const int* stretchIndices,
+                                   const float* stretchLengths, const float* invMasses, unsigned numConstraints);
+/* .cuh L120-128 / .cu L117-203 */
+VELVET_API int velvet_SolveBending(float* predicted, float* deltas, int* deltaCounts, const unsigned* bendingIndices,
+                                   const float* bendingAngles, const float* invMass, unsigned numConstraints,
+                                   float deltaTime);
+/* .cuh L130-139 / .cu L205-251 */
+VELVET_API int velvet_SolveAttachment(float* predicted, float* deltas, int* deltaCounts, const float* invMass,
+                                      const int* attachParticleIDs, const int* attachSlotIDs,
+                                      const float* attachSlotPositions, const float* attachDistances,
+                                      int numConstraints);
+/* .cuh L141 / .cu L253-270 */
+VELVET_API int velvet_ApplyDeltas(float* predicted, float* deltas, int* deltaCounts);
+/* .cuh L143-148 / .cu L289-327.  predicted may alias positions (pre-stabilisation pass). */
+VELVET_API int velvet_CollideSDF(float* predicted, const VtSDFCollider* colliders, const float* positions,
+                                 unsigned numColliders, float deltaTime);
+/* .cuh L150-156 / .cu L329-386 (includes the trailing ApplyDeltas) */
+VELVET_API int velvet_CollideParticles(float* deltas, int* deltaCounts, float* predicted, const float* invMasses,
+                                       const unsigned* neighbors, const float* positions);
+/* .cuh L158-162 / .cu L388-417 */
+VELVET_API int velvet_Finalize(float* velocities, float* positions, const float* predicted, float deltaTime);
+/* .cuh L164-168 / .cu L419-465 */
+VELVET_API int velvet_ComputeNormal(float* normals, const float* positions, const unsigned* indices,
+                                    unsigned numTriangles);
+/* SpatialHashGPU.cuh L17-25 / .cu L159-196.  cellStart/cellEnd hold tableSize entries. */
+VELVET_API int velvet_HashObjects(unsigned* particleHash, unsigned* particleIndex, unsigned* cellStart,
+                                  unsigned* cellEnd, unsigned* neighbors, const float* positions,
+                                  const float* originalPositions, VtHashParams params);
+
+/* Stand-alone stable LSD radix sort of (key,value) pairs on bits [0,endBit) -- the replacement for the
+ * reference's cub::DeviceRadixSort::SortPairs call (SpatialHashGPU.cu L133-157); sorts in place. */
+VELVET_API int velvet_SortPairs(unsigned* keys, unsigned* values, unsigned numItems, int endBit);
+
+/* Stream used by the seam functions (a cudaStream_t); NULL = legacy default stream. */
+VELVET_API int velvet_seam_set_stream(void* cudaStream);
+VELVET_API int velvet_device_synchronize(void);
+
+/* VtAllocBuffer / VtFreeBuffer (Common.cuh L66-78): managed memory, plus explicit copies. */
+VELVET_API int velvet_alloc(void** devPtr, size_t bytes);
+VELVET_API int velvet_free(void* devPtr);
+VELVET_API int velvet_copy(void* dst, const void* src, size_t bytes); /* cudaMemcpyDefault, synchronous */
+
+/* ------------------------------------------------------------------ 2. object surface */
+
+typedef struct VelvetSolver VelvetSolver;
+
+/* Names follow the public members of VtClothSolverGPU (hpp L209-231) and SpatialHashGPU (hpp L54-60). */
+typedef enum VelvetBufferId {
+    VELVET_BUF_POSITIONS = 0,       /* float3  */
+    VELVET_BUF_NORMALS,             /* float3  */
+    VELVET_BUF_INDICES,             /* uint    */
+    VELVET_BUF_VELOCITIES,          /* float3  */
+    VELVET_BUF_PREDICTED,           /* float3  */
+    VELVET_BUF_DELTAS,              /* float3  */
+    VELVET_BUF_DELTACOUNTS,         /* int     */
+    VELVET_BUF_INVMASSES,           /* float   */
+    VELVET_BUF_STRETCHINDICES,      /* int[2S] */
+    VELVET_BUF_STRETCHLENGTHS,      /* float   */
+    VELVET_BUF_BENDINDICES,         /* uint[4B]*/
+    VELVET_BUF_BENDANGLES,          /* float   */
+    VELVET_BUF_ATTACHPARTICLEIDS,   /* int     */
+    VELVET_BUF_ATTACHSLOTIDS,       /* int     */
+    VELVET_BUF_ATTACHDISTANCES,     /* float   */
+    VELVET_BUF_ATTACHSLOTPOSITIONS, /* float3  */
+    VELVET_BUF_NEIGHBORS,           /* uint, column-major [i + N*k] */
+    VELVET_BUF_INITIALPOSITIONS,    /* float3  */
+    VELVET_BUF_PARTICLEHASH,        /* uint    */
+    VELVET_BUF_PARTICLEINDEX,       /* uint    */
+    VELVET_BUF_CELLSTART,           /* uint    */
+    VELVET_BUF_CELLEND,             /* uint    */
+    VELVET_BUF_SDFCOLLIDERS,        /* VtSDFCollider */
+    VELVET_BUF_COUNT
+} VelvetBufferId;
+
+typedef enum VelvetPipeline {
+    VELVET_PIPELINE_FUSED = 0, /* SoA float4 + tile-fused Jacobi + CUDA graph (default)           */
+    VELVET_PIPELINE_SEAM = 1   /* the reference's launch sequence over the seam kernels (A/B, debug) */
+} VelvetPipeline;
+
+/* VtClothSolverGPU::Start (hpp L27-33): numParticles = 0.  params may be NULL (defaults).
+ * device < 0 keeps the current CUDA device. */
+VELVET_API int velvet_solver_create(VelvetSolver** out, int device, const VtSimParams* params);
+VELVET_API int velvet_solver_destroy(VelvetSolver* s);
+/* Global::simParams of this instance; the caller may edit it between frames (ImGui sliders / ModifyParameter). */
+VELVET_API VtSimParams* velvet_solver_params(VelvetSolver* s);
+VELVET_API int velvet_solver_set_pipeline(VelvetSolver* s, int pipeline);
+/* Fused pipeline only: particles per Jacobi tile (0 = default). */
+VELVET_API int velvet_solver_set_tile_size(VelvetSolver* s, int particlesPerTile);
+
+/* AddCloth (hpp L114-156): vertices = host float[3*numVertices] in model space, indices = host uint[numIndices].
+ * Writes the particle offset of the new cloth to *offset. */
+VELVET_API int velvet_solver_add_cloth(VelvetSolver* s, const float* vertices, int numVertices,
+                                       const unsigned* indices, int numIndices, const float* modelMatrix16,
+                                       float particleDiameter, int* offset);
+VELVET_API int velvet_solver_add_stretch(VelvetSolver* s, int idx1, int idx2, float distance);     /* L158-163 */
+VELVET_API int velvet_solver_add_attach_slot(VelvetSolver* s, const float* slotPos3);              /* L165-168 */
+VELVET_API int velvet_solver_add_attach(VelvetSolver* s, int particleIndex, int slotIndex, float distance); /* L170-176 */
+VELVET_API int velvet_solver_add_bend(VelvetSolver* s, unsigned idx1, unsigned idx2, unsigned idx3,
+                                      unsigned idx4, float angle);                                  /* L178-185 */
+/* UpdateColliders (hpp L187-205) with the SDFCollider structs already marshalled by the caller. */
+VELVET_API int velvet_solver_update_colliders(VelvetSolver* s, const VtSDFCollider* colliders, int numColliders);
+/* Convenience marshal of one collider exactly as hpp L195-203 does (invCurTransform = glm::inverse(cur)). */
+VELVET_API int velvet_make_collider(int type, const float* position3, const float* scale3, const float* curTransform16,
+                                    const float* lastTransform16, float deltaTime, VtSDFCollider* out);
+/* Simulate (hpp L56-111): one frame of 1/60 s.  Asynchronous unless sync != 0 (the reference always syncs). */
+VELVET_API int velvet_solver_simulate(VelvetSolver* s, int sync);
+/* New overload named by the spec: Simulate(dt). */
+VELVET_API int velvet_solver_simulate_dt(VelvetSolver* s, float frameTime, int sync);
+VELVET_API int velvet_solver_synchronize(VelvetSolver* s);
+/* SpatialHashGPU::Hash(predicted) on the solver's own hash (hpp L83). */
+VELVET_API int velvet_solver_hash(VelvetSolver* s);
+
+/* Device pointer + element count (elements of the type listed at VelvetBufferId) of a public buffer. */
+VELVET_API int velvet_solver_buffer(VelvetSolver* s, int bufferId, void** devPtr, size_t* count);
+/* Copy a public buffer to / from host memory (count elements of the buffer's type, synchronous). */
+VELVET_API int velvet_solver_download(VelvetSolver* s, int bufferId, void* host, size_t bytes);
+VELVET_API int velvet_solver_upload(VelvetSolver* s, int bufferId, const void* host, size_t bytes);
+/* Asynchronous read-back of positions+normals on the solver stream into pinned host memory (headless
+ * replacement of positions.sync()/normals.sync(), hpp L109-110). */
+VELVET_API int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals);
+/* The cudaStream_t the solver launches on. */
+VELVET_API void* velvet_solver_stream(VelvetSolver* s);
+/* Number of kernel launches (graph kernel nodes included) issued by the last Simulate call. */
+VELVET_API int velvet_solver_last_launch_count(VelvetSolver* s);
+/* Per-stage GPU milliseconds of the last *timed* frame under the reference's labels (GUI.cpp L32-51);
+ * labels/ms arrays of capacity cap; returns the number of stages written. Timing runs outside the graph. */
+VELVET_API int velvet_solver_simulate_timed(VelvetSolver* s, const char** labels, float* ms, int cap);
+
+/* ---- inputs either side of the path: Scene.hpp / VtClothObjectGPU.hpp / Transform.hpp */
+/* GenerateClothMesh (Scene.hpp L131-168): vertices float[3*(R+1)^2], indices uint[6*R^2]. */
+VELVET_API int velvet_generate_cloth_mesh(int resolution, float* vertices, unsigned* indices);
+/* Transform::matrix() (Transform.hpp L22-29, Helper.cpp L8-15): T * Ry * Rz * Rx * S, degrees. */
+VELVET_API int velvet_transform_matrix(const float* position3, const float* rotationDeg3, const float* scale3,
+                                       float* out16);
+/* VtClothObjectGPU::Start (VtClothObjectGPU.hpp L43-58): AddCloth + stretch + attach + bend generation. */
+VELVET_API int velvet_cloth_object_start(VelvetSolver* s, int resolution, const float* vertices,
+                                         const unsigned* indices, const float* modelMatrix16,
+                                         const int* attachedIndices, int numAttached, int* offset);
+
+/* ---- SpatialHashGPU as its own object (SpatialHashGPU.hpp L15-60) */
+typedef struct VelvetSpatialHash VelvetSpatialHash;
+VELVET_API int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects,
+                                  float hashCellSizeScalar, int maxNumNeighbors);
+VELVET_API int velvet_hash_destroy(VelvetSpatialHash* h);
+/* SetInitialPositions: device-accessible float3 array of count elements. */
+VELVET_API int velvet_hash_set_initial_positions(VelvetSpatialHash* h, const float* positions, size_t count);
+/* Hash(positions): device-accessible float3 array of count elements. */
+VELVET_API int velvet_hash_hash(VelvetSpatialHash* h, const float* positions, size_t count);
+VELVET_API int velvet_hash_buffer(VelvetSpatialHash* h, int bufferId, void** devPtr, size_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELVET_B200_H */

@@ -1,0 +1,129 @@
+"""GPU parity of the spatial hash and of the hand-written radix sort: integer work, bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import velvet_b200 as vb
+from velvet_b200 import seam
+from oracle import o1
+
+from util import valid_prefix_table
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+f = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,end_bit", [(1, 8), (33, 5), (1000, 11), (4097, 13), (65536, 17), (300000, 20),
+                                       (1 << 20, 21), (2500000, 23), (1 << 20, 32)])
+def test_sort_pairs_is_a_stable_sort(n, end_bit):
+    rng = np.random.default_rng(n + end_bit)
+    keys = rng.integers(0, 1 << min(end_bit, 31), n, dtype=np.int64).astype(np.uint32)
+    if end_bit == 32:
+        keys = rng.integers(0, 1 << 32, n, dtype=np.int64).astype(np.uint32)
+    keys[: n // 3] = keys[0]  # long runs of equal keys exercise stability
+    rng.shuffle(keys)
+    vals = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys, kind="stable")
+    dk, dv = dev(keys), dev(vals)
+    seam.SortPairs(dk, dv, n, end_bit)
+    assert np.array_equal(host(dk), keys[order])
+    assert np.array_equal(host(dv), vals[order])
+
+
+def test_sort_ignores_bits_above_end_bit():
+    rng = np.random.default_rng(0)
+    n = 50000
+    keys = rng.integers(0, 1 << 20, n, dtype=np.int64).astype(np.uint32)
+    vals = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys & 0xFFF, kind="stable")
+    dk, dv = dev(keys), dev(vals)
+    seam.SortPairs(dk, dv, n, 12)
+    assert np.array_equal(host(dv), vals[order])
+
+
+def _hash_both(pos, init, D, k=64):
+    n = len(pos)
+    cell = np.float32(np.float32(D) * np.float32(1.5))
+    args = (n, k, cell, np.float32(cell * cell), 2 * n, np.float32(np.float32(D) * np.float32(D)))
+    ph, pi, cs, ce, nb = (np.zeros(m, np.uint32) for m in (n, n, 2 * n, 2 * n, k * n))
+    o1.lib().o1_hash_objects(f(ph), f(pi), f(cs), f(ce), f(nb), f(pos), f(init), o1.HashParams(*args))
+    d = [dev(np.zeros(m, np.uint32)) for m in (n, n, 2 * n, 2 * n, k * n)]
+    seam.HashObjects(*d, dev(pos), dev(init), vb.VtHashParams(*args))
+    g = [host(t) for t in d]
+    assert np.array_equal(g[0], ph), "sorted cell keys"
+    assert np.array_equal(g[1], pi), "sorted particle order"
+    assert np.array_equal(g[2], cs), "cellStart"
+    valid = cs != 0xFFFFFFFF
+    assert np.array_equal(g[3][valid], ce[valid]), "cellEnd"
+    assert np.array_equal(valid_prefix_table(g[4], n, k), valid_prefix_table(nb, n, k)), "neighbor lists"
+    return valid_prefix_table(nb, n, k)
+
+
+@pytest.mark.parametrize("R", [31, 63, 255])
+def test_hash_flat_grid_cloth(R):
+    v, _ = o1.generate_cloth_mesh(R)
+    M = o1.transform_matrix((0, 1.5, 1), (90, 0, 0), (1, 1, 1))
+    pos = v.copy().reshape(-1)
+    o1.lib().o1_initialize_positions(f(pos), 0, len(v), f(M))
+    pos = pos.reshape(-1, 3)
+    D = np.float32(np.linalg.norm(v[0] - v[1]).astype(np.float32) * np.float32(1.5))
+    tab = _hash_both(pos, pos.copy(), D)
+    cnt = (tab != 0xFFFFFFFF).sum(0)
+    assert 10 < cnt.mean() < 13
+
+
+def test_hash_random_cloud_with_negative_coordinates():
+    rng = np.random.default_rng(3)
+    n = 20000
+    init = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    pos = (init + rng.normal(0, 0.1, (n, 3))).astype(np.float32)
+    _hash_both(pos, init, np.float32(0.2))
+
+
+def test_hash_dense_cluster_overflows_the_64_entry_caps():
+    # > 64 particles per bucket and > 64 accepted neighbours: bucket scan truncated at 64 entries
+    # (SpatialHashGPU.cu L108), list truncated at 64 with no terminator (L120)
+    rng = np.random.default_rng(4)
+    n = 3000
+    init = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+    pos = rng.uniform(0, 0.3, (n, 3)).astype(np.float32)
+    tab = _hash_both(pos, init, np.float32(0.2))
+    assert ((tab != 0xFFFFFFFF).sum(0) == 64).any()
+
+
+def test_hash_small_neighbor_cap_and_single_particle():
+    rng = np.random.default_rng(5)
+    init = rng.uniform(-1, 1, (500, 3)).astype(np.float32)
+    pos = rng.uniform(0, 0.5, (500, 3)).astype(np.float32)
+    _hash_both(pos, init, np.float32(0.1), k=8)
+    one = np.zeros((1, 3), np.float32)
+    _hash_both(one, one.copy(), np.float32(0.1))
+
+
+def test_spatial_hash_object_matches_oracle():
+    rng = np.random.default_rng(6)
+    n = 5000
+    init = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    pos = (init + rng.normal(0, 0.05, (n, 3))).astype(np.float32)
+    D = np.float32(0.08)
+    h = vb.SpatialHashGPU(D, n)
+    h.SetInitialPositions(init)
+    h.Hash(pos)
+    cell = np.float32(D * np.float32(1.5))
+    ph, pi, cs, ce, nb = (np.zeros(m, np.uint32) for m in (n, n, 2 * n, 2 * n, 64 * n))
+    o1.lib().o1_hash_objects(f(ph), f(pi), f(cs), f(ce), f(nb), f(pos), f(init),
+                             o1.HashParams(n, 64, cell, np.float32(cell * cell), 2 * n, np.float32(D * D)))
+    assert np.array_equal(h.download("particleHash"), ph)
+    assert np.array_equal(h.download("particleIndex"), pi)
+    assert np.array_equal(valid_prefix_table(h.download("neighbors"), n, 64), valid_prefix_table(nb, n, 64))

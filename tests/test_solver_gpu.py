@@ -1,0 +1,222 @@
+"""GPU parity of VtClothSolverGPU::Simulate (fused sm_100a pipeline and the reference-order seam pipeline)
+against the O1 oracle, through the C ABI.
+
+Tolerances are north_star's: max |dx| <= 1e-4 x cloth extent after 1 frame, <= 1e-3 x extent after 60 frames
+(extent = 2.0).  The fused pipeline sums corrections in the oracle's order, so it is in practice far tighter;
+hash outputs (integer work) are compared bit-exactly on the first rebuild."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import velvet_b200 as vb
+from oracle import o1
+
+from util import EXTENT, ColliderTrack, gpu_params, make_pair, max_abs_diff, set_colliders, valid_prefix_table
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+TOL_1 = 1e-4 * EXTENT
+TOL_60 = 1e-3 * EXTENT
+
+
+def _run_cfg1(g, o, frames):
+    """Config 1 (main.cpp L149-178): 32x32, attach {0, R}, plane + sphere r=0.6 at (0, 0.6, -cos 2t)."""
+    sphere = ColliderTrack(vb.COLLIDER_SPHERE, (0, 0.6, -1.0), (0.6, 0.6, 0.6))
+    plane = vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1))
+    for fr in range(frames):
+        sphere.move((0, 0.6, -math.cos(2 * fr / 60.0)))
+        set_colliders(g, o, [plane, sphere.collider()])
+        g.Simulate()
+        if o is not None:
+            o.simulate()
+
+
+@pytest.mark.parametrize("pipeline", [vb.PIPELINE_FUSED, vb.PIPELINE_SEAM])
+def test_cfg1_one_frame(pipeline):
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(31, p, position=(0, 2.5, 0), rotation=(0, 0, 0), attached=[0, 31], pipeline=pipeline)
+    assert np.array_equal(g.download("positions").reshape(-1), o.buffer("positions")), "registration (InitializePositions)"
+    for name in ("stretchIndices", "stretchLengths", "bendIndices", "bendAngles", "attachParticleIDs", "attachSlotIDs",
+                 "attachDistances", "attachSlotPositions", "invMasses", "indices", "initialPositions"):
+        assert np.array_equal(g.download(name).reshape(-1), o.buffer(name)), name
+    _run_cfg1(g, o, 1)
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_1
+    assert max_abs_diff(g.download("velocities"), o.buffer("velocities")) <= 60 * 5 * TOL_1
+    assert max_abs_diff(g.download("normals"), o.buffer("normals")) <= 1e-3
+    # integer work: the hash rebuilt on the last hashing substep
+    assert np.array_equal(g.download("particleHash"), o.buffer("particleHash"))
+    assert np.array_equal(g.download("particleIndex"), o.buffer("particleIndex"))
+    assert np.array_equal(valid_prefix_table(g.download("neighbors"), 1024, 64),
+                          valid_prefix_table(o.buffer("neighbors"), 1024, 64))
+
+
+def test_cfg1_fused_is_bit_close_to_oracle_order():
+    # same summation order as the oracle: only libm-vs-CUDA acosf may differ
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(31, p, position=(0, 2.5, 0), rotation=(0, 0, 0), attached=[0, 31])
+    _run_cfg1(g, o, 1)
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= 2e-6
+
+
+@pytest.mark.parametrize("pipeline", [vb.PIPELINE_FUSED, vb.PIPELINE_SEAM])
+def test_cfg1_sixty_frames(pipeline):
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(31, p, position=(0, 2.5, 0), rotation=(0, 0, 0), attached=[0, 31], pipeline=pipeline)
+    _run_cfg1(g, o, 60)
+    pos = g.download("positions")
+    assert np.isfinite(pos).all()
+    assert max_abs_diff(pos, o.buffer("positions")) <= TOL_60
+    path = os.path.join(GOLDEN, "cfg1_frame60.npz")
+    if os.path.exists(path):
+        assert max_abs_diff(pos, np.load(path)["positions"]) <= TOL_60
+
+
+@pytest.mark.parametrize("frames,tol", [(1, TOL_1), (30, TOL_60)])
+def test_drape_64_self_collision(frames, tol):
+    """Horizontal 64x64 sheet (model = T(0,1.5,1) Rx(90), main.cpp L141) draped over the static sphere + plane."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(63, p)
+    cols = vb.sphere_plane_colliders()
+    set_colliders(g, o, cols)
+    for _ in range(frames):
+        g.Simulate()
+        o.simulate()
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= tol
+
+
+def test_corner_attach_40(self=None):
+    """'Cloth / Attach' scene (main.cpp L125-147): 41x41, four corner attach slots, 2 substeps x 4 iterations."""
+    R = 40
+    p = gpu_params()
+    corners = [0, R, (R + 1) * (R + 1) - 1, (R + 1) * R]
+    g, o = make_pair(R, p, attached=corners)
+    cols = vb.sphere_plane_colliders(radius=0.5)
+    set_colliders(g, o, cols)
+    for _ in range(20):
+        g.Simulate()
+        o.simulate()
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_60
+    inv = g.download("invMasses")
+    assert [inv[c] for c in corners] == [0, 0, 0, 0]
+
+
+def test_moving_attach_slot_and_disabled_self_collision():
+    """Swirl scene (main.cpp L302-333): one attach slot moved by the host between frames; self-collision off."""
+    R = 36
+    p = gpu_params(enableSelfCollision=0)
+    g, o = make_pair(R, p, attached=[0])
+    set_colliders(g, o, [vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1))])
+    for fr in range(10):
+        t = fr / 60.0 * 3
+        slot = np.array([math.sin(t), math.cos(t) + 2, 0], np.float32)
+        g.upload("attachSlotPositions", slot)
+        o.buffer("attachSlotPositions")[:] = slot
+        g.Simulate()
+        o.simulate()
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_60
+
+
+def test_two_cloths_and_cube_collider():
+    """'Multiple Object' scene (main.cpp L232-268): cloths registered one after another on one solver + cube SDF."""
+    p = gpu_params(numSubsteps=5, numIterations=5, friction=0.6)
+    g = vb.VtClothSolverGPU(p)
+    o = o1.O1Solver(__import__("util").to_o1_params(p))
+    for height in (1.5, 1.8):
+        R = 24
+        v, idx = vb.GenerateClothMesh(R)
+        M = vb.TransformMatrix((0, height, 1.0), (90, 0, 0), (1, 1, 1))
+        obj = vb.VtClothObjectGPU(R, g)
+        obj.Start(v, idx, M)
+        o.cloth_object_start(R, v, idx, M, [])
+    assert g.simParams.numParticles == 2 * 25 * 25 == o.params.numParticles
+    cube = ColliderTrack(vb.COLLIDER_CUBE, (0, 0.5, 0), (1, 1, 1), (0, 15, 0))
+    cols = [vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1)), cube.collider()]
+    set_colliders(g, o, cols)
+    for _ in range(25):
+        g.Simulate()
+        o.simulate()
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_60
+
+
+def test_host_may_edit_buffers_between_frames():
+    """MouseGrabber-style edits (MouseGrabber.hpp L64-77): invMass = 0 and position/velocity writes between frames."""
+    p = gpu_params()
+    g, o = make_pair(20, p)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    for fr in range(6):
+        if fr == 2:
+            inv = g.download("invMasses"); inv[5] = 0; g.upload("invMasses", inv); o.buffer("invMasses")[5] = 0
+            pos = g.download("positions"); pos[5] += np.float32(0.05); g.upload("positions", pos)
+            o.buffer("positions").reshape(-1, 3)[5] += np.float32(0.05)
+            vel = g.download("velocities"); vel[7] = (0.5, 0.5, 0); g.upload("velocities", vel)
+            o.buffer("velocities").reshape(-1, 3)[7] = (0.5, 0.5, 0)
+        g.Simulate()
+        o.simulate()
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_60
+
+
+def test_param_changes_between_frames_and_simulate_dt():
+    p = gpu_params(numSubsteps=2, numIterations=4)
+    g, o = make_pair(24, p)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    g.Simulate(); o.simulate()
+    for q in (g.simParams, o.params):
+        q.numIterations = 7
+        q.numSubsteps = 3
+        q.friction = 0.4
+        q.interleavedHash = 2
+    g.Simulate(); o.simulate()
+    g.Simulate(1.0 / 60.0); o.simulate()
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_1 * 3
+
+
+def test_256_one_frame_and_tile_sizes():
+    """Config 2 (256x256, 65k particles): one frame against the oracle, for every supported Jacobi tile size."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    ref = None
+    for tile in (0, 128, 512):
+        g, o = make_pair(255, p, tile_size=tile, oracle=ref is None)
+        cols = vb.sphere_plane_colliders()
+        if ref is None:
+            set_colliders(g, o, cols)
+            o.simulate()
+            ref = o.buffer("positions").copy()
+        else:
+            g.UpdateColliders(cols)
+        g.Simulate()
+        assert max_abs_diff(g.download("positions"), ref) <= TOL_1, tile
+
+
+def test_fused_is_deterministic_and_matches_seam_at_1m():
+    """Headline size (1024x1024, 1M particles): properties that do not need the CPU oracle.
+    Two independent fused runs are bit-identical (deterministic summation); the fused pipeline agrees with the
+    reference-order seam pipeline (float atomics) within the 1-frame tolerance; hash outputs agree bit-exactly."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    outs = []
+    for pipeline in (vb.PIPELINE_FUSED, vb.PIPELINE_FUSED, vb.PIPELINE_SEAM):
+        g, _ = make_pair(1023, p, pipeline=pipeline, oracle=False)
+        g.UpdateColliders(vb.sphere_plane_colliders())
+        g.Simulate()
+        g.Simulate()
+        outs.append((g.download("positions"), g.download("particleIndex"), g.download("particleHash")))
+        assert g.lastLaunchCount > 0
+        g.close()
+    assert np.isfinite(outs[0][0]).all()
+    assert np.array_equal(outs[0][0], outs[1][0]), "fused pipeline is run-to-run deterministic"
+    assert max_abs_diff(outs[0][0], outs[2][0]) <= TOL_1
+    assert np.array_equal(outs[0][2], outs[2][2]) and np.array_equal(outs[0][1], outs[2][1])
+    # sortedness / permutation properties at full size
+    assert np.all(np.diff(outs[0][2].astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(outs[0][1]), np.arange(1 << 20, dtype=np.uint32))
+
+
+def test_empty_solver_and_error_convention():
+    g = vb.VtClothSolverGPU()
+    g.Simulate()  # no cloth registered: silently nothing to do (CUDA_CALL early-out)
+    with pytest.raises(vb.VelvetError):
+        g.AddAttach(3, 0, 0.0)  # out of range -> error status, never exit()
+    with pytest.raises(vb.VelvetError):
+        g.SetTileSize(100)

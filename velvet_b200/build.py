@@ -1,0 +1,78 @@
+"""Builds libvelvet_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+    python -m velvet_b200.build [--force] [--verbose]
+
+Flags that matter:
+  -gencode arch=compute_100a,code=sm_100a   B200 only, no other targets, no PTX fallback
+  -fmad=false                               no FMA contraction: fp32 results follow the written operation
+                                            order and match the CPU oracle (which uses -ffp-contract=off)
+  -lineinfo                                 ncu --import-source maps SASS back to these sources
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libvelvet_b200.so")
+INCLUDE = os.path.normpath(os.path.join(HERE, "..", "include"))
+
+SOURCES = ["radix_sort.cu", "seam_kernels.cu", "fused_kernels.cu", "tile_plan.cpp", "solver.cu", "capi.cu"]
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-Wall,-Wno-unused-function",
+    "-I", INCLUDE,
+]
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))]
+    headers.append(os.path.join(INCLUDE, "velvet_b200.h"))
+    headers.append(os.path.abspath(__file__))
+    objs, jobs = [], []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJDIR, src + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [path] + headers):
+            cmd = [NVCC, *FLAGS, "-x", "cu", "-c", path, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append(cmd)
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if verbose or r.stderr.strip():
+            sys.stderr.write(r.stderr)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(run, jobs))
+    if jobs or force or _stale(LIB, objs):
+        run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

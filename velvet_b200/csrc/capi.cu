@@ -1,0 +1,386 @@
+// capi.cu -- extern "C" object surface of include/velvet_b200.h over velvet::VtClothSolverGPU / SpatialHashGPU.
+#include <cstring>
+
+#include "capi_util.hpp"
+#include "solver.hpp"
+
+namespace velvet {
+
+namespace {
+thread_local std::string t_lastError;
+}
+
+int set_error(int status, const std::string& msg)
+{
+    t_lastError = msg;
+    return status;
+}
+void clear_error() { t_lastError.clear(); }
+
+}  // namespace velvet
+
+using namespace velvet;
+
+struct VelvetSolver {
+    VtClothSolverGPU impl;
+    VelvetSolver(int device, const VtSimParams* p) : impl(device, p) {}
+};
+
+struct VelvetSpatialHash {
+    SpatialHashGPU impl;
+    float particleDiameter;
+    cudaStream_t stream = 0;
+    VelvetSpatialHash(float d, int n, float scalar, int k) : impl(d, n, scalar, k), particleDiameter(d) {}
+};
+
+#define VT_REQUIRE(cond, msg) \
+    if (!(cond)) return set_error(VELVET_ERR_INVALID_ARGUMENT, msg)
+
+namespace {
+
+struct BufView {
+    void* ptr;
+    size_t count;     // elements
+    size_t elemSize;  // bytes per element
+};
+
+bool solver_buffer(VtClothSolverGPU& s, int id, BufView& v)
+{
+    SpatialHashGPU* h = s.spatialHash().get();
+    switch (id) {
+    case VELVET_BUF_POSITIONS: v = {s.positions.data(), s.positions.size(), 12}; return true;
+    case VELVET_BUF_NORMALS: v = {s.normals.data(), s.normals.size(), 12}; return true;
+    case VELVET_BUF_INDICES: v = {s.indices.data(), s.indices.size(), 4}; return true;
+    case VELVET_BUF_VELOCITIES: v = {s.velocities.data(), s.velocities.size(), 12}; return true;
+    case VELVET_BUF_PREDICTED: v = {s.predicted.data(), s.predicted.size(), 12}; return true;
+    case VELVET_BUF_DELTAS: v = {s.deltas.data(), s.deltas.size(), 12}; return true;
+    case VELVET_BUF_DELTACOUNTS: v = {s.deltaCounts.data(), s.deltaCounts.size(), 4}; return true;
+    case VELVET_BUF_INVMASSES: v = {s.invMasses.data(), s.invMasses.size(), 4}; return true;
+    case VELVET_BUF_STRETCHINDICES: v = {s.stretchIndices.data(), s.stretchIndices.size(), 4}; return true;
+    case VELVET_BUF_STRETCHLENGTHS: v = {s.stretchLengths.data(), s.stretchLengths.size(), 4}; return true;
+    case VELVET_BUF_BENDINDICES: v = {s.bendIndices.data(), s.bendIndices.size(), 4}; return true;
+    case VELVET_BUF_BENDANGLES: v = {s.bendAngles.data(), s.bendAngles.size(), 4}; return true;
+    case VELVET_BUF_ATTACHPARTICLEIDS: v = {s.attachParticleIDs.data(), s.attachParticleIDs.size(), 4}; return true;
+    case VELVET_BUF_ATTACHSLOTIDS: v = {s.attachSlotIDs.data(), s.attachSlotIDs.size(), 4}; return true;
+    case VELVET_BUF_ATTACHDISTANCES: v = {s.attachDistances.data(), s.attachDistances.size(), 4}; return true;
+    case VELVET_BUF_ATTACHSLOTPOSITIONS: v = {s.attachSlotPositions.data(), s.attachSlotPositions.size(), 12}; return true;
+    case VELVET_BUF_SDFCOLLIDERS: v = {s.sdfColliders.data(), s.sdfColliders.size(), sizeof(VtSDFCollider)}; return true;
+    default: break;
+    }
+    if (!h) {
+        v = {nullptr, 0, 4};
+        return id >= VELVET_BUF_NEIGHBORS && id <= VELVET_BUF_CELLEND;
+    }
+    switch (id) {
+    case VELVET_BUF_NEIGHBORS: v = {h->neighbors.data(), h->neighbors.size(), 4}; return true;
+    case VELVET_BUF_INITIALPOSITIONS: v = {h->initialPositions.data(), h->initialPositions.size(), 12}; return true;
+    case VELVET_BUF_PARTICLEHASH: v = {h->particleHash.data(), h->particleHash.size(), 4}; return true;
+    case VELVET_BUF_PARTICLEINDEX: v = {h->particleIndex.data(), h->particleIndex.size(), 4}; return true;
+    case VELVET_BUF_CELLSTART: v = {h->cellStart.data(), h->cellStart.size(), 4}; return true;
+    case VELVET_BUF_CELLEND: v = {h->cellEnd.data(), h->cellEnd.size(), 4}; return true;
+    default: return false;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* velvet_last_error(void) { return t_lastError.c_str(); }
+int velvet_version(void) { return 100; }
+
+int velvet_default_params(VtSimParams* p)
+{
+    VT_REQUIRE(p, "params is NULL");
+    default_sim_params(*p);
+    return VELVET_OK;
+}
+
+int velvet_solver_create(VelvetSolver** out, int device, const VtSimParams* params)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_error(VELVET_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    *out = new VelvetSolver(device, params);
+    VT_API_END
+}
+
+int velvet_solver_destroy(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    delete s;
+    VT_API_END
+}
+
+VtSimParams* velvet_solver_params(VelvetSolver* s) { return s ? &s->impl.simParams : nullptr; }
+
+int velvet_solver_set_pipeline(VelvetSolver* s, int pipeline)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.setPipeline(pipeline);
+    VT_API_END
+}
+
+int velvet_solver_set_tile_size(VelvetSolver* s, int n)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.setTileSize(n);
+    VT_API_END
+}
+
+int velvet_solver_add_cloth(VelvetSolver* s, const float* vertices, int numVertices, const unsigned* indices, int numIndices,
+                            const float* modelMatrix16, float particleDiameter, int* offset)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    const int off = s->impl.AddCloth(vertices, numVertices, indices, numIndices, modelMatrix16, particleDiameter);
+    if (offset) *offset = off;
+    VT_API_END
+}
+
+int velvet_solver_add_stretch(VelvetSolver* s, int idx1, int idx2, float distance)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.AddStretch(idx1, idx2, distance);
+    VT_API_END
+}
+
+int velvet_solver_add_attach_slot(VelvetSolver* s, const float* slotPos3)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && slotPos3, "bad argument");
+    s->impl.AddAttachSlot(slotPos3);
+    VT_API_END
+}
+
+int velvet_solver_add_attach(VelvetSolver* s, int particleIndex, int slotIndex, float distance)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.AddAttach(particleIndex, slotIndex, distance);
+    VT_API_END
+}
+
+int velvet_solver_add_bend(VelvetSolver* s, unsigned idx1, unsigned idx2, unsigned idx3, unsigned idx4, float angle)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.AddBend(idx1, idx2, idx3, idx4, angle);
+    VT_API_END
+}
+
+int velvet_solver_update_colliders(VelvetSolver* s, const VtSDFCollider* colliders, int numColliders)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.UpdateColliders(colliders, numColliders);
+    VT_API_END
+}
+
+int velvet_make_collider(int type, const float* position3, const float* scale3, const float* cur16, const float* last16,
+                         float deltaTime, VtSDFCollider* out)
+{
+    VT_REQUIRE(position3 && scale3 && cur16 && last16 && out, "make_collider: NULL argument");
+    MakeCollider(type, position3, scale3, cur16, last16, deltaTime, out);
+    return VELVET_OK;
+}
+
+int velvet_solver_simulate(VelvetSolver* s, int sync)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.Simulate();
+    if (sync) s->impl.Synchronize();
+    VT_API_END
+}
+
+int velvet_solver_simulate_dt(VelvetSolver* s, float frameTime, int sync)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    VT_REQUIRE(frameTime > 0, "frameTime must be positive");
+    s->impl.Simulate(frameTime);
+    if (sync) s->impl.Synchronize();
+    VT_API_END
+}
+
+int velvet_solver_synchronize(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.Synchronize();
+    VT_API_END
+}
+
+int velvet_solver_hash(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    VT_REQUIRE(s->impl.spatialHash(), "no cloth registered");
+    s->impl.spatialHash()->Hash(reinterpret_cast<const float*>(s->impl.predicted.data()), s->impl.predicted.size(),
+                                s->impl.simParams.particleDiameter, s->impl.stream());
+    VT_API_END
+}
+
+int velvet_solver_buffer(VelvetSolver* s, int bufferId, void** devPtr, size_t* count)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    BufView v;
+    if (!solver_buffer(s->impl, bufferId, v)) return set_error(VELVET_ERR_INVALID_ARGUMENT, "unknown buffer id");
+    if (devPtr) *devPtr = v.ptr;
+    if (count) *count = v.count;
+    VT_API_END
+}
+
+int velvet_solver_download(VelvetSolver* s, int bufferId, void* host, size_t bytes)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && host, "bad argument");
+    BufView v;
+    if (!solver_buffer(s->impl, bufferId, v)) return set_error(VELVET_ERR_INVALID_ARGUMENT, "unknown buffer id");
+    VT_REQUIRE(bytes <= v.count * v.elemSize, "download: more bytes than the buffer holds");
+    s->impl.Synchronize();
+    if (bytes) VT_CUDA(cudaMemcpy(host, v.ptr, bytes, cudaMemcpyDefault));
+    VT_API_END
+}
+
+int velvet_solver_upload(VelvetSolver* s, int bufferId, const void* host, size_t bytes)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && host, "bad argument");
+    BufView v;
+    if (!solver_buffer(s->impl, bufferId, v)) return set_error(VELVET_ERR_INVALID_ARGUMENT, "unknown buffer id");
+    VT_REQUIRE(bytes <= v.count * v.elemSize, "upload: more bytes than the buffer holds");
+    s->impl.Synchronize();
+    if (bytes) VT_CUDA(cudaMemcpy(v.ptr, host, bytes, cudaMemcpyDefault));
+    VT_API_END
+}
+
+int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    const size_t bytes = s->impl.positions.size() * 12;
+    if (hostPositions && bytes)
+        VT_CUDA(cudaMemcpyAsync(hostPositions, s->impl.positions.data(), bytes, cudaMemcpyDeviceToHost, s->impl.stream()));
+    if (hostNormals && bytes)
+        VT_CUDA(cudaMemcpyAsync(hostNormals, s->impl.normals.data(), bytes, cudaMemcpyDeviceToHost, s->impl.stream()));
+    VT_API_END
+}
+
+void* velvet_solver_stream(VelvetSolver* s) { return s ? (void*)s->impl.stream() : nullptr; }
+int velvet_solver_last_launch_count(VelvetSolver* s) { return s ? s->impl.lastLaunchCount() : 0; }
+
+int velvet_solver_simulate_timed(VelvetSolver* s, const char** labels, float* ms, int cap)
+{
+    static thread_local StageTiming keep;  // owns the label strings handed back to the caller
+    try {
+        clear_error();
+        if (!s) return set_error(VELVET_ERR_INVALID_ARGUMENT, "solver is NULL");
+        keep = s->impl.SimulateTimed();
+        int n = (int)keep.labels.size();
+        if (n > cap) n = cap;
+        for (int i = 0; i < n; i++) {
+            if (labels) labels[i] = keep.labels[i].c_str();
+            if (ms) ms[i] = keep.ms[i];
+        }
+        return n;
+    } catch (const Error& e) {
+        return set_error(e.status, e.what());
+    } catch (const std::exception& e) {
+        return set_error(VELVET_ERR_STATE, e.what());
+    }
+}
+
+int velvet_generate_cloth_mesh(int resolution, float* vertices, unsigned* indices)
+{
+    VT_REQUIRE(resolution > 0 && vertices && indices, "generate_cloth_mesh: bad argument");
+    GenerateClothMesh(resolution, vertices, indices);
+    return VELVET_OK;
+}
+
+int velvet_transform_matrix(const float* position3, const float* rotationDeg3, const float* scale3, float* out16)
+{
+    VT_REQUIRE(position3 && rotationDeg3 && scale3 && out16, "transform_matrix: NULL argument");
+    TransformMatrix(position3, rotationDeg3, scale3, out16);
+    return VELVET_OK;
+}
+
+int velvet_cloth_object_start(VelvetSolver* s, int resolution, const float* vertices, const unsigned* indices,
+                              const float* modelMatrix16, const int* attachedIndices, int numAttached, int* offset)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && resolution > 0 && vertices && indices && modelMatrix16 && numAttached >= 0, "cloth_object_start: bad argument");
+    VT_REQUIRE(numAttached == 0 || attachedIndices, "cloth_object_start: attachedIndices is NULL");
+    const int nv = (resolution + 1) * (resolution + 1);
+    for (int i = 0; i < numAttached; i++) VT_REQUIRE(attachedIndices[i] >= 0 && attachedIndices[i] < nv, "attached index out of range");
+    VtClothObjectGPU obj(resolution, &s->impl);
+    obj.SetAttachedIndices(std::vector<int>(attachedIndices, attachedIndices + numAttached));
+    obj.Start(vertices, indices, modelMatrix16);
+    if (offset) *offset = obj.indexOffset();
+    VT_API_END
+}
+
+int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects, float hashCellSizeScalar,
+                       int maxNumNeighbors)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(out && maxNumObjects > 0 && maxNumNeighbors > 0 && particleDiameter > 0 && hashCellSizeScalar > 0,
+               "hash_create: bad argument");
+    *out = new VelvetSpatialHash(particleDiameter, maxNumObjects, hashCellSizeScalar, maxNumNeighbors);
+    VT_API_END
+}
+
+int velvet_hash_destroy(VelvetSpatialHash* h)
+{
+    VT_API_BEGIN
+    delete h;
+    VT_API_END
+}
+
+int velvet_hash_set_initial_positions(VelvetSpatialHash* h, const float* positions, size_t count)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(h && (positions || !count), "bad argument");
+    h->impl.SetInitialPositions(positions, count);
+    VT_API_END
+}
+
+int velvet_hash_hash(VelvetSpatialHash* h, const float* positions, size_t count)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(h && (positions || !count), "bad argument");
+    h->impl.Hash(positions, count, h->particleDiameter, h->stream);
+    VT_CUDA(cudaStreamSynchronize(h->stream));
+    VT_API_END
+}
+
+int velvet_hash_buffer(VelvetSpatialHash* h, int bufferId, void** devPtr, size_t* count)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(h, "hash is NULL");
+    void* p = nullptr;
+    size_t n = 0;
+    switch (bufferId) {
+    case VELVET_BUF_NEIGHBORS: p = h->impl.neighbors.data(); n = h->impl.neighbors.size(); break;
+    case VELVET_BUF_INITIALPOSITIONS: p = h->impl.initialPositions.data(); n = h->impl.initialPositions.size(); break;
+    case VELVET_BUF_PARTICLEHASH: p = h->impl.particleHash.data(); n = h->impl.particleHash.size(); break;
+    case VELVET_BUF_PARTICLEINDEX: p = h->impl.particleIndex.data(); n = h->impl.particleIndex.size(); break;
+    case VELVET_BUF_CELLSTART: p = h->impl.cellStart.data(); n = h->impl.cellStart.size(); break;
+    case VELVET_BUF_CELLEND: p = h->impl.cellEnd.data(); n = h->impl.cellEnd.size(); break;
+    default: return set_error(VELVET_ERR_INVALID_ARGUMENT, "unknown hash buffer id");
+    }
+    if (devPtr) *devPtr = p;
+    if (count) *count = n;
+    VT_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// fused_kernels.cu -- the B200-native substep pipeline behind VtClothSolverGPU::Simulate.
+//
+// State lives in SoA float4 arrays (x, y, z, invMass) so that one 16-byte load brings a particle's position
+// and its weight; the packed-float3 public buffers are touched once per frame (import / export).  Per frame:
+//
+//   begin_frame      import + CollideSDF pre-stabilisation (frame dt) + PredictPositions(substep 0)
+//   per substep      [hash rebuild]  collide (particles + apply + SDF)  I x iterate  end_substep
+//   normals          per-vertex gather
+//
+// All kernels are HBM/L2-bound gather-scatter work: no tensor cores.  Design points:
+//   * every buffer that a kernel both gathers from and writes is double-buffered (predIn -> predOut), so no
+//     kernel needs atomics or a separate delta array;
+//   * the Jacobi iteration (reference: 3 constraint kernels with 6-16 global atomics per constraint + an
+//     averaging kernel, VtClothSolverGPU.cu L65-264) is ONE kernel per iteration: a CTA owns a tile of
+//     particles, stages tile + halo positions in shared memory, evaluates each constraint once, drops the
+//     per-endpoint corrections into private shared-memory slots and lets each particle sum its slots in
+//     constraint-id order -- deterministic, atomic-free, and ~0.9x the algorithmic bytes thanks to 16-bit
+//     tile-local indices;
+//   * colliders are prepared once per frame (lastTransform * invCurTransform hoisted) and staged per CTA.
+#include "fused_kernels.cuh"
+
+#include "hash_kernels.cuh"
+#include "vt_buffer.hpp"
+
+namespace velvet {
+
+namespace {
+
+constexpr int PB = 256;  // threads per CTA for per-particle kernels
+inline unsigned pgrid(unsigned n) { return (n + PB - 1) / PB; }
+
+__device__ __forceinline__ float4 F4(vec3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+__device__ __forceinline__ void stage_colliders(PreparedCollider* s_col, const PreparedCollider* __restrict__ g_col,
+                                                unsigned n)
+{
+    // 196-byte structs copied as 49 words each
+    const unsigned words = n * (unsigned)(sizeof(PreparedCollider) / 4);
+    const unsigned* src = reinterpret_cast<const unsigned*>(g_col);
+    unsigned* dst = reinterpret_cast<unsigned*>(s_col);
+    for (unsigned i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+__global__ void prepare_inputs_kernel(const VtSDFCollider* __restrict__ colliders, PreparedCollider* prepared,
+                                      const float* __restrict__ slotPositions, float* __restrict__ slotPositionsOut,
+                                      unsigned numSlotFloats, const FrameParams* __restrict__ fp)
+{
+    const unsigned i = threadIdx.x;
+    if (i < fp->numColliders) prepare_collider(colliders[i], prepared[i]);
+    for (unsigned k = i; k < numSlotFloats; k += blockDim.x) slotPositionsOut[k] = slotPositions[k];
+}
+
+__global__ void __launch_bounds__(PB) fill_kernel(unsigned* __restrict__ dst, unsigned value, unsigned n)
+{
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id < n) dst[id] = value;
+}
+
+__global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict__ positions,
+                                                         const float* __restrict__ velocities,
+                                                         const float* __restrict__ invMasses, float4* __restrict__ pos4,
+                                                         float4* __restrict__ vel4, float4* __restrict__ pred,
+                                                         const PreparedCollider* __restrict__ colliders,
+                                                         const FrameParams* __restrict__ fp, unsigned n)
+{
+    __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
+    const unsigned nc = fp->numColliders;
+    stage_colliders(s_col, colliders, nc);
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const VtSimParams& P = fp->P;
+    vec3 pos = load3(positions, id);
+    const float w = invMasses[id];
+    // pre-stabilisation: CollideSDF(positions, colliders, positions, frameTime), VtClothSolverGPU.hpp L73
+    pos = collide_sdf_point(s_col, nc, pos, pos, P.collisionMargin, P.friction, fp->frameTime);
+    // PredictPositions, VtClothSolverGPU.cu L51-52
+    const float dt = fp->substepTime;
+    const vec3 vel = load3(velocities, id) + V3(P.gravity[0], P.gravity[1], P.gravity[2]) * dt;
+    pos4[id] = F4(pos, w);
+    vel4[id] = F4(vel, 0.0f);
+    pred[id] = F4(pos + vel * dt, w);
+}
+
+__global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut,
+                                                     const float4* __restrict__ pos4,
+                                                     const unsigned* __restrict__ neighbors,
+                                                     const PreparedCollider* __restrict__ colliders,
+                                                     const FrameParams* __restrict__ fp, unsigned N, int selfCollision)
+{
+    __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
+    const unsigned nc = fp->numColliders;
+    stage_colliders(s_col, colliders, nc);
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N) return;
+    const VtSimParams& P = fp->P;
+    const float4 pi4 = predIn[id];
+    const float4 xi4 = pos4[id];
+    vec3 pred_i = V3(pi4);
+    const vec3 pos_i = V3(xi4);
+    const float w_i = pi4.w;
+
+    if (selfCollision) {
+        // CollideParticles_Kernel, VtClothSolverGPU.cu L339-372 (gather over the cached neighbour column)
+        vec3 positionDelta = V3(0, 0, 0);
+        int deltaCount = 0;
+        const vec3 vel_i = pred_i - pos_i;
+        const float D = P.particleDiameter;
+        const unsigned maxK = (unsigned)P.maxNumNeighbors;
+        const unsigned* col = neighbors + id;
+        for (unsigned k = 0; k < maxK; k++, col += N) {
+            const unsigned j = __ldg(col);
+            if (j > N) break;
+            const float4 pj4 = __ldg(predIn + j);
+            const float denom = w_i + pj4.w;
+            if (denom <= 0) continue;
+            const vec3 pred_j = V3(pj4);
+            const vec3 diff = pred_i - pred_j;
+            const float distance = length(diff);
+            if (distance >= D) continue;
+            const vec3 gradient = diff / (distance + VT_EPSILON);
+            const float lambda = (distance - D) / denom;
+            const vec3 common = lambda * gradient;
+            deltaCount++;
+            positionDelta -= w_i * common;
+            const vec3 relativeVelocity = vel_i - (pred_j - V3(__ldg(pos4 + j)));
+            positionDelta += w_i * compute_friction(P.friction, common, relativeVelocity);
+        }
+        // ApplyDeltas_Kernel, L257-263
+        const float count = (float)deltaCount;
+        if (count > 0) pred_i += positionDelta / count * P.relaxationFactor;
+    }
+    // CollideSDF_Kernel with the substep dt, L298-313
+    pred_i = collide_sdf_point(s_col, nc, pred_i, pos_i, P.collisionMargin, P.friction, fp->substepTime);
+    predOut[id] = F4(pred_i, w_i);
+}
+
+// ---------------------------------------------------------------- tile-fused Jacobi iteration
+//
+// Shared memory: sp[maxLocals] float4 (tile + halo predicted, w = invMass)
+//                slots[maxSlots] float4 (xyz = correction, w = 1 if the constraint was active)
+//                sb[tileSize+1], bb[tileSize+1] uint16 slot bases
+__global__ void __launch_bounds__(VT_MAX_TILE) iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut,
+                                                            const TilePlanDev plan,
+                                                            const float* __restrict__ attachSlotPositions,
+                                                            const FrameParams* __restrict__ fp)
+{
+    extern __shared__ float4 s_mem[];
+    float4* sp = s_mem;
+    float4* slots = s_mem + plan.maxLocals;
+    uint16_t* sb = reinterpret_cast<uint16_t*>(slots + plan.maxSlots);
+    uint16_t* bb = sb + (plan.tileSize + 2);
+
+    const TileDesc td = plan.tiles[blockIdx.x];
+    const unsigned tid = threadIdx.x;
+    const bool owner = tid < td.nOwned;
+
+    unsigned gid = 0;
+    float4 mine = make_float4(0, 0, 0, 0);
+    if (owner) {
+        gid = __ldg(plan.ownedIds + td.ownedOff + tid);
+        mine = predIn[gid];
+        sp[tid] = mine;
+    }
+    for (unsigned i = tid; i < td.nHalo; i += blockDim.x) sp[td.nOwned + i] = predIn[__ldg(plan.haloIds + td.haloOff + i)];
+    for (unsigned i = tid; i <= td.nOwned; i += blockDim.x) {
+        sb[i] = plan.sBase[td.baseOff + i];
+        bb[i] = plan.bBase[td.baseOff + i];
+    }
+    __syncthreads();
+
+    // SolveStretch_Kernel, VtClothSolverGPU.cu L76-101, one evaluation per constraint
+    for (unsigned c = tid; c < td.nStretch; c += blockDim.x) {
+        const uint2 r = __ldg(plan.stretchRec + td.stretchOff + c);
+        const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
+        const unsigned la = ea >> TP_ORD_BITS, ka = ea & 31u, lb = eb >> TP_ORD_BITS, kb = eb & 31u;
+        const float4 pa = sp[la], pb = sp[lb];
+        vec3 c1, c2;
+        const bool active = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2);
+        if (ka != TP_NO_SLOT) slots[sb[la] + ka] = active ? F4(c1, 1.0f) : make_float4(0, 0, 0, 0);
+        if (kb != TP_NO_SLOT) slots[sb[lb] + kb] = active ? F4(c2, 1.0f) : make_float4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    vec3 delta = V3(0, 0, 0);
+    float count = 0;
+    if (owner) {
+        const unsigned s1 = sb[tid + 1];
+        for (unsigned s = sb[tid]; s < s1; s++) {
+            const float4 v = slots[s];
+            if (v.w != 0) {
+                delta += V3(v);
+                count += 1.0f;
+            }
+        }
+        // SolveAttachment_Kernel, L218-234: per-particle, no slot needed
+        if (plan.hasAttach) {
+            const float lrs = fp->P.longRangeStretchiness;
+            const unsigned a1 = __ldg(plan.attOff + td.baseOff + tid + 1);
+            for (unsigned a = __ldg(plan.attOff + td.baseOff + tid); a < a1; a++) {
+                const uint2 r = __ldg(plan.attachRec + td.attachOff + a);
+                vec3 corr;
+                if (attach_eval(V3(mine), mine.w, load3(attachSlotPositions, r.x), __uint_as_float(r.y), lrs, corr)) {
+                    delta += corr;
+                    count += 1.0f;
+                }
+            }
+        }
+    }
+    __syncthreads();  // slots are reused by the bending phase
+
+    // SolveBending_Kernel, L128-188
+    const float xpbd_bend = fp->xpbdBend;
+    for (unsigned c = tid; c < td.nBend; c += blockDim.x) {
+        const uint4 r = __ldg(plan.bendRec + td.bendOff + c);
+        const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
+        const float4 p0 = sp[e0 >> TP_ORD_BITS], p1 = sp[e1 >> TP_ORD_BITS], p2 = sp[e2 >> TP_ORD_BITS],
+                     p3 = sp[e3 >> TP_ORD_BITS];
+        vec3 c0, c1, c2, c3;
+        const bool active = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z),
+                                      xpbd_bend, c0, c1, c2, c3);
+        const float4 zero = make_float4(0, 0, 0, 0);
+        if ((e0 & 31u) != TP_NO_SLOT) slots[bb[e0 >> TP_ORD_BITS] + (e0 & 31u)] = active ? F4(c0, 1.0f) : zero;
+        if ((e1 & 31u) != TP_NO_SLOT) slots[bb[e1 >> TP_ORD_BITS] + (e1 & 31u)] = active ? F4(c1, 1.0f) : zero;
+        if ((e2 & 31u) != TP_NO_SLOT) slots[bb[e2 >> TP_ORD_BITS] + (e2 & 31u)] = active ? F4(c2, 1.0f) : zero;
+        if ((e3 & 31u) != TP_NO_SLOT) slots[bb[e3 >> TP_ORD_BITS] + (e3 & 31u)] = active ? F4(c3, 1.0f) : zero;
+    }
+    __syncthreads();
+
+    if (owner) {
+        const unsigned s1 = bb[tid + 1];
+        for (unsigned s = bb[tid]; s < s1; s++) {
+            const float4 v = slots[s];
+            if (v.w != 0) {
+                delta += V3(v);
+                count += 1.0f;
+            }
+        }
+        // ApplyDeltas_Kernel, L257-263
+        vec3 p = V3(mine);
+        if (count > 0) p += delta / count * fp->P.relaxationFactor;
+        predOut[gid] = F4(p, mine.w);
+    }
+}
+
+__global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restrict__ predIn, float4* __restrict__ pos4,
+                                                         float4* __restrict__ vel4, float4* __restrict__ predNext,
+                                                         int last, float* __restrict__ positionsOut,
+                                                         float* __restrict__ velocitiesOut,
+                                                         float* __restrict__ predictedOut,
+                                                         const FrameParams* __restrict__ fp, unsigned n)
+{
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const VtSimParams& P = fp->P;
+    const float dt = fp->substepTime;
+    const float4 pr = predIn[id];
+    const float4 po = pos4[id];
+    vec3 newPos, vel;
+    finalize_point(V3(pr), V3(po), dt, P.maxSpeed, P.damping, newPos, vel);  // Finalize_Kernel, .cu L396-406
+    pos4[id] = F4(newPos, po.w);
+    if (last) {
+        vel4[id] = F4(vel, 0.0f);
+        store3(positionsOut, id, newPos);
+        store3(velocitiesOut, id, vel);
+        store3(predictedOut, id, V3(pr));
+    } else {
+        // PredictPositions of the next substep, .cu L51-52
+        vel = vel + V3(P.gravity[0], P.gravity[1], P.gravity[2]) * dt;
+        vel4[id] = F4(vel, 0.0f);
+        predNext[id] = F4(newPos + vel * dt, po.w);
+    }
+}
+
+// ComputeTriangleNormals + ComputeVertexNormals (.cu L419-450) as a gather: vertex v sums the face normals of
+// its incident triangles in ascending triangle id (the oracle's order), then normalises.
+__global__ void __launch_bounds__(PB) normals_kernel(const float4* __restrict__ pos4, const unsigned* __restrict__ indices,
+                                                     const unsigned* __restrict__ vtxTriOff,
+                                                     const unsigned* __restrict__ vtxTris, float* __restrict__ normalsOut,
+                                                     unsigned n)
+{
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    vec3 sum = V3(0, 0, 0);
+    const unsigned t1 = __ldg(vtxTriOff + id + 1);
+    for (unsigned t = __ldg(vtxTriOff + id); t < t1; t++) {
+        const unsigned tri = __ldg(vtxTris + t);
+        const vec3 p1 = V3(__ldg(pos4 + __ldg(indices + 3 * (size_t)tri)));
+        const vec3 p2 = V3(__ldg(pos4 + __ldg(indices + 3 * (size_t)tri + 1)));
+        const vec3 p3 = V3(__ldg(pos4 + __ldg(indices + 3 * (size_t)tri + 2)));
+        sum += cross(p2 - p1, p3 - p1);
+    }
+    store3(normalsOut, id, normalize(sum));
+}
+
+__global__ void __launch_bounds__(PB) pack_float4_kernel(const float* __restrict__ packed3, float4* __restrict__ out, unsigned n)
+{
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    out[id] = F4(load3(packed3, id), 0.0f);
+}
+
+}  // namespace
+
+void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders, PreparedCollider* prepared,
+                           const float* slotPositions, float* slotPositionsOut, unsigned numSlotFloats, const FrameParams* fp)
+{
+    prepare_inputs_kernel<<<1, 256, 0, L.stream>>>(colliders, prepared, slotPositions, slotPositionsOut, numSlotFloats, fp);
+}
+
+void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
+                        float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders, const FrameParams* fp)
+{
+    begin_frame_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(positions, velocities, invMasses, pos4, vel4, pred,
+                                                                   colliders, fp, L.numParticles);
+}
+
+void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
+                    const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision)
+{
+    collide_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp,
+                                                               L.numParticles, selfCollision ? 1 : 0);
+}
+
+size_t iterate_smem_bytes(const TilePlanDev& plan)
+{
+    return sizeof(float4) * ((size_t)plan.maxLocals + plan.maxSlots) + sizeof(uint16_t) * 2 * ((size_t)plan.tileSize + 2);
+}
+
+void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
+                    const float* attachSlotPositions, const FrameParams* fp)
+{
+    iterate_tile_kernel<<<plan.numTiles, plan.tileSize, iterate_smem_bytes(plan), L.stream>>>(predIn, predOut, plan,
+                                                                                               attachSlotPositions, fp);
+}
+
+void configure_iterate_kernel(size_t smemBytes)
+{
+    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+}
+
+void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext, bool last,
+                        float* positionsOut, float* velocitiesOut, float* predictedOut, const FrameParams* fp)
+{
+    end_substep_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(predIn, pos4, vel4, predNext, last ? 1 : 0, positionsOut,
+                                                                   velocitiesOut, predictedOut, fp, L.numParticles);
+}
+
+void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
+                    const unsigned* vtxTris, float* normalsOut)
+{
+    normals_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(pos4, indices, vtxTriOff, vtxTris, normalsOut, L.numParticles);
+}
+
+void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
+                           int tableSize)
+{
+    hash_particles_kernel<PosFloat4><<<pgrid(L.numParticles), PB, 0, L.stream>>>(keys, vals, PosFloat4{pred}, L.numParticles,
+                                                                                 cellSpacing, tableSize);
+}
+
+void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash,
+                            int tableSize)
+{
+    // a fill kernel rather than cudaMemsetAsync: cellStart is managed memory and this runs under graph capture
+    fill_kernel<<<pgrid((unsigned)tableSize), PB, 0, L.stream>>>(cellStart, 0xffffffffu, (unsigned)tableSize);
+    find_cell_start_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(cellStart, cellEnd, particleHash, L.numParticles);
+}
+
+void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
+                            const unsigned* cellStart, const unsigned* cellEnd, const float4* pred, const float4* init4,
+                            VtHashParams hp)
+{
+    cache_neighbors_kernel<PosFloat4, PosFloat4><<<pgrid(L.numParticles), PB, 0, L.stream>>>(
+        neighbors, particleIndex, cellStart, cellEnd, PosFloat4{pred}, PosFloat4{init4}, hp);
+}
+
+void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n)
+{
+    if (n) pack_float4_kernel<<<pgrid(n), PB, 0, L.stream>>>(packed3, out, n);
+}
+
+}  // namespace velvet

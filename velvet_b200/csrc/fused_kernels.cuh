@@ -1,0 +1,84 @@
+// fused_kernels.cuh -- launch interface of the fused sm_100a substep pipeline (see fused_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "tile_plan.hpp"
+#include "vt_math.cuh"
+
+namespace velvet {
+
+// Refreshed in device memory before every frame; graph topology never depends on these values.
+struct FrameParams {
+    VtSimParams P;
+    float frameTime;
+    float substepTime;
+    float xpbdBend;  // bendCompliance / substepTime / substepTime (VtClothSolverGPU.cu L173)
+    unsigned numColliders;
+};
+
+struct TilePlanDev {
+    const TileDesc* tiles;
+    const unsigned* ownedIds;
+    const unsigned* haloIds;
+    const uint16_t* sBase;
+    const uint16_t* bBase;
+    const unsigned* attOff;
+    const uint2* stretchRec;
+    const uint4* bendRec;
+    const uint2* attachRec;
+    unsigned numTiles, maxLocals, maxSlots, tileSize;
+    unsigned hasAttach;
+};
+
+constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)
+constexpr int VT_MAX_TILE = 512;           // particles (= threads) per Jacobi tile, upper bound
+
+struct FusedLaunch {
+    cudaStream_t stream;
+    unsigned numParticles;
+};
+
+// Per-frame inputs the host may have rewritten in managed memory: colliders (prepared once, with
+// lastTransform * invCurTransform hoisted) and attach slot positions (copied to device scratch).
+void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders, PreparedCollider* prepared,
+                           const float* slotPositions, float* slotPositionsOut, unsigned numSlotFloats,
+                           const FrameParams* fp);
+
+// AoS import + pre-stabilisation SDF pass (frame dt) + PredictPositions of substep 0.
+void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
+                        float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders,
+                        const FrameParams* fp);
+
+// CollideParticles + ApplyDeltas + CollideSDF (substep dt): predIn -> predOut.
+void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
+                    const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp,
+                    bool selfCollision);
+
+// One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
+void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
+                    const float* attachSlotPositions, const FrameParams* fp);
+size_t iterate_smem_bytes(const TilePlanDev& plan);
+void configure_iterate_kernel(size_t smemBytes);  // opt in to > 48 KB dynamic shared memory
+
+// Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
+// of positions / velocities / predicted to the public packed-float3 buffers).
+void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext,
+                        bool last, float* positionsOut, float* velocitiesOut, float* predictedOut,
+                        const FrameParams* fp);
+
+// ComputeNormal as a per-vertex gather over incident triangles (ascending triangle id).
+void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
+                    const unsigned* vtxTris, float* normalsOut);
+
+// spatial hash on float4 positions (keys/vals may be the alternate sort buffers)
+void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
+                           int tableSize);
+void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash,
+                            int tableSize);
+void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
+                            const unsigned* cellStart, const unsigned* cellEnd, const float4* pred, const float4* init4,
+                            VtHashParams hp);
+void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
+
+}  // namespace velvet

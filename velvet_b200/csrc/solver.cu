@@ -1,0 +1,885 @@
+// solver.cu -- VtClothSolverGPU / SpatialHashGPU / VtClothObjectGPU host orchestration (see solver.hpp).
+//
+// Reference flow being replaced (VtClothSolverGPU.hpp L56-111): ~250 default-stream launches per frame, each
+// bracketed by two cudaEventCreate + two cudaEventRecord (Timer.hpp L95-119), a cudaMemcpyToSymbol of the
+// params, then cudaDeviceSynchronize.  Here a frame is one cudaMemcpyAsync of a 100-byte parameter block plus
+// one cudaGraphLaunch on the solver's own stream; the graph is re-captured only when the topology changes
+// (particle/constraint counts, substeps, iterations, hash interleave, buffer reallocation).
+#include "solver.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace velvet {
+
+void default_sim_params(VtSimParams& p)
+{
+    std::memset(&p, 0, sizeof(p));
+    p.numSubsteps = 2;
+    p.numIterations = 4;
+    p.maxNumNeighbors = 64;
+    p.maxSpeed = 50.0f;
+    p.gravity[0] = 0.0f;
+    p.gravity[1] = -9.8f;
+    p.gravity[2] = 0.0f;
+    p.bendCompliance = 0.0f;
+    p.damping = 0.25f;
+    p.relaxationFactor = 1.0f;
+    p.longRangeStretchiness = 1.2f;
+    p.collisionMargin = 0.06f;
+    p.friction = 0.1f;
+    p.enableSelfCollision = 1;
+    p.interleavedHash = 3;
+    p.particleDiameterScalar = 1.5f;
+    p.hashCellSizeScalar = 1.5f;
+}
+
+// ------------------------------------------------------------------------------------------------ SpatialHashGPU
+
+SpatialHashGPU::SpatialHashGPU(float particleDiameter, int maxNumObjects, float hashCellSizeScalar, int maxNumNeighbors)
+{
+    m_spacing = particleDiameter * hashCellSizeScalar;
+    m_tableSize = 2 * maxNumObjects;
+    m_maxNumNeighbors = maxNumNeighbors;
+    neighbors.resize((size_t)maxNumObjects * (size_t)maxNumNeighbors);
+    particleHash.resize((size_t)maxNumObjects);
+    particleIndex.resize((size_t)maxNumObjects);
+    cellStart.resize((size_t)m_tableSize);
+    cellEnd.resize((size_t)m_tableSize);
+}
+
+void SpatialHashGPU::SetInitialPositions(const float* positions, size_t count)
+{
+    initialPositions.resize(count);
+    if (count) VT_CUDA(cudaMemcpy(initialPositions.data(), positions, count * sizeof(vec3), cudaMemcpyDefault));
+}
+
+VtHashParams SpatialHashGPU::MakeParams(size_t count, float particleDiameter) const
+{
+    VtHashParams hp;
+    hp.numObjects = (uint)count;
+    hp.cellSpacing = m_spacing;
+    hp.cellSpacing2 = m_spacing * m_spacing;
+    hp.tableSize = m_tableSize;
+    hp.maxNumNeighbors = (uint)m_maxNumNeighbors;
+    hp.particleDiameter2 = particleDiameter * particleDiameter;
+    return hp;
+}
+
+void SpatialHashGPU::Hash(const float* positions, size_t count, float particleDiameter, cudaStream_t stream)
+{
+    if (count > particleHash.size()) throw Error(VELVET_ERR_INVALID_ARGUMENT, "SpatialHashGPU::Hash: more objects than maxNumObjects");
+    if (initialPositions.size() < count) throw Error(VELVET_ERR_STATE, "SpatialHashGPU::Hash: SetInitialPositions not called");
+    seam::HashObjects(particleHash, particleIndex, cellStart, cellEnd, neighbors, positions,
+                      reinterpret_cast<const float*>(initialPositions.data()), MakeParams(count, particleDiameter), stream);
+}
+
+int SpatialHashGPU::ComputeIntCoord(float value) const { return int_coord(value, m_spacing); }
+int SpatialHashGPU::HashCoords(int x, int y, int z) const { return hash_coords(x, y, z, m_tableSize); }
+int SpatialHashGPU::HashPosition(const float* p) const
+{
+    return HashCoords(ComputeIntCoord(p[0]), ComputeIntCoord(p[1]), ComputeIntCoord(p[2]));
+}
+
+// ------------------------------------------------------------------------------------------------ timing helper
+
+struct VtClothSolverGPU::Stage {
+    struct Span {
+        std::string label;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    cudaStream_t stream;
+    explicit Stage(cudaStream_t st) : stream(st) {}
+    void begin(const char* label)
+    {
+        Span s;
+        s.label = label;
+        VT_CUDA(cudaEventCreate(&s.a));
+        VT_CUDA(cudaEventCreate(&s.b));
+        VT_CUDA(cudaEventRecord(s.a, stream));
+        spans.push_back(s);
+    }
+    void end() { VT_CUDA(cudaEventRecord(spans.back().b, stream)); }
+    StageTiming collect()
+    {
+        StageTiming out;
+        VT_CUDA(cudaStreamSynchronize(stream));
+        for (auto& s : spans) {
+            float ms = 0;
+            VT_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+            auto it = std::find(out.labels.begin(), out.labels.end(), s.label);
+            if (it == out.labels.end()) {
+                out.labels.push_back(s.label);
+                out.ms.push_back(ms);
+            } else {
+                out.ms[it - out.labels.begin()] += ms;
+            }
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        spans.clear();
+        return out;
+    }
+};
+
+#define STAGE_BEGIN(t, label) \
+    if (t) (t)->begin(label)
+#define STAGE_END(t) \
+    if (t) (t)->end()
+
+// ------------------------------------------------------------------------------------------------ VtClothSolverGPU
+
+VtClothSolverGPU::VtClothSolverGPU(int device, const VtSimParams* params)
+{
+    if (device >= 0) VT_CUDA(cudaSetDevice(device));
+    VT_CUDA(cudaGetDevice(&m_device));
+    VT_CUDA(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+    if (params) simParams = *params;
+    else default_sim_params(simParams);
+    simParams.numParticles = 0;  // VtClothSolverGPU.hpp L29
+}
+
+VtClothSolverGPU::~VtClothSolverGPU()
+{
+    cudaSetDevice(m_device);
+    if (m_stream) cudaStreamSynchronize(m_stream);
+    if (m_graphExec) cudaGraphExecDestroy(m_graphExec);
+    if (m_graph) cudaGraphDestroy(m_graph);
+    if (m_stream) cudaStreamDestroy(m_stream);
+}
+
+void VtClothSolverGPU::Synchronize() { VT_CUDA(cudaStreamSynchronize(m_stream)); }
+
+void VtClothSolverGPU::OnDestroy()
+{
+    Synchronize();
+    positions.destroy();
+    normals.destroy();
+    invalidate();
+}
+
+void VtClothSolverGPU::setPipeline(int pipeline)
+{
+    if (pipeline != VELVET_PIPELINE_FUSED && pipeline != VELVET_PIPELINE_SEAM)
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "unknown pipeline");
+    m_pipeline = pipeline;
+}
+
+void VtClothSolverGPU::setTileSize(int particlesPerTile)
+{
+    if (particlesPerTile != 0 && (particlesPerTile < 32 || particlesPerTile > VT_MAX_TILE || particlesPerTile % 32))
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "tile size must be 0 or a multiple of 32 in [32,512]");
+    m_tileSize = particlesPerTile;
+    invalidate();
+}
+
+int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uint* meshIndices, int numIndices,
+                               const float* modelMatrix16, float particleDiameter)
+{
+    if (!vertices || numVertices <= 0 || !modelMatrix16 || numIndices < 0 || (numIndices && !meshIndices))
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddCloth: bad argument");
+    VT_CUDA(cudaSetDevice(m_device));
+    Synchronize();
+    const int prevNumParticles = (int)simParams.numParticles;
+    const int newParticles = numVertices;
+
+    // global parameters, hpp L122-125
+    simParams.numParticles += (uint)newParticles;
+    simParams.particleDiameter = particleDiameter;
+    simParams.deltaTime = kFixedDeltaTime;
+    simParams.maxSpeed = 2 * particleDiameter / kFixedDeltaTime * simParams.numSubsteps;
+
+    positions.registerNewBuffer(reinterpret_cast<const vec3*>(vertices), (size_t)newParticles);
+    normals.registerNewBuffer(nullptr, (size_t)newParticles);
+
+    std::vector<uint> shifted((size_t)numIndices);
+    for (int i = 0; i < numIndices; i++) shifted[i] = meshIndices[i] + (uint)prevNumParticles;
+    indices.push_back(shifted);
+
+    velocities.push_back((size_t)newParticles, V3(0, 0, 0));
+    predicted.push_back((size_t)newParticles, V3(0, 0, 0));
+    deltas.push_back((size_t)newParticles, V3(0, 0, 0));
+    deltaCounts.push_back((size_t)newParticles, 0);
+    invMasses.push_back((size_t)newParticles, 1.0f);
+
+    // world transform on the device, hpp L143-145
+    seam::InitializePositions(reinterpret_cast<float*>(positions.data()), prevNumParticles, newParticles, modelMatrix16, m_stream);
+    Synchronize();
+
+    // hash sized to the total particle count; snapshot taken after the transform, hpp L148-149
+    m_spatialHash = std::make_shared<SpatialHashGPU>(particleDiameter, (int)simParams.numParticles,
+                                                     simParams.hashCellSizeScalar, simParams.maxNumNeighbors);
+    m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
+    invalidate();
+    return prevNumParticles;
+}
+
+void VtClothSolverGPU::AddStretch(int idx1, int idx2, float distance)
+{
+    stretchIndices.push_back(idx1);
+    stretchIndices.push_back(idx2);
+    stretchLengths.push_back(distance);
+    invalidate();
+}
+
+void VtClothSolverGPU::AddAttachSlot(const float* p)
+{
+    attachSlotPositions.push_back(V3(p[0], p[1], p[2]));
+    invalidate();
+}
+
+void VtClothSolverGPU::AddAttach(int particleIndex, int slotIndex, float distance)
+{
+    if (particleIndex < 0 || (size_t)particleIndex >= invMasses.size())
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddAttach: particle index out of range");
+    if (distance == 0) invMasses[(size_t)particleIndex] = 0;  // hpp L172
+    attachParticleIDs.push_back(particleIndex);
+    attachSlotIDs.push_back(slotIndex);
+    attachDistances.push_back(distance);
+    invalidate();
+}
+
+void VtClothSolverGPU::AddBend(uint idx1, uint idx2, uint idx3, uint idx4, float angle)
+{
+    bendIndices.push_back(idx1);
+    bendIndices.push_back(idx2);
+    bendIndices.push_back(idx3);
+    bendIndices.push_back(idx4);
+    bendAngles.push_back(angle);
+    invalidate();
+}
+
+void VtClothSolverGPU::AddStretchBulk(const int* idxPairs, const float* distances, size_t n)
+{
+    stretchIndices.append(idxPairs, 2 * n);
+    stretchLengths.append(distances, n);
+    invalidate();
+}
+
+void VtClothSolverGPU::AddBendBulk(const uint* idxQuads, const float* angles, size_t n)
+{
+    bendIndices.append(idxQuads, 4 * n);
+    bendAngles.append(angles, n);
+    invalidate();
+}
+
+void VtClothSolverGPU::AddAttachBulk(const int* particleIds, const int* slotIds, const float* distances, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        if (particleIds[i] < 0 || (size_t)particleIds[i] >= invMasses.size())
+            throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddAttach: particle index out of range");
+        if (distances[i] == 0) invMasses[(size_t)particleIds[i]] = 0;
+    }
+    attachParticleIDs.append(particleIds, n);
+    attachSlotIDs.append(slotIds, n);
+    attachDistances.append(distances, n);
+    invalidate();
+}
+
+void VtClothSolverGPU::UpdateColliders(const VtSDFCollider* colliders, int numColliders)
+{
+    if (numColliders < 0 || (numColliders && !colliders)) throw Error(VELVET_ERR_INVALID_ARGUMENT, "UpdateColliders: bad argument");
+    Synchronize();  // the previous (possibly asynchronous) frame may still be reading the collider block
+    sdfColliders.resize((size_t)numColliders);
+    if (numColliders) std::memcpy(sdfColliders.data(), colliders, sizeof(VtSDFCollider) * (size_t)numColliders);
+}
+
+// ---- the reference's launch order over the seam kernels (pipeline = SEAM), VtClothSolverGPU.hpp L62-101
+void VtClothSolverGPU::simulateSeam(float frameTime, Stage* t)
+{
+    const VtSimParams& P = simParams;
+    const float substepTime = frameTime / (float)P.numSubsteps;
+    cudaStream_t st = m_stream;
+    float* pos = reinterpret_cast<float*>(positions.data());
+    float* pred = reinterpret_cast<float*>(predicted.data());
+    float* vel = reinterpret_cast<float*>(velocities.data());
+    float* dlt = reinterpret_cast<float*>(deltas.data());
+    const float* slots = reinterpret_cast<const float*>(attachSlotPositions.data());
+    const uint numColliders = (uint)sdfColliders.size();
+    int launches = 0;
+
+    STAGE_BEGIN(t, "Solver_CollideSDFs");
+    seam::CollideSDF(P, pos, sdfColliders, pos, numColliders, frameTime, st);
+    launches += seam::LastLaunchCount();
+    STAGE_END(t);
+    for (int substep = 0; substep < P.numSubsteps; substep++) {
+        STAGE_BEGIN(t, "Solver_Predict");
+        seam::PredictPositions(P, pred, vel, pos, substepTime, st);
+        launches += seam::LastLaunchCount();
+        STAGE_END(t);
+        if (P.enableSelfCollision) {
+            if (substep % P.interleavedHash == 0) {
+                STAGE_BEGIN(t, "Solver_Hash");
+                m_spatialHash->Hash(pred, predicted.size(), P.particleDiameter, st);
+                launches += seam::LastLaunchCount();
+                STAGE_END(t);
+            }
+            STAGE_BEGIN(t, "Solver_CollideParticles");
+            seam::CollideParticles(P, dlt, deltaCounts, pred, invMasses, m_spatialHash->neighbors, pos, st);
+            launches += seam::LastLaunchCount();
+            STAGE_END(t);
+        }
+        STAGE_BEGIN(t, "Solver_CollideSDFs");
+        seam::CollideSDF(P, pred, sdfColliders, pos, numColliders, substepTime, st);
+        launches += seam::LastLaunchCount();
+        STAGE_END(t);
+        for (int iteration = 0; iteration < P.numIterations; iteration++) {
+            STAGE_BEGIN(t, "Solver_SolveStretch");
+            seam::SolveStretch(pred, dlt, deltaCounts, stretchIndices, stretchLengths, invMasses, (uint)stretchLengths.size(), st);
+            launches += seam::LastLaunchCount();
+            STAGE_END(t);
+            STAGE_BEGIN(t, "Solver_SolveAttach");
+            seam::SolveAttachment(P, pred, dlt, deltaCounts, invMasses, attachParticleIDs, attachSlotIDs, slots,
+                                  attachDistances, (int)attachParticleIDs.size(), st);
+            launches += seam::LastLaunchCount();
+            STAGE_END(t);
+            STAGE_BEGIN(t, "Solver_SolveBending");
+            seam::SolveBending(P, pred, dlt, deltaCounts, bendIndices, bendAngles, invMasses, (uint)bendAngles.size(),
+                               substepTime, st);
+            launches += seam::LastLaunchCount();
+            STAGE_END(t);
+            STAGE_BEGIN(t, "Solver_ApplyDeltas");
+            seam::ApplyDeltas(P, pred, dlt, deltaCounts, st);
+            launches += seam::LastLaunchCount();
+            STAGE_END(t);
+        }
+        STAGE_BEGIN(t, "Solver_Finalize");
+        seam::Finalize(P, vel, pos, pred, substepTime, st);
+        launches += seam::LastLaunchCount();
+        STAGE_END(t);
+    }
+    STAGE_BEGIN(t, "Solver_UpdateNormals");
+    seam::ComputeNormal(P, reinterpret_cast<float*>(normals.data()), pos, indices, (uint)(indices.size() / 3), st);
+    launches += seam::LastLaunchCount();
+    STAGE_END(t);
+    m_lastLaunches = launches;
+}
+
+// ---- fused pipeline resources: SoA state, tile plan, vertex->triangle CSR (rebuilt when the topology changes)
+void VtClothSolverGPU::ensureFusedResources()
+{
+    if (!m_topologyDirty) return;
+    Synchronize();
+    const uint N = simParams.numParticles;
+    m_fusedUsable = false;
+    m_fallbackReason.clear();
+    if (m_graphExec) {
+        cudaGraphExecDestroy(m_graphExec);
+        m_graphExec = nullptr;
+    }
+    if (m_graph) {
+        cudaGraphDestroy(m_graph);
+        m_graph = nullptr;
+    }
+    m_topologyDirty = false;
+    if (N == 0) {
+        m_fallbackReason = "no particles";
+        return;
+    }
+
+    const int tileSize = m_tileSize ? m_tileSize : 256;
+    m_plan = build_tile_plan(N, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), stretchIndices.data(),
+                             stretchLengths.data(), stretchLengths.size(), bendIndices.data(), bendAngles.data(),
+                             bendAngles.size(), attachParticleIDs.data(), attachSlotIDs.data(), attachDistances.data(),
+                             attachParticleIDs.size(), tileSize);
+    if (!m_plan.valid) {
+        m_fallbackReason = m_plan.whyInvalid;
+        return;
+    }
+    for (size_t i = 0; i < attachSlotIDs.size(); i++)
+        if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= attachSlotPositions.size()) {
+            m_fallbackReason = "attach slot index out of range";
+            return;
+        }
+    for (size_t i = 0; i < indices.size(); i++)
+        if (indices[i] >= N) {
+            m_fallbackReason = "triangle index out of range";
+            return;
+        }
+
+    cudaStream_t st = m_stream;
+    m_dTiles.upload(m_plan.tiles, st);
+    m_dOwned.upload(m_plan.ownedIds, st);
+    m_dHalo.upload(m_plan.haloIds, st);
+    m_dSBase.upload(m_plan.sBase, st);
+    m_dBBase.upload(m_plan.bBase, st);
+    m_dAttOff.upload(m_plan.attOff, st);
+    m_dStretchRec.upload(reinterpret_cast<const uint2*>(m_plan.stretchRec.data()), m_plan.stretchRec.size(), st);
+    m_dBendRec.upload(reinterpret_cast<const uint4*>(m_plan.bendRec.data()), m_plan.bendRec.size(), st);
+    m_dAttachRec.upload(reinterpret_cast<const uint2*>(m_plan.attachRec.data()), m_plan.attachRec.size(), st);
+    m_planDev.tiles = m_dTiles;
+    m_planDev.ownedIds = m_dOwned;
+    m_planDev.haloIds = m_dHalo;
+    m_planDev.sBase = m_dSBase;
+    m_planDev.bBase = m_dBBase;
+    m_planDev.attOff = m_dAttOff;
+    m_planDev.stretchRec = m_dStretchRec;
+    m_planDev.bendRec = m_dBendRec;
+    m_planDev.attachRec = m_dAttachRec;
+    m_planDev.numTiles = (uint)m_plan.tiles.size();
+    m_planDev.maxLocals = m_plan.maxLocals;
+    m_planDev.maxSlots = std::max(m_plan.maxSlots, 1u);
+    m_planDev.tileSize = (uint)m_plan.tileSize;
+    m_planDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
+    const size_t smem = iterate_smem_bytes(m_planDev);
+    if (smem > 200 * 1024) {
+        m_fallbackReason = "tile needs more than 200 KB of shared memory";
+        return;
+    }
+    configure_iterate_kernel(smem);
+
+    // vertex -> incident triangles, ascending triangle id
+    {
+        const size_t T = indices.size() / 3;
+        std::vector<uint> off((size_t)N + 1, 0), tris(3 * T);
+        for (size_t i = 0; i < 3 * T; i++) off[indices[i] + 1]++;
+        for (uint v = 0; v < N; v++) off[v + 1] += off[v];
+        std::vector<uint> cur(off.begin(), off.end() - 1);
+        for (size_t tIdx = 0; tIdx < T; tIdx++)
+            for (int k = 0; k < 3; k++) tris[cur[indices[3 * tIdx + k]]++] = (uint)tIdx;
+        if (tris.empty()) tris.push_back(0);
+        m_vtxTriOff.upload(off, st);
+        m_vtxTris.upload(tris, st);
+    }
+
+    m_pos4.allocate(N);
+    m_vel4.allocate(N);
+    m_predA.allocate(N);
+    m_predB.allocate(N);
+    m_init4.allocate(N);
+    m_keysAlt.allocate(N);
+    m_valsAlt.allocate(N);
+    m_prepared.allocate(VT_MAX_COLLIDERS);
+    m_frameParams.allocate(1);
+    m_slotsDev.allocate(std::max<size_t>(3 * attachSlotPositions.size(), 3));
+    m_sorter.reserve(N);
+    FusedLaunch L{st, N};
+    launch_pack_float4(L, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4, N);
+
+    // the big public buffers live in managed memory (reference contract): make them device-resident now
+    auto prefetch = [&](const void* p, size_t bytes) {
+        if (p && bytes) cudaMemPrefetchAsync(p, bytes, m_device, st);
+    };
+    prefetch(positions.data(), positions.size() * sizeof(vec3));
+    prefetch(normals.data(), normals.size() * sizeof(vec3));
+    prefetch(velocities.data(), velocities.size() * sizeof(vec3));
+    prefetch(predicted.data(), predicted.size() * sizeof(vec3));
+    prefetch(invMasses.data(), invMasses.size() * sizeof(float));
+    prefetch(indices.data(), indices.size() * sizeof(uint));
+    prefetch(m_spatialHash->neighbors.data(), m_spatialHash->neighbors.size() * sizeof(uint));
+    prefetch(m_spatialHash->particleHash.data(), m_spatialHash->particleHash.size() * sizeof(uint));
+    prefetch(m_spatialHash->particleIndex.data(), m_spatialHash->particleIndex.size() * sizeof(uint));
+    prefetch(m_spatialHash->cellStart.data(), m_spatialHash->cellStart.size() * sizeof(uint));
+    prefetch(m_spatialHash->cellEnd.data(), m_spatialHash->cellEnd.size() * sizeof(uint));
+    (void)cudaGetLastError();  // prefetch is best effort
+    VT_CUDA(cudaStreamSynchronize(st));
+    m_fusedUsable = true;
+}
+
+unsigned long long VtClothSolverGPU::topologyKey() const
+{
+    // everything the captured launch sequence depends on (values inside FrameParams are read at run time)
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) {
+        h ^= v;
+        h *= 1099511628211ull;
+    };
+    mix(simParams.numParticles);
+    mix((unsigned)simParams.numSubsteps);
+    mix((unsigned)simParams.numIterations);
+    mix(simParams.enableSelfCollision ? 1u : 0u);
+    mix((unsigned)simParams.interleavedHash);
+    mix((unsigned)simParams.maxNumNeighbors);
+    mix(positions.generation());
+    mix(normals.generation());
+    mix(velocities.generation());
+    mix(predicted.generation());
+    mix(invMasses.generation());
+    mix(indices.generation());
+    mix(sdfColliders.generation());
+    mix(attachSlotPositions.generation());
+    mix(attachSlotPositions.size());
+    mix((unsigned long long)(uintptr_t)m_spatialHash.get());
+    return h;
+}
+
+// ---- one fused frame on m_stream (captured into the graph, or run directly when timing)
+void VtClothSolverGPU::recordFusedFrame(Stage* t)
+{
+    const VtSimParams& P = simParams;
+    const uint N = P.numParticles;
+    FusedLaunch L{m_stream, N};
+    const FrameParams* fp = m_frameParams;
+    SpatialHashGPU& H = *m_spatialHash;
+    int launches = 0;
+
+    STAGE_BEGIN(t, "Solver_SetParams");
+    launch_prepare_inputs(L, sdfColliders, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()),
+                          m_slotsDev, (uint)(3 * attachSlotPositions.size()), fp);
+    launches++;
+    STAGE_END(t);
+
+    float4* cur = m_predA;
+    float4* other = m_predB;
+    STAGE_BEGIN(t, "Solver_Predict");  // import + pre-stabilisation + predict(0)
+    launch_begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()),
+                       invMasses, m_pos4, m_vel4, cur, m_prepared, fp);
+    launches++;
+    STAGE_END(t);
+
+    const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
+    const bool odd = RadixSorter::numPasses(maxBit) & 1;
+    for (int substep = 0; substep < P.numSubsteps; substep++) {
+        if (P.enableSelfCollision && substep % P.interleavedHash == 0) {
+            uint* k0 = odd ? m_keysAlt.data() : H.particleHash.data();
+            uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
+            uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
+            uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
+            STAGE_BEGIN(t, "Solver_HashParticle");
+            launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize());
+            launches++;
+            STAGE_END(t);
+            STAGE_BEGIN(t, "Solver_HashSort");
+            m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
+            launches += m_sorter.lastLaunchCount();
+            STAGE_END(t);
+            STAGE_BEGIN(t, "Solver_HashBuildCell");
+            launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            launches++;
+            STAGE_END(t);
+            STAGE_BEGIN(t, "Solver_HashCache");
+            launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
+                                   H.MakeParams(N, P.particleDiameter));
+            launches++;
+            STAGE_END(t);
+        }
+        STAGE_BEGIN(t, "Solver_CollideParticles");  // + ApplyDeltas + CollideSDFs
+        launch_collide(L, cur, other, m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0);
+        launches++;
+        std::swap(cur, other);
+        STAGE_END(t);
+
+        STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
+        for (int iteration = 0; iteration < P.numIterations; iteration++) {
+            launch_iterate(L, cur, other, m_planDev, m_slotsDev, fp);
+            launches++;
+            std::swap(cur, other);
+        }
+        STAGE_END(t);
+
+        STAGE_BEGIN(t, "Solver_Finalize");  // + Predict of the next substep / export on the last one
+        const bool last = substep == P.numSubsteps - 1;
+        launch_end_substep(L, cur, m_pos4, m_vel4, other, last, reinterpret_cast<float*>(positions.data()),
+                           reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
+        launches++;
+        if (!last) std::swap(cur, other);
+        STAGE_END(t);
+    }
+    STAGE_BEGIN(t, "Solver_UpdateNormals");
+    launch_normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()));
+    launches++;
+    STAGE_END(t);
+    VT_CUDA(cudaGetLastError());
+    m_graphLaunches = launches;
+}
+
+void VtClothSolverGPU::Simulate() { Simulate(kFixedDeltaTime); }
+
+void VtClothSolverGPU::Simulate(float frameTime)
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    if (simParams.numSubsteps <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "numSubsteps must be positive");
+    if (simParams.interleavedHash <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "interleavedHash must be positive");
+    if (simParams.numParticles == 0) {
+        m_lastLaunches = 0;
+        return;
+    }
+    bool fused = (m_pipeline == VELVET_PIPELINE_FUSED);
+    if (fused) {
+        ensureFusedResources();
+        if (!m_fusedUsable || sdfColliders.size() > VT_MAX_COLLIDERS) fused = false;
+    }
+    if (!fused) {
+        simulateSeam(frameTime, nullptr);
+        return;
+    }
+
+    FrameParams hp;
+    hp.P = simParams;
+    hp.frameTime = frameTime;
+    hp.substepTime = frameTime / (float)simParams.numSubsteps;
+    hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
+    hp.numColliders = (uint)sdfColliders.size();
+    VT_CUDA(cudaMemcpyAsync(m_frameParams.data(), &hp, sizeof(hp), cudaMemcpyHostToDevice, m_stream));
+
+    const unsigned long long key = topologyKey();
+    if (!m_graphExec || key != m_graphKey) {
+        if (m_graphExec) {
+            cudaGraphExecDestroy(m_graphExec);
+            m_graphExec = nullptr;
+        }
+        if (m_graph) {
+            cudaGraphDestroy(m_graph);
+            m_graph = nullptr;
+        }
+        VT_CUDA(cudaStreamBeginCapture(m_stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            recordFusedFrame(nullptr);
+        } catch (...) {
+            cudaGraph_t broken = nullptr;
+            cudaStreamEndCapture(m_stream, &broken);
+            if (broken) cudaGraphDestroy(broken);
+            throw;
+        }
+        VT_CUDA(cudaStreamEndCapture(m_stream, &m_graph));
+        VT_CUDA(cudaGraphInstantiate(&m_graphExec, m_graph, 0));
+        m_graphKey = key;
+    }
+    VT_CUDA(cudaGraphLaunch(m_graphExec, m_stream));
+    m_lastLaunches = m_graphLaunches;
+}
+
+StageTiming VtClothSolverGPU::SimulateTimed()
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    Stage timing(m_stream);
+    if (simParams.numParticles == 0) return StageTiming{};
+    bool fused = (m_pipeline == VELVET_PIPELINE_FUSED);
+    if (fused) {
+        ensureFusedResources();
+        if (!m_fusedUsable || sdfColliders.size() > VT_MAX_COLLIDERS) fused = false;
+    }
+    timing.begin("Solver_Total");
+    if (!fused) {
+        simulateSeam(kFixedDeltaTime, &timing);
+    } else {
+        FrameParams hp;
+        hp.P = simParams;
+        hp.frameTime = kFixedDeltaTime;
+        hp.substepTime = kFixedDeltaTime / (float)simParams.numSubsteps;
+        hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
+        hp.numColliders = (uint)sdfColliders.size();
+        VT_CUDA(cudaMemcpyAsync(m_frameParams.data(), &hp, sizeof(hp), cudaMemcpyHostToDevice, m_stream));
+        recordFusedFrame(&timing);
+        m_lastLaunches = m_graphLaunches;
+    }
+    // close Solver_Total (it is the first span)
+    VT_CUDA(cudaEventRecord(timing.spans.front().b, m_stream));
+    return timing.collect();
+}
+
+// ------------------------------------------------------------------------------------------------ inputs
+
+// Scene.hpp L131-168
+void GenerateClothMesh(int resolution, float* vertices, uint* meshIndices)
+{
+    const float clothSize = 2.0f;
+    const float r = (float)resolution;
+    float* v = vertices;
+    for (int y = 0; y <= resolution; y++)
+        for (int x = 0; x <= resolution; x++) {
+            *v++ = clothSize * ((float)x / r - 0.5f);
+            *v++ = clothSize * (-(float)y / r);
+            *v++ = clothSize * 0.0f;
+        }
+    const uint side = (uint)resolution + 1;
+    auto at = [side](uint x, uint y) { return x * side + y; };
+    uint* o = meshIndices;
+    for (uint x = 0; x < (uint)resolution; x++)
+        for (uint y = 0; y < (uint)resolution; y++) {
+            const uint quad[6] = {at(x, y), at(x + 1, y), at(x, y + 1), at(x, y + 1), at(x + 1, y), at(x + 1, y + 1)};
+            std::memcpy(o, quad, sizeof(quad));
+            o += 6;
+        }
+}
+
+namespace {
+
+struct Mat4 {
+    float c[4][4];  // c[col][row]
+};
+
+Mat4 identity4()
+{
+    Mat4 m{};
+    for (int i = 0; i < 4; i++) m.c[i][i] = 1.0f;
+    return m;
+}
+
+// glm::rotate(m, angle, unit axis): rotation block first, then m * R column by column (left-to-right sums)
+Mat4 rotated(const Mat4& m, float angle, float ax, float ay, float az)
+{
+    const float c = std::cos(angle), s = std::sin(angle);
+    const float axis[3] = {ax, ay, az};
+    const float temp[3] = {(1.0f - c) * ax, (1.0f - c) * ay, (1.0f - c) * az};
+    float R[3][3];
+    R[0][0] = c + temp[0] * axis[0];
+    R[0][1] = temp[0] * axis[1] + s * axis[2];
+    R[0][2] = temp[0] * axis[2] - s * axis[1];
+    R[1][0] = temp[1] * axis[0] - s * axis[2];
+    R[1][1] = c + temp[1] * axis[1];
+    R[1][2] = temp[1] * axis[2] + s * axis[0];
+    R[2][0] = temp[2] * axis[0] + s * axis[1];
+    R[2][1] = temp[2] * axis[1] - s * axis[0];
+    R[2][2] = c + temp[2] * axis[2];
+    Mat4 out = m;
+    for (int col = 0; col < 3; col++)
+        for (int row = 0; row < 4; row++)
+            out.c[col][row] = (m.c[0][row] * R[col][0] + m.c[1][row] * R[col][1]) + m.c[2][row] * R[col][2];
+    return out;
+}
+
+}  // namespace
+
+// Transform::matrix(): translate, RotateWithDegree (y, z, x), scale -- Transform.hpp L22-29, Helper.cpp L8-15
+void TransformMatrix(const float* position3, const float* rotationDeg3, const float* scale3, float* out16)
+{
+    Mat4 m = identity4();
+    for (int row = 0; row < 4; row++)  // glm::translate: m[3] = m[0]*v.x + m[1]*v.y + m[2]*v.z + m[3]
+        m.c[3][row] = ((m.c[0][row] * position3[0] + m.c[1][row] * position3[1]) + m.c[2][row] * position3[2]) + m.c[3][row];
+    const float toRad = 0.01745329251994329576923690768489f;  // glm::radians
+    m = rotated(m, rotationDeg3[1] * toRad, 0, 1, 0);
+    m = rotated(m, rotationDeg3[2] * toRad, 0, 0, 1);
+    m = rotated(m, rotationDeg3[0] * toRad, 1, 0, 0);
+    for (int col = 0; col < 3; col++)
+        for (int row = 0; row < 4; row++) m.c[col][row] *= scale3[col];
+    std::memcpy(out16, m.c, sizeof(float) * 16);
+}
+
+// glm::inverse(mat4): the cofactor expansion published in glm/detail/func_matrix.inl
+void Mat4Inverse(const float* in16, float* out16)
+{
+    float m[4][4];
+    std::memcpy(m, in16, sizeof(m));  // m[col][row]
+    const float Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3];
+    const float Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
+    const float Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+    const float Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
+    const float Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3];
+    const float Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    const float Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2];
+    const float Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2];
+    const float Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    const float Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
+    const float Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3];
+    const float Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    const float Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2];
+    const float Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2];
+    const float Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+    const float Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+    const float Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1];
+    const float Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+
+    const float Fac0[4] = {Coef00, Coef00, Coef02, Coef03};
+    const float Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+    const float Fac2[4] = {Coef08, Coef08, Coef10, Coef11};
+    const float Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+    const float Fac4[4] = {Coef16, Coef16, Coef18, Coef19};
+    const float Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+    const float Vec0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]};
+    const float Vec1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+    const float Vec2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]};
+    const float Vec3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+    const float SignA[4] = {+1, -1, +1, -1};
+    const float SignB[4] = {-1, +1, -1, +1};
+    float inv[4][4];
+    for (int k = 0; k < 4; k++) {
+        inv[0][k] = ((Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k]) * SignA[k];
+        inv[1][k] = ((Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k]) * SignB[k];
+        inv[2][k] = ((Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k]) * SignA[k];
+        inv[3][k] = ((Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k]) * SignB[k];
+    }
+    const float Dot0[4] = {m[0][0] * inv[0][0], m[0][1] * inv[1][0], m[0][2] * inv[2][0], m[0][3] * inv[3][0]};
+    const float Dot1 = (Dot0[0] + Dot0[1]) + (Dot0[2] + Dot0[3]);
+    const float OneOverDeterminant = 1.0f / Dot1;
+    for (int col = 0; col < 4; col++)
+        for (int row = 0; row < 4; row++) out16[4 * col + row] = inv[col][row] * OneOverDeterminant;
+}
+
+// UpdateColliders body for one collider, VtClothSolverGPU.hpp L195-203
+void MakeCollider(int type, const float* position3, const float* scale3, const float* cur16, const float* last16,
+                  float deltaTime, VtSDFCollider* out)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->type = type;
+    std::memcpy(out->position, position3, 12);
+    std::memcpy(out->scale, scale3, 12);
+    out->deltaTime = deltaTime;
+    for (int col = 0; col < 3; col++)
+        for (int row = 0; row < 3; row++) out->curTransform[3 * col + row] = cur16[4 * col + row];
+    Mat4Inverse(cur16, out->invCurTransform);
+    std::memcpy(out->lastTransform, last16, 64);
+}
+
+// ------------------------------------------------------------------------------------------------ VtClothObjectGPU
+
+void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, const float* M)
+{
+    const int R = m_resolution;
+    const int side = R + 1;
+    const size_t nv = (size_t)side * side;
+    const size_t ni = (size_t)6 * R * R;
+    auto vtx = [&](size_t i) { return load3(vertices, i); };
+    m_particleDiameter = length(vtx(0) - vtx(1)) * m_solver->simParams.particleDiameterScalar;  // L49
+    m_indexOffset = m_solver->AddCloth(vertices, (int)nv, meshIndices, (int)ni, M, m_particleDiameter);
+    const int off = m_indexOffset;
+
+    // ApplyTransform (L67-73): host copy of the world-space positions, used for rest lengths only
+    std::vector<vec3> world(nv);
+    for (size_t i = 0; i < nv; i++) world[i] = mul_point(M, vtx(i), 1.0f);
+    auto dist = [&](int a, int b) { return length(world[(size_t)a] - world[(size_t)b]); };
+    auto at = [side](int x, int y) { return x * side + y; };
+
+    // GenerateStretch (L75-116): structural (y, x) then the two shear diagonals, in that emission order
+    std::vector<int> sIdx;
+    std::vector<float> sLen;
+    sIdx.reserve(2 * (size_t)(4 * R * R + 2 * R));
+    sLen.reserve((size_t)(4 * R * R + 2 * R));
+    auto emit = [&](int a, int b) {
+        sIdx.push_back(off + a);
+        sIdx.push_back(off + b);
+        sLen.push_back(dist(a, b));
+    };
+    for (int x = 0; x < side; x++)
+        for (int y = 0; y < side; y++) {
+            if (y != R) emit(at(x, y), at(x, y + 1));
+            if (x != R) emit(at(x, y), at(x + 1, y));
+            if (y != R && x != R) {
+                emit(at(x, y), at(x + 1, y + 1));
+                emit(at(x, y + 1), at(x + 1, y));
+            }
+        }
+    m_solver->AddStretchBulk(sIdx.data(), sLen.data(), sLen.size());
+
+    // GenerateAttach (L134-148): every particle gets a long-range attachment to every slot
+    for (size_t slot = 0; slot < m_attachedIndices.size(); slot++) {
+        const vec3 slotPos = world[(size_t)m_attachedIndices[slot]];
+        const float sp[3] = {slotPos.x, slotPos.y, slotPos.z};
+        m_solver->AddAttachSlot(sp);
+        std::vector<int> pid(nv), sid(nv, (int)slot);
+        std::vector<float> d(nv);
+        for (size_t i = 0; i < nv; i++) {
+            pid[i] = off + (int)i;
+            d[i] = length(slotPos - world[i]);
+        }
+        m_solver->AddAttachBulk(pid.data(), sid.data(), d.data(), nv);
+    }
+
+    // GenerateBending (L118-132): one dihedral per quad, indices (i, i+5, i+2, i+1), rest angle 0
+    std::vector<uint> bIdx;
+    std::vector<float> bAng;
+    bIdx.reserve(4 * (size_t)R * R);
+    bAng.reserve((size_t)R * R);
+    for (size_t i = 0; i + 5 < ni; i += 6) {
+        bIdx.push_back((uint)off + meshIndices[i]);
+        bIdx.push_back((uint)off + meshIndices[i + 5]);
+        bIdx.push_back((uint)off + meshIndices[i + 2]);
+        bIdx.push_back((uint)off + meshIndices[i + 1]);
+        bAng.push_back(0.0f);
+    }
+    m_solver->AddBendBulk(bIdx.data(), bAng.data(), bAng.size());
+}
+
+}  // namespace velvet

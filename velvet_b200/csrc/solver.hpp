@@ -1,0 +1,191 @@
+// solver.hpp -- headless C++17 mirror of the reference's host classes for the hot path:
+//   velvet::SpatialHashGPU     <-> Velvet::SpatialHashGPU     (SpatialHashGPU.hpp L15-60)
+//   velvet::VtClothSolverGPU   <-> Velvet::VtClothSolverGPU   (VtClothSolverGPU.hpp L23-231)
+//   velvet::VtClothObjectGPU   <-> Velvet::VtClothObjectGPU   (VtClothObjectGPU.hpp L12-149, constraint generation)
+// Same member names, argument meaning and buffer layouts; no GL, no ECS, no globals: each solver owns its
+// VtSimParams (the reference's process-global Global::simParams), its CUDA stream and its device.
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fused_kernels.cuh"
+#include "radix_sort.cuh"
+#include "seam.hpp"
+#include "tile_plan.hpp"
+#include "vt_buffer.hpp"
+
+namespace velvet {
+
+using uint = unsigned int;
+
+void default_sim_params(VtSimParams& p);  // Common.hpp L21-46
+constexpr float kFixedDeltaTime = 1.0f / 60.0f;  // Timer.hpp L235
+
+class SpatialHashGPU {
+public:
+    // SpatialHashGPU.hpp L18-28 (hashCellSizeScalar / maxNumNeighbors come from Global::simParams there)
+    SpatialHashGPU(float particleDiameter, int maxNumObjects, float hashCellSizeScalar, int maxNumNeighbors);
+
+    // L32-39: snapshot of `count` packed float3 positions (device-accessible or host pointer)
+    void SetInitialPositions(const float* positions, size_t count);
+    // L41-52: runs the seam HashObjects on `count` packed float3 positions
+    void Hash(const float* positions, size_t count, float particleDiameter, cudaStream_t stream);
+    VtHashParams MakeParams(size_t count, float particleDiameter) const;
+
+    VtBuffer<uint> neighbors;
+    VtBuffer<vec3> initialPositions;
+    VtBuffer<uint> particleHash;
+    VtBuffer<uint> particleIndex;
+    VtBuffer<uint> cellStart;
+    VtBuffer<uint> cellEnd;
+
+    float spacing() const { return m_spacing; }
+    int tableSize() const { return m_tableSize; }
+    int maxNumNeighbors() const { return m_maxNumNeighbors; }
+
+    // debug helpers of the reference (L63-90), host side
+    int ComputeIntCoord(float value) const;
+    int HashCoords(int x, int y, int z) const;
+    int HashPosition(const float* p3) const;
+
+private:
+    float m_spacing;
+    int m_tableSize;
+    int m_maxNumNeighbors;
+};
+
+struct StageTiming {
+    std::vector<std::string> labels;
+    std::vector<float> ms;
+};
+
+class VtClothSolverGPU {
+public:
+    explicit VtClothSolverGPU(int device = -1, const VtSimParams* params = nullptr);
+    ~VtClothSolverGPU();
+    VtClothSolverGPU(const VtClothSolverGPU&) = delete;
+    VtClothSolverGPU& operator=(const VtClothSolverGPU&) = delete;
+
+    // ---- reference surface
+    void Simulate();                 // hpp L56-111, frame time = 1/60
+    void Simulate(float frameTime);  // overload named by the spec
+    int AddCloth(const float* vertices, int numVertices, const uint* meshIndices, int numIndices,
+                 const float* modelMatrix16, float particleDiameter);                   // L114-156
+    void AddStretch(int idx1, int idx2, float distance);                               // L158-163
+    void AddAttachSlot(const float* attachSlotPos3);                                   // L165-168
+    void AddAttach(int particleIndex, int slotIndex, float distance);                  // L170-176
+    void AddBend(uint idx1, uint idx2, uint idx3, uint idx4, float angle);             // L178-185
+    void UpdateColliders(const VtSDFCollider* colliders, int numColliders);            // L187-205
+    void Synchronize();
+    void OnDestroy();  // L50-54
+
+    // bulk variants (one memcpy instead of a managed-memory push_back per element)
+    void AddStretchBulk(const int* idxPairs, const float* distances, size_t n);
+    void AddBendBulk(const uint* idxQuads, const float* angles, size_t n);
+    void AddAttachBulk(const int* particleIds, const int* slotIds, const float* distances, size_t n);
+
+    // per-stage timing of one frame, labels as in GUI.cpp L32-51 (runs the frame un-graphed)
+    StageTiming SimulateTimed();
+
+    VtSimParams simParams;  // Global::simParams of this solver
+
+    // ---- public sim buffers, names as VtClothSolverGPU.hpp L209-231
+    VtMergedBuffer<vec3> positions;
+    VtMergedBuffer<vec3> normals;
+    VtBuffer<uint> indices;
+    VtBuffer<vec3> velocities;
+    VtBuffer<vec3> predicted;
+    VtBuffer<vec3> deltas;
+    VtBuffer<int> deltaCounts;
+    VtBuffer<float> invMasses;
+    VtBuffer<int> stretchIndices;
+    VtBuffer<float> stretchLengths;
+    VtBuffer<uint> bendIndices;
+    VtBuffer<float> bendAngles;
+    VtBuffer<int> attachParticleIDs;
+    VtBuffer<int> attachSlotIDs;
+    VtBuffer<float> attachDistances;
+    VtBuffer<vec3> attachSlotPositions;
+    VtBuffer<VtSDFCollider> sdfColliders;
+
+    std::shared_ptr<SpatialHashGPU> spatialHash() const { return m_spatialHash; }
+
+    // ---- new controls
+    void setPipeline(int pipeline);
+    int pipeline() const { return m_pipeline; }
+    void setTileSize(int particlesPerTile);
+    cudaStream_t stream() const { return m_stream; }
+    int device() const { return m_device; }
+    int lastLaunchCount() const { return m_lastLaunches; }
+    const TilePlan& tilePlan() const { return m_plan; }
+    const std::string& fusedFallbackReason() const { return m_fallbackReason; }
+
+private:
+    struct Stage;  // timing helper
+    void simulateSeam(float frameTime, Stage* timing);
+    void recordFusedFrame(Stage* timing);
+    void ensureFusedResources();
+    void invalidate() { m_topologyDirty = true; }
+    unsigned long long topologyKey() const;
+
+    int m_device = 0;
+    cudaStream_t m_stream = nullptr;
+    int m_pipeline = 0;
+    int m_tileSize = 0;
+    int m_lastLaunches = 0;
+    std::shared_ptr<SpatialHashGPU> m_spatialHash;
+
+    // fused pipeline state
+    bool m_topologyDirty = true;
+    bool m_fusedUsable = false;
+    std::string m_fallbackReason;
+    unsigned long long m_graphKey = 0;
+    cudaGraph_t m_graph = nullptr;
+    cudaGraphExec_t m_graphExec = nullptr;
+    int m_graphLaunches = 0;
+
+    DeviceBuffer<float4> m_pos4, m_vel4, m_predA, m_predB, m_init4;
+    DeviceBuffer<uint> m_keysAlt, m_valsAlt;
+    DeviceBuffer<PreparedCollider> m_prepared;
+    DeviceBuffer<FrameParams> m_frameParams;
+    DeviceBuffer<uint> m_vtxTriOff, m_vtxTris;
+    DeviceBuffer<float> m_slotsDev;  // per-frame device copy of attachSlotPositions
+    RadixSorter m_sorter;
+    TilePlan m_plan;
+    TilePlanDev m_planDev{};
+    DeviceBuffer<TileDesc> m_dTiles;
+    DeviceBuffer<uint> m_dOwned, m_dHalo, m_dAttOff;
+    DeviceBuffer<uint16_t> m_dSBase, m_dBBase;
+    DeviceBuffer<uint2> m_dStretchRec, m_dAttachRec;
+    DeviceBuffer<uint4> m_dBendRec;
+};
+
+// Constraint generation of the reference's cloth component (VtClothObjectGPU.hpp L43-148) for grid meshes
+// produced by GenerateClothMesh (Scene.hpp L131-168).
+class VtClothObjectGPU {
+public:
+    VtClothObjectGPU(int resolution, VtClothSolverGPU* solver) : m_resolution(resolution), m_solver(solver) {}
+    void SetAttachedIndices(std::vector<int> indices) { m_attachedIndices = std::move(indices); }
+    float particleDiameter() const { return m_particleDiameter; }
+    int indexOffset() const { return m_indexOffset; }
+    // Start(): vertices in model space (host), mesh indices (host), model matrix
+    void Start(const float* vertices, const uint* meshIndices, const float* modelMatrix16);
+
+private:
+    int m_resolution;
+    int m_indexOffset = 0;
+    VtClothSolverGPU* m_solver;
+    std::vector<int> m_attachedIndices;
+    float m_particleDiameter = 0;
+};
+
+// Scene.hpp L131-168, Transform.hpp L22-29 (+ Helper.cpp L8-15), glm::inverse, VtClothSolverGPU.hpp L195-203
+void GenerateClothMesh(int resolution, float* vertices, uint* meshIndices);
+void TransformMatrix(const float* position3, const float* rotationDeg3, const float* scale3, float* out16);
+void Mat4Inverse(const float* m16, float* out16);
+void MakeCollider(int type, const float* position3, const float* scale3, const float* cur16, const float* last16,
+                  float deltaTime, VtSDFCollider* out);
+
+}  // namespace velvet

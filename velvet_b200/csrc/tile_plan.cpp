@@ -1,0 +1,241 @@
+// tile_plan.cpp -- see tile_plan.hpp.
+#include "tile_plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace velvet {
+
+namespace {
+
+inline uint64_t spread21(uint64_t v)
+{  // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+inline unsigned float_bits(float f)
+{
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+
+}  // namespace
+
+TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchIndices, const float* stretchLengths,
+                         size_t S, const unsigned* bendIndices, const float* bendAngles, size_t B,
+                         const int* attachParticleIDs, const int* attachSlotIDs, const float* attachDistances, size_t A,
+                         int tileSize)
+{
+    TilePlan plan;
+    plan.tileSize = tileSize;
+    auto fail = [&](const std::string& why) {
+        plan.valid = false;
+        plan.whyInvalid = why;
+        return plan;
+    };
+    if (N == 0) return fail("no particles");
+    if (tileSize < 32 || tileSize > 1024 || (tileSize % 32) != 0) return fail("tile size must be a multiple of 32 in [32,1024]");
+
+    // validate indices (the reference would read out of bounds; we refuse the fused plan instead)
+    for (size_t c = 0; c < S; c++)
+        if ((unsigned)stretchIndices[2 * c] >= N || (unsigned)stretchIndices[2 * c + 1] >= N) return fail("stretch index out of range");
+    for (size_t c = 0; c < 4 * B; c++)
+        if (bendIndices[c] >= N) return fail("bend index out of range");
+    for (size_t c = 0; c < A; c++)
+        if ((unsigned)attachParticleIDs[c] >= N) return fail("attach particle index out of range");
+
+    // ---- 1. spatial order: Morton code of the quantised positions, ties by particle id
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned i = 0; i < N; i++)
+        for (int k = 0; k < 3; k++) {
+            const float v = positions[3 * (size_t)i + k];
+            if (std::isfinite(v)) {
+                lo[k] = std::min(lo[k], v);
+                hi[k] = std::max(hi[k], v);
+            }
+        }
+    float extent = 0;
+    for (int k = 0; k < 3; k++)
+        if (hi[k] >= lo[k]) extent = std::max(extent, hi[k] - lo[k]);
+    const double scale = extent > 0 ? 2097151.0 / (double)extent : 0.0;
+    std::vector<std::pair<uint64_t, unsigned>> order(N);
+    for (unsigned i = 0; i < N; i++) {
+        uint64_t q[3];
+        for (int k = 0; k < 3; k++) {
+            const float v = positions[3 * (size_t)i + k];
+            double t = std::isfinite(v) ? ((double)v - (double)lo[k]) * scale : 0.0;
+            if (t < 0) t = 0;
+            if (t > 2097151.0) t = 2097151.0;
+            q[k] = (uint64_t)t;
+        }
+        order[i] = {spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2), i};
+    }
+    std::sort(order.begin(), order.end());
+
+    const unsigned T = (unsigned)tileSize;
+    const unsigned numTiles = (N + T - 1) / T;
+    std::vector<unsigned> tileOf(N);
+    plan.ownedIds.resize(N);
+    for (unsigned r = 0; r < N; r++) {
+        tileOf[order[r].second] = r / T;
+        plan.ownedIds[r] = order[r].second;
+    }
+    order.clear();
+    order.shrink_to_fit();
+    for (unsigned t = 0; t < numTiles; t++) {
+        const unsigned b = t * T, e = std::min(N, b + T);
+        std::sort(plan.ownedIds.begin() + b, plan.ownedIds.begin() + e);  // ascending ids => coalesced loads
+    }
+    std::vector<unsigned> localOf(N);
+    for (unsigned r = 0; r < N; r++) localOf[plan.ownedIds[r]] = r % T;
+
+    // ---- 2. per-tile constraint lists (CSR, ascending constraint id inside each tile)
+    auto distinct_tiles = [&](const unsigned* ids, int n, unsigned* out) {
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            const unsigned t = tileOf[ids[i]];
+            bool seen = false;
+            for (int j = 0; j < m; j++) seen |= (out[j] == t);
+            if (!seen) out[m++] = t;
+        }
+        return m;
+    };
+    std::vector<size_t> sOff(numTiles + 1, 0), bOff(numTiles + 1, 0), aOff(numTiles + 1, 0);
+    unsigned tl[4];
+    for (size_t c = 0; c < S; c++) {
+        const unsigned ids[2] = {(unsigned)stretchIndices[2 * c], (unsigned)stretchIndices[2 * c + 1]};
+        const int m = distinct_tiles(ids, 2, tl);
+        for (int j = 0; j < m; j++) sOff[tl[j] + 1]++;
+    }
+    for (size_t c = 0; c < B; c++) {
+        const int m = distinct_tiles(bendIndices + 4 * c, 4, tl);
+        for (int j = 0; j < m; j++) bOff[tl[j] + 1]++;
+    }
+    for (size_t c = 0; c < A; c++) aOff[tileOf[(unsigned)attachParticleIDs[c]] + 1]++;
+    for (unsigned t = 0; t < numTiles; t++) {
+        sOff[t + 1] += sOff[t];
+        bOff[t + 1] += bOff[t];
+        aOff[t + 1] += aOff[t];
+    }
+    std::vector<unsigned> sList(sOff[numTiles]), bList(bOff[numTiles]), aList(aOff[numTiles]);
+    {
+        std::vector<size_t> sc(sOff.begin(), sOff.end() - 1), bc(bOff.begin(), bOff.end() - 1), ac(aOff.begin(), aOff.end() - 1);
+        for (size_t c = 0; c < S; c++) {
+            const unsigned ids[2] = {(unsigned)stretchIndices[2 * c], (unsigned)stretchIndices[2 * c + 1]};
+            const int m = distinct_tiles(ids, 2, tl);
+            for (int j = 0; j < m; j++) sList[sc[tl[j]]++] = (unsigned)c;
+        }
+        for (size_t c = 0; c < B; c++) {
+            const int m = distinct_tiles(bendIndices + 4 * c, 4, tl);
+            for (int j = 0; j < m; j++) bList[bc[tl[j]]++] = (unsigned)c;
+        }
+        for (size_t c = 0; c < A; c++) aList[ac[tileOf[(unsigned)attachParticleIDs[c]]]++] = (unsigned)c;
+    }
+
+    // ---- 3. per tile: halo discovery, slot ordinals, records
+    plan.tiles.resize(numTiles);
+    plan.stretchRec.resize(sList.size());
+    plan.bendRec.resize(bList.size());
+    plan.attachRec.resize(aList.size());
+    plan.sBase.resize((size_t)N + numTiles);
+    plan.bBase.resize((size_t)N + numTiles);
+    plan.attOff.resize((size_t)N + numTiles);
+    plan.haloIds.clear();
+    std::vector<unsigned> haloStamp(N, 0xffffffffu), haloLocal(N);
+    std::vector<unsigned> cntS(T), cntB(T), cntA(T);
+
+    for (unsigned t = 0; t < numTiles; t++) {
+        TileDesc& td = plan.tiles[t];
+        td.ownedOff = t * T;
+        td.nOwned = std::min(N, td.ownedOff + T) - td.ownedOff;
+        td.haloOff = (unsigned)plan.haloIds.size();
+        td.nHalo = 0;
+        td.stretchOff = (unsigned)sOff[t];
+        td.nStretch = (unsigned)(sOff[t + 1] - sOff[t]);
+        td.bendOff = (unsigned)bOff[t];
+        td.nBend = (unsigned)(bOff[t + 1] - bOff[t]);
+        td.attachOff = (unsigned)aOff[t];
+        td.nAttach = (unsigned)(aOff[t + 1] - aOff[t]);
+        td.baseOff = td.ownedOff + t;
+        td.pad = 0;
+        std::fill(cntS.begin(), cntS.end(), 0u);
+        std::fill(cntB.begin(), cntB.end(), 0u);
+        std::fill(cntA.begin(), cntA.end(), 0u);
+
+        bool overflow = false;
+        auto endpoint = [&](unsigned p, std::vector<unsigned>& cnt) -> unsigned {
+            if (tileOf[p] == t) {
+                const unsigned l = localOf[p];
+                const unsigned k = cnt[l]++;
+                if (k >= TP_NO_SLOT) overflow = true;
+                return (l << TP_ORD_BITS) | (k & 31u);
+            }
+            if (haloStamp[p] != t) {
+                haloStamp[p] = t;
+                haloLocal[p] = td.nOwned + td.nHalo++;
+                plan.haloIds.push_back(p);
+            }
+            return (haloLocal[p] << TP_ORD_BITS) | TP_NO_SLOT;
+        };
+
+        for (unsigned i = 0; i < td.nStretch; i++) {
+            const unsigned c = sList[td.stretchOff + i];
+            const unsigned ea = endpoint((unsigned)stretchIndices[2 * (size_t)c], cntS);
+            const unsigned eb = endpoint((unsigned)stretchIndices[2 * (size_t)c + 1], cntS);
+            plan.stretchRec[td.stretchOff + i] = Rec2{ea | (eb << 16), float_bits(stretchLengths[c])};
+        }
+        for (unsigned i = 0; i < td.nBend; i++) {
+            const unsigned c = bList[td.bendOff + i];
+            unsigned e[4];
+            for (int k = 0; k < 4; k++) e[k] = endpoint(bendIndices[4 * (size_t)c + k], cntB);
+            plan.bendRec[td.bendOff + i] = Rec4{e[0] | (e[1] << 16), e[2] | (e[3] << 16), float_bits(bendAngles[c]), c};
+        }
+        if (overflow) return fail("a particle has more than 30 stretch or bend constraints");
+        if (td.nOwned + td.nHalo > TP_MAX_LOCALS) return fail("tile halo too large (more than 2047 local particles)");
+
+        // slot bases
+        unsigned accS = 0, accB = 0;
+        for (unsigned l = 0; l < td.nOwned; l++) {
+            plan.sBase[td.baseOff + l] = (uint16_t)accS;
+            plan.bBase[td.baseOff + l] = (uint16_t)accB;
+            accS += cntS[l];
+            accB += cntB[l];
+        }
+        if (accS > 65535u || accB > 65535u) return fail("too many slots in a tile");
+        plan.sBase[td.baseOff + td.nOwned] = (uint16_t)accS;
+        plan.bBase[td.baseOff + td.nOwned] = (uint16_t)accB;
+        plan.maxSlots = std::max(plan.maxSlots, std::max(accS, accB));
+        plan.maxLocals = std::max(plan.maxLocals, td.nOwned + td.nHalo);
+
+        // attach: CSR by owned particle, ascending constraint id inside each particle
+        for (unsigned i = 0; i < td.nAttach; i++) cntA[localOf[(unsigned)attachParticleIDs[aList[td.attachOff + i]]]]++;
+        unsigned accA = 0;
+        for (unsigned l = 0; l < td.nOwned; l++) {
+            plan.attOff[td.baseOff + l] = accA;
+            accA += cntA[l];
+            cntA[l] = plan.attOff[td.baseOff + l];
+        }
+        plan.attOff[td.baseOff + td.nOwned] = accA;
+        for (unsigned i = 0; i < td.nAttach; i++) {
+            const unsigned c = aList[td.attachOff + i];
+            const unsigned l = localOf[(unsigned)attachParticleIDs[c]];
+            plan.attachRec[td.attachOff + cntA[l]++] = Rec2{(unsigned)attachSlotIDs[c], float_bits(attachDistances[c])};
+        }
+    }
+    plan.numStretchEvaluated = sList.size();
+    plan.numBendEvaluated = bList.size();
+    plan.numHalo = plan.haloIds.size();
+    if (plan.haloIds.empty()) plan.haloIds.push_back(0);  // keep device arrays non-empty
+    plan.valid = true;
+    return plan;
+}
+
+}  // namespace velvet

@@ -1,0 +1,66 @@
+// tile_plan.hpp -- host preprocessing for the tile-fused Jacobi iteration kernel.
+//
+// The reference runs one kernel per constraint type and scatters every correction with 3 float + 1 int
+// global atomics (VtClothSolverGPU.cu L65-251), then a fourth kernel averages (L253-264).  Here particles are
+// partitioned into spatially compact tiles (Morton order of the registration-time positions); every
+// constraint is assigned to the tile(s) owning one of its particles; inside a tile each (constraint,
+// endpoint) pair gets a private shared-memory slot and each particle sums its slots in ascending
+// constraint-id order (stretch, then attach, then bend).  That order is exactly the sequential order of
+// the CPU oracle, so the result is deterministic and, up to libm, bit-identical to it.
+//
+// Constraints that straddle tiles are evaluated by each owning tile (same inputs, same code, same bits);
+// only owned endpoints receive a slot.  Particles referenced but not owned form the tile's halo.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace velvet {
+
+struct TileDesc {
+    unsigned ownedOff, nOwned;      // range in ownedIds
+    unsigned haloOff, nHalo;        // range in haloIds
+    unsigned stretchOff, nStretch;  // range in stretchRec
+    unsigned bendOff, nBend;        // range in bendRec
+    unsigned baseOff;               // first of nOwned+1 entries in sBase / bBase / attOff
+    unsigned attachOff, nAttach;    // range in attachRec
+    unsigned pad;
+};
+
+struct Rec2 {
+    unsigned x, y;
+};
+struct Rec4 {
+    unsigned x, y, z, w;
+};
+
+// endpoint encoding inside a record: (localIndex << 5) | slotOrdinal, slotOrdinal 31 = halo (no slot)
+constexpr unsigned TP_ORD_BITS = 5;
+constexpr unsigned TP_NO_SLOT = 31;
+constexpr unsigned TP_MAX_LOCALS = 2047;
+
+struct TilePlan {
+    bool valid = false;
+    std::string whyInvalid;
+    int tileSize = 0;
+    std::vector<TileDesc> tiles;
+    std::vector<unsigned> ownedIds, haloIds;
+    std::vector<uint16_t> sBase, bBase;  // slot bases per owned particle (+1 terminator per tile)
+    std::vector<unsigned> attOff;        // attach CSR per owned particle (+1 per tile), relative to attachOff
+    std::vector<Rec2> stretchRec;        // {ea | eb << 16, restLength bits}
+    std::vector<Rec4> bendRec;           // {e0 | e1 << 16, e2 | e3 << 16, restAngle bits, constraint id}
+    std::vector<Rec2> attachRec;         // {slot id, distance bits}
+    unsigned maxLocals = 0;              // max over tiles of nOwned + nHalo
+    unsigned maxSlots = 0;               // max over tiles of max(stretch slots, bend slots)
+    // statistics
+    size_t numStretchEvaluated = 0, numBendEvaluated = 0, numHalo = 0;
+};
+
+// positions: packed float3 (host) used only to order particles spatially.
+TilePlan build_tile_plan(unsigned numParticles, const float* positions, const int* stretchIndices,
+                         const float* stretchLengths, size_t numStretch, const unsigned* bendIndices,
+                         const float* bendAngles, size_t numBend, const int* attachParticleIDs,
+                         const int* attachSlotIDs, const float* attachDistances, size_t numAttach, int tileSize);
+
+}  // namespace velvet

@@ -1,0 +1,201 @@
+// vt_buffer.hpp -- VtBuffer<T> / VtMergedBuffer<T> (reference: VtBuffer.hpp L7-236, Common.cuh L66-78)
+// plus DeviceBuffer<T>, the plain-cudaMalloc scratch used by the fused pipeline.
+//
+// VtBuffer keeps the reference's contract: a growable array in *managed* memory (so callers may index it
+// on the host between frames), implicit conversion to T*, push_back / resize / reserve with 1.5x growth,
+// destroy().  Differences: errors throw velvet::Error instead of exit(); bulk append is one memcpy; a
+// `generation()` counter tells the solver when a pointer changed so it can re-capture its CUDA graph.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cassert>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace velvet {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string& msg) : std::runtime_error(msg), status(st) {}
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e != cudaSuccess) {
+        throw Error(-2, std::string(what) + " failed: " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")");
+    }
+}
+#define VT_CUDA(expr) ::velvet::cuda_check((expr), #expr, __FILE__, __LINE__)
+
+template <class T>
+class VtBuffer {
+public:
+    VtBuffer() = default;
+    explicit VtBuffer(size_t size) { resize(size); }
+    VtBuffer(const VtBuffer&) = delete;
+    VtBuffer& operator=(const VtBuffer&) = delete;
+    ~VtBuffer()
+    {
+        try { destroy(); } catch (...) {}
+    }
+
+    operator T*() const { return m_data; }
+    T* data() const { return m_data; }
+    size_t size() const { return m_count; }
+    size_t capacity() const { return m_capacity; }
+    unsigned generation() const { return m_generation; }
+
+    T& operator[](size_t index)
+    {
+        assert(m_data && index < m_count);
+        return m_data[index];
+    }
+
+    void push_back(const T& t)
+    {
+        reserve(m_count + 1);
+        m_data[m_count++] = t;
+    }
+    void push_back(size_t newCount, const T& val)
+    {
+        reserve(m_count + newCount);
+        for (size_t i = 0; i < newCount; i++) m_data[m_count++] = val;
+    }
+    void push_back(const std::vector<T>& data) { append(data.data(), data.size()); }
+    void append(const T* src, size_t n)
+    {
+        if (!n) return;
+        reserve(m_count + n);
+        std::memcpy(m_data + m_count, src, n * sizeof(T));
+        m_count += n;
+    }
+
+    void reserve(size_t minCapacity)
+    {
+        if (minCapacity <= m_capacity) return;
+        const size_t newCapacity = minCapacity * 3 / 2;  // growth factor of the reference
+        T* fresh = nullptr;
+        VT_CUDA(cudaMallocManaged((void**)&fresh, newCapacity * sizeof(T)));
+        if (m_data) {
+            // the GPU may still be reading the old block (async frames): drain before the host touches it
+            VT_CUDA(cudaDeviceSynchronize());
+            std::memcpy(fresh, m_data, m_count * sizeof(T));
+            VT_CUDA(cudaFree(m_data));
+        }
+        m_data = fresh;
+        m_capacity = newCapacity;
+        m_generation++;
+    }
+    void resize(size_t newCount)
+    {
+        reserve(newCount);
+        m_count = newCount;
+    }
+    void resize(size_t newCount, const T& val)
+    {
+        const size_t first = m_count;
+        resize(newCount);
+        for (size_t i = first; i < newCount; i++) m_data[i] = val;
+    }
+    void destroy()
+    {
+        if (m_data) {
+            cudaDeviceSynchronize();
+            cudaFree(m_data);
+            m_generation++;
+        }
+        m_data = nullptr;
+        m_count = m_capacity = 0;
+    }
+
+private:
+    size_t m_count = 0;
+    size_t m_capacity = 0;
+    T* m_data = nullptr;
+    unsigned m_generation = 0;
+};
+
+// Headless VtMergedBuffer: one managed array holding every cloth's range.  The reference mirrors each range
+// into a GL VBO (registerNewBuffer(GLuint) / sync(), VtBuffer.hpp L202-229); headless callers register host
+// data instead and read results back with cudaMemcpy (velvet_solver_download / readback_async).
+template <class T>
+class VtMergedBuffer {
+public:
+    VtMergedBuffer() = default;
+    VtMergedBuffer(const VtMergedBuffer&) = delete;
+    VtMergedBuffer& operator=(const VtMergedBuffer&) = delete;
+
+    // Appends `count` elements (copied from host `src`, or zero when src == nullptr); returns the offset.
+    size_t registerNewBuffer(const T* src, size_t count)
+    {
+        const size_t offset = m_vbuffer.size();
+        m_offsets.push_back(offset);
+        m_counts.push_back(count);
+        m_vbuffer.resize(offset + count);
+        if (src) std::memcpy(m_vbuffer.data() + offset, src, count * sizeof(T));
+        else std::memset((void*)(m_vbuffer.data() + offset), 0, count * sizeof(T));
+        return offset;
+    }
+    size_t size() const { return m_vbuffer.size(); }
+    size_t numRanges() const { return m_offsets.size(); }
+    size_t rangeOffset(size_t i) const { return m_offsets[i]; }
+    size_t rangeCount(size_t i) const { return m_counts[i]; }
+    void sync() {}  // GL mirrors only exist under VELVET_GL_INTEROP (not built headless)
+    void destroy()
+    {
+        m_vbuffer.destroy();
+        m_offsets.clear();
+        m_counts.clear();
+    }
+    operator T*() const { return m_vbuffer.data(); }
+    T* data() const { return m_vbuffer.data(); }
+    T& operator[](size_t i) { return m_vbuffer[i]; }
+    unsigned generation() const { return m_vbuffer.generation(); }
+
+private:
+    std::vector<size_t> m_offsets, m_counts;
+    VtBuffer<T> m_vbuffer;
+};
+
+// Plain device scratch (never touched by the host).
+template <class T>
+class DeviceBuffer {
+public:
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer() { release(); }
+    void release()
+    {
+        if (m_data) cudaFree(m_data);
+        m_data = nullptr;
+        m_count = 0;
+    }
+    // (Re)allocates when the size changes; contents are undefined afterwards.
+    void allocate(size_t count)
+    {
+        if (count == m_count && m_data) return;
+        release();
+        if (count) VT_CUDA(cudaMalloc((void**)&m_data, count * sizeof(T)));
+        m_count = count;
+    }
+    void upload(const T* host, size_t count, cudaStream_t st = 0)
+    {
+        allocate(count);
+        if (count) VT_CUDA(cudaMemcpyAsync(m_data, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void upload(const std::vector<T>& v, cudaStream_t st = 0) { upload(v.data(), v.size(), st); }
+    T* data() const { return m_data; }
+    operator T*() const { return m_data; }
+    size_t size() const { return m_count; }
+    size_t bytes() const { return m_count * sizeof(T); }
+
+private:
+    T* m_data = nullptr;
+    size_t m_count = 0;
+};
+
+}  // namespace velvet
