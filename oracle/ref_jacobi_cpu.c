@@ -134,6 +134,51 @@ void o1_solve_stretch(float* predicted, float* deltas, int* deltaCounts, const i
     }
 }
 
+static inline int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+/* acos(float) of VtClothSolverGPU.cu L163.  The reference calls CUDA's acosf (<= 2 ulp, unspecified last bit);
+ * the oracle and the product both use the published fdlibm e_acosf.c algorithm (< 1 ulp, only + - * / sqrt) so
+ * that the bending constraint is bit-reproducible between CPU and GPU. */
+float o1_acosf(float x)
+{
+    const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f,
+                pio2_lo = 7.5497894159e-08f, pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f,
+                pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f, pS4 = 7.9153501429e-04f,
+                pS5 = 3.4793309169e-05f, qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f,
+                qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+    const int hx = f2i(x);
+    const int ix = hx & 0x7fffffff;
+    if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo;
+    if (ix > 0x3f800000) return (x - x) / (x - x);
+    if (ix < 0x3f000000) {
+        if (ix <= 0x23000000) return pio2_hi + pio2_lo;
+        const float z = x * x;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (hx < 0) {
+        const float z = (one + x) * 0.5f;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float s = sqrtf(z);
+        const float r = p / q;
+        const float w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    }
+    const float z = (one - x) * 0.5f;
+    const float s = sqrtf(z);
+    const float df = i2f(f2i(s) & (int)0xfffff000);
+    const float c = (z - df * df) / (s + df);
+    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float r = p / q;
+    const float w = r * s + c;
+    return 2.0f * (df + w);
+}
+
 /* VtClothSolverGPU.cu L117-189 */
 void o1_solve_bending(const O1SimParams* P, float* predicted, float* deltas, int* deltaCounts,
                       const uint32_t* bendIndices, const float* bendAngles, const float* invMass,
@@ -162,7 +207,7 @@ void o1_solve_bending(const O1SimParams* P, float* predicted, float* deltas, int
         n1 = normalize3(n1);
         n2 = normalize3(n2);
         float d = clampf(dot3(n1, n2), -1.0f, 1.0f);
-        float phi = acosf(d);
+        float phi = o1_acosf(d);
 
         float lambda = w0 * dot3(d0, d0) + w1 * dot3(d1, d1) + w2 * dot3(d2, d2) + w3 * dot3(d3, d3);
         if (lambda < O1_EPSILON) continue;

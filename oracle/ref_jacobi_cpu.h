@@ -98,6 +98,7 @@ void o1_hash_objects(uint32_t* particleHash, uint32_t* particleIndex, uint32_t* 
                      uint32_t* cellEnd, uint32_t* neighbors, const float* positions,
                      const float* originalPositions, O1HashParams hp);
 int o1_hash_position(const float* p3, float cellSpacing, int tableSize);
+float o1_acosf(float x);
 
 /* ---- host-side helpers (glm restatements) ---- */
 void o1_transform_matrix(const float* position3, const float* rotationDeg3, const float* scale3,

@@ -16,7 +16,7 @@ f = lambda a: a.ctypes.data_as(C.c_void_p)
 
 
 def dev(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return torch.from_numpy(np.array(a, copy=True)).cuda()
 
 
 def host(t):

@@ -164,6 +164,19 @@ def test_stretch_residual_decreases():
     assert residual() < 0.5 * r0
 
 
+def test_acosf_restatement_is_within_one_ulp():
+    # VtClothSolverGPU.cu L163 calls CUDA acosf (<= 2 ulp); oracle and product share the fdlibm algorithm (< 1 ulp)
+    L = o1.lib()
+    L.o1_acosf.restype = C.c_float
+    L.o1_acosf.argtypes = [C.c_float]
+    xs = np.concatenate([np.linspace(-1, 1, 20001), 1 - np.logspace(-8, 0, 500), -1 + np.logspace(-8, 0, 500)]).astype(np.float32)
+    got = np.array([L.o1_acosf(float(x)) for x in xs], np.float32).astype(np.float64)
+    ref = np.arccos(xs.astype(np.float64))
+    ulp = np.spacing(ref.astype(np.float32)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ulp) < 1.0
+    assert L.o1_acosf(1.0) == 0.0 and np.isnan(L.o1_acosf(float("nan")))
+
+
 def test_mat4_inverse_and_transform():
     M = o1.transform_matrix((0.3, 1.5, -1), (33, -20, 71), (1.5, 2, 0.7))
     inv = o1.mat4_inverse(M)
