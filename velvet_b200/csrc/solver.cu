@@ -139,6 +139,7 @@ VtClothSolverGPU::VtClothSolverGPU(int device, const VtSimParams* params)
     if (params) simParams = *params;
     else default_sim_params(simParams);
     simParams.numParticles = 0;  // VtClothSolverGPU.hpp L29
+    m_collidersDev.allocate(VT_MAX_COLLIDERS);
 }
 
 VtClothSolverGPU::~VtClothSolverGPU()
@@ -281,9 +282,17 @@ void VtClothSolverGPU::AddAttachBulk(const int* particleIds, const int* slotIds,
 void VtClothSolverGPU::UpdateColliders(const VtSDFCollider* colliders, int numColliders)
 {
     if (numColliders < 0 || (numColliders && !colliders)) throw Error(VELVET_ERR_INVALID_ARGUMENT, "UpdateColliders: bad argument");
-    Synchronize();  // the previous (possibly asynchronous) frame may still be reading the collider block
+    VT_CUDA(cudaSetDevice(m_device));
+    // The seam pipeline reads the managed block directly (like the reference): drain the previous frame first.
+    // The fused pipeline reads a device copy that is refreshed in stream order, so no host sync is needed.
+    if (m_pipeline != VELVET_PIPELINE_FUSED) Synchronize();
     sdfColliders.resize((size_t)numColliders);
-    if (numColliders) std::memcpy(sdfColliders.data(), colliders, sizeof(VtSDFCollider) * (size_t)numColliders);
+    if (numColliders) {
+        std::memcpy(sdfColliders.data(), colliders, sizeof(VtSDFCollider) * (size_t)numColliders);
+        if ((unsigned)numColliders <= VT_MAX_COLLIDERS)
+            VT_CUDA(cudaMemcpyAsync(m_collidersDev.data(), colliders, sizeof(VtSDFCollider) * (size_t)numColliders,
+                                    cudaMemcpyHostToDevice, m_stream));
+    }
 }
 
 // ---- the reference's launch order over the seam kernels (pipeline = SEAM), VtClothSolverGPU.hpp L62-101
@@ -498,7 +507,6 @@ unsigned long long VtClothSolverGPU::topologyKey() const
     mix(predicted.generation());
     mix(invMasses.generation());
     mix(indices.generation());
-    mix(sdfColliders.generation());
     mix(attachSlotPositions.generation());
     mix(attachSlotPositions.size());
     mix((unsigned long long)(uintptr_t)m_spatialHash.get());
@@ -516,7 +524,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
     int launches = 0;
 
     STAGE_BEGIN(t, "Solver_SetParams");
-    launch_prepare_inputs(L, sdfColliders, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()),
+    launch_prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()),
                           m_slotsDev, (uint)(3 * attachSlotPositions.size()), fp);
     launches++;
     STAGE_END(t);

@@ -148,6 +148,7 @@ private:
 
     DeviceBuffer<float4> m_pos4, m_vel4, m_predA, m_predB, m_init4;
     DeviceBuffer<uint> m_keysAlt, m_valsAlt;
+    DeviceBuffer<VtSDFCollider> m_collidersDev;  // stream-ordered device copy of the UpdateColliders block
     DeviceBuffer<PreparedCollider> m_prepared;
     DeviceBuffer<FrameParams> m_frameParams;
     DeviceBuffer<uint> m_vtxTriOff, m_vtxTris;
