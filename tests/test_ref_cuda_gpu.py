@@ -1,0 +1,118 @@
+"""Pins the O1 oracle (and the product) against the REFERENCE's own CUDA kernels, compiled for sm_100a by
+oracle/ref_cuda/build_ref_cuda.sh into oracle/_ref/ (skipped when that library was not built).
+
+Integer work (cell keys, sorted order, cellStart/cellEnd, neighbour lists) must be bit-exact on identical inputs.
+Floating point: the reference build contracts FMAs (nvcc default) and scatters with float atomics in a nondeterministic
+order, so positions are compared at north_star's tolerance: 1e-4 x extent after 1 frame, 1e-3 x extent after 60."""
+import math
+
+import numpy as np
+import pytest
+
+import velvet_b200 as vb
+from oracle import o1, refcuda
+
+from util import EXTENT, ColliderTrack, gpu_params, make_pair, max_abs_diff, to_o1_collider, to_o1_params, valid_prefix_table
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refcuda.available(), reason="oracle/_ref/libvelvet_refcuda.so not built")]
+
+TOL_1 = 1e-4 * EXTENT
+TOL_60 = 1e-3 * EXTENT
+
+
+def _triple(R, p, position, rotation, attached):
+    g, o = make_pair(R, p, position=position, rotation=rotation, attached=attached)
+    r = refcuda.RefCudaSolver(to_o1_params(p))
+    r.register_like(o, R, o1.transform_matrix(position, rotation, (1, 1, 1)), attached)
+    return g, o, r
+
+
+def test_registration_matches_reference_kernels():
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o, r = _triple(31, p, (0.3, 1.5, 1.0), (70, 20, -10), [0, 31])
+    assert r.params.numParticles == 1024
+    assert abs(r.params.maxSpeed - o.params.maxSpeed) == 0 and r.params.particleDiameter == o.params.particleDiameter
+    # InitializePositions: the reference build contracts m0*x + m1*y into FMAs -> last-bit differences only
+    assert max_abs_diff(r.buffer("positions"), o.buffer("positions")) <= 5e-7
+    assert np.array_equal(r.buffer("invMasses"), o.buffer("invMasses"))
+    assert np.array_equal(r.buffer("indices"), o.buffer("indices"))
+
+
+@pytest.mark.parametrize("R", [31, 127])
+def test_hash_bit_exact_against_reference_kernels(R):
+    p = gpu_params()
+    g, o, r = _triple(R, p, (0, 1.5, 1.0), (90, 0, 0), [])
+    n = (R + 1) ** 2
+    rng = np.random.default_rng(R)
+    pred = (o.buffer("positions") + rng.normal(0, 0.02, 3 * n)).astype(np.float32)
+    # identical inputs everywhere: predicted + the same initial positions
+    init = o.buffer("initialPositions").copy()
+    r.buffer("initialPositions")[:] = init
+    r.buffer("predicted")[:] = pred
+    o.buffer("predicted")[:] = pred
+    g.upload("initialPositions", init)
+    g.upload("predicted", pred)
+    r.hash_predicted()
+    o.hash()
+    g.Hash()
+    for other, tag in ((o.buffer, "oracle"), (lambda k: g.download(k), "velvet_b200")):
+        assert np.array_equal(r.buffer("particleHash"), other("particleHash")), tag
+        assert np.array_equal(r.buffer("particleIndex"), other("particleIndex")), tag
+        cs = r.buffer("cellStart")
+        assert np.array_equal(cs, other("cellStart")), tag
+        valid = cs != 0xFFFFFFFF
+        assert np.array_equal(r.buffer("cellEnd")[valid], other("cellEnd")[valid]), tag
+        assert np.array_equal(valid_prefix_table(r.buffer("neighbors"), n, 64), valid_prefix_table(other("neighbors"), n, 64)), tag
+    assert (valid_prefix_table(o.buffer("neighbors"), n, 64) != 0xFFFFFFFF).sum() > 4 * n
+
+
+def _cfg1_frames(g, o, r, frames):
+    sphere = ColliderTrack(vb.COLLIDER_SPHERE, (0, 0.6, -1.0), (0.6, 0.6, 0.6))
+    plane = vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1))
+    for fr in range(frames):
+        sphere.move((0, 0.6, -math.cos(2 * fr / 60.0)))
+        cols = [plane, sphere.collider()]
+        oc = [to_o1_collider(c) for c in cols]
+        g.UpdateColliders(cols)
+        o.set_colliders(oc)
+        r.set_colliders(oc)
+        g.Simulate()
+        o.simulate()
+        r.simulate()
+
+
+def test_cfg1_one_frame_against_reference_kernels():
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o, r = _triple(31, p, (0, 2.5, 0), (0, 0, 0), [0, 31])
+    _cfg1_frames(g, o, r, 1)
+    ref = r.buffer("positions")
+    assert np.isfinite(ref).all()
+    assert max_abs_diff(o.buffer("positions"), ref) <= TOL_1, "oracle vs reference CUDA"
+    assert max_abs_diff(g.download("positions"), ref) <= TOL_1, "velvet_b200 vs reference CUDA"
+    assert max_abs_diff(g.download("velocities"), r.buffer("velocities")) <= 300 * TOL_1
+    assert max_abs_diff(g.download("normals"), r.buffer("normals")) <= 1e-3
+    assert np.array_equal(g.download("invMasses"), r.buffer("invMasses"))
+
+
+def test_cfg1_sixty_frames_against_reference_kernels():
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o, r = _triple(31, p, (0, 2.5, 0), (0, 0, 0), [0, 31])
+    _cfg1_frames(g, o, r, 60)
+    d = max_abs_diff(g.download("positions"), r.buffer("positions"))
+    print(f"cfg1 60 frames: max |dx| velvet_b200 vs reference CUDA = {d:.3e}")
+    assert d <= TOL_60
+
+
+def test_drape_64_one_frame_and_twenty_frames_against_reference_kernels():
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o, r = _triple(63, p, (0, 1.5, 1.0), (90, 0, 0), [])
+    cols = vb.sphere_plane_colliders()
+    oc = [to_o1_collider(c) for c in cols]
+    g.UpdateColliders(cols); o.set_colliders(oc); r.set_colliders(oc)
+    g.Simulate(); o.simulate(); r.simulate()
+    assert max_abs_diff(g.download("positions"), r.buffer("positions")) <= TOL_1
+    for _ in range(19):
+        g.Simulate(); r.simulate()
+    d = max_abs_diff(g.download("positions"), r.buffer("positions"))
+    print(f"drape64 20 frames: max |dx| velvet_b200 vs reference CUDA = {d:.3e}")
+    assert d <= TOL_60
