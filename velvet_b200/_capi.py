@@ -6,6 +6,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvelvet_b200.so")
+if os.environ.get("VELVET_VARIANT"):  # experiments only, see build.py
+    LIB_PATH = os.path.join(_HERE, "lib", f"libvelvet_b200_{os.environ['VELVET_VARIANT']}.so")
 
 
 class VtSimParams(C.Structure):

@@ -25,8 +25,15 @@ INCLUDE = os.path.normpath(os.path.join(HERE, "..", "include"))
 SOURCES = ["radix_sort.cu", "seam_kernels.cu", "fused_kernels.cu", "tile_plan.cpp", "solver.cu", "capi.cu"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# Experiments only (never the default, never used by tests): VELVET_VARIANT=fast builds a second library with FMA
+# contraction and approximate division/sqrt to measure what bit-exactness with the CPU oracle costs.
+VARIANT = os.environ.get("VELVET_VARIANT", "")
+if VARIANT:
+    LIB = os.path.join(LIBDIR, f"libvelvet_b200_{VARIANT}.so")
+    OBJDIR = os.path.join(HERE, f"build_{VARIANT}")
 FLAGS = [
-    "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
+    "-std=c++17", "-O3", "-lineinfo",
+    *(["-fmad=true", "-prec-div=false", "-prec-sqrt=false"] if VARIANT == "fast" else ["-fmad=false"]),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-Wall,-Wno-unused-function",
     "-I", INCLUDE,

@@ -137,57 +137,98 @@ __global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ 
 
 // ---------------------------------------------------------------- tile-fused Jacobi iteration
 //
-// Shared memory: sp[maxLocals] float4 (tile + halo predicted, w = invMass)
-//                slots[maxSlots] float4 (xyz = correction, w = 1 if the constraint was active)
-//                sb[tileSize+1], bb[tileSize+1] uint16 slot bases
+// Shared memory: sp[maxLocals] float4     tile + halo predicted positions, w = invMass
+//                slots[maxK][tileSize] float4   xyz = correction, w = 1 if the constraint was active
+// Slot (ordinal k, particle l) lives at slots[k * tileSize + l]: the per-particle sums read consecutive 16-byte words
+// (no bank conflicts); constraint threads scatter, but consecutive constraints touch neighbouring particles.
+// All global loads of a tile (positions, halo, constraint records) are issued before the first barrier so that their
+// latencies overlap; on a grid cloth one chunk covers the whole tile.
+constexpr int IT_SR = 5;  // stretch records per thread per chunk
+constexpr int IT_BR = 2;  // bend records per thread per chunk
+
+__device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots,
+                                                 unsigned T)
+{
+    const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
+    const unsigned la = ea >> TP_ORD_BITS, ka = ea & 31u, lb = eb >> TP_ORD_BITS, kb = eb & 31u;
+    const float4 pa = sp[la], pb = sp[lb];
+    vec3 c1, c2;
+    const bool active = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2);
+    const float4 zero = make_float4(0, 0, 0, 0);
+    if (ka != TP_NO_SLOT) slots[ka * T + la] = active ? F4(c1, 1.0f) : zero;
+    if (kb != TP_NO_SLOT) slots[kb * T + lb] = active ? F4(c2, 1.0f) : zero;
+}
+
+__device__ __forceinline__ void bend_to_slots(const uint4 r, const float4* __restrict__ sp, float4* __restrict__ slots,
+                                              unsigned T, float xpbd_bend)
+{
+    const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
+    const unsigned l0 = e0 >> TP_ORD_BITS, l1 = e1 >> TP_ORD_BITS, l2 = e2 >> TP_ORD_BITS, l3 = e3 >> TP_ORD_BITS;
+    const float4 p0 = sp[l0], p1 = sp[l1], p2 = sp[l2], p3 = sp[l3];
+    vec3 c0, c1, c2, c3;
+    const bool active = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
+                                  c0, c1, c2, c3);
+    const float4 zero = make_float4(0, 0, 0, 0);
+    if ((e0 & 31u) != TP_NO_SLOT) slots[(e0 & 31u) * T + l0] = active ? F4(c0, 1.0f) : zero;
+    if ((e1 & 31u) != TP_NO_SLOT) slots[(e1 & 31u) * T + l1] = active ? F4(c1, 1.0f) : zero;
+    if ((e2 & 31u) != TP_NO_SLOT) slots[(e2 & 31u) * T + l2] = active ? F4(c2, 1.0f) : zero;
+    if ((e3 & 31u) != TP_NO_SLOT) slots[(e3 & 31u) * T + l3] = active ? F4(c3, 1.0f) : zero;
+}
+
 __global__ void __launch_bounds__(VT_MAX_TILE) iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut,
-                                                            const TilePlanDev plan,
-                                                            const float* __restrict__ attachSlotPositions,
-                                                            const FrameParams* __restrict__ fp)
+                                                                   const TilePlanDev plan,
+                                                                   const float* __restrict__ attachSlotPositions,
+                                                                   const FrameParams* __restrict__ fp)
 {
     extern __shared__ float4 s_mem[];
     float4* sp = s_mem;
     float4* slots = s_mem + plan.maxLocals;
-    uint16_t* sb = reinterpret_cast<uint16_t*>(slots + plan.maxSlots);
-    uint16_t* bb = sb + (plan.tileSize + 2);
 
     const TileDesc td = plan.tiles[blockIdx.x];
     const unsigned tid = threadIdx.x;
+    const unsigned T = blockDim.x;
     const bool owner = tid < td.nOwned;
 
-    unsigned gid = 0;
+    // ---- issue every global load of the tile up front
+    unsigned gid = 0, cntS = 0, cntB = 0;
     float4 mine = make_float4(0, 0, 0, 0);
     if (owner) {
         gid = __ldg(plan.ownedIds + td.ownedOff + tid);
+        cntS = __ldg(plan.sCnt + td.ownedOff + tid);
+        cntB = __ldg(plan.bCnt + td.ownedOff + tid);
+    }
+    uint2 srec[IT_SR];
+#pragma unroll
+    for (int j = 0; j < IT_SR; j++) {
+        const unsigned c = tid + j * T;
+        srec[j] = c < td.nStretch ? __ldg(plan.stretchRec + td.stretchOff + c) : make_uint2(0, 0);
+    }
+    uint4 brec[IT_BR];
+#pragma unroll
+    for (int j = 0; j < IT_BR; j++) {
+        const unsigned c = tid + j * T;
+        brec[j] = c < td.nBend ? __ldg(plan.bendRec + td.bendOff + c) : make_uint4(0, 0, 0, 0);
+    }
+    if (owner) {
         mine = predIn[gid];
         sp[tid] = mine;
     }
-    for (unsigned i = tid; i < td.nHalo; i += blockDim.x) sp[td.nOwned + i] = predIn[__ldg(plan.haloIds + td.haloOff + i)];
-    for (unsigned i = tid; i <= td.nOwned; i += blockDim.x) {
-        sb[i] = plan.sBase[td.baseOff + i];
-        bb[i] = plan.bBase[td.baseOff + i];
-    }
+    for (unsigned i = tid; i < td.nHalo; i += T) sp[td.nOwned + i] = predIn[__ldg(plan.haloIds + td.haloOff + i)];
     __syncthreads();
 
-    // SolveStretch_Kernel, VtClothSolverGPU.cu L76-101, one evaluation per constraint
-    for (unsigned c = tid; c < td.nStretch; c += blockDim.x) {
-        const uint2 r = __ldg(plan.stretchRec + td.stretchOff + c);
-        const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
-        const unsigned la = ea >> TP_ORD_BITS, ka = ea & 31u, lb = eb >> TP_ORD_BITS, kb = eb & 31u;
-        const float4 pa = sp[la], pb = sp[lb];
-        vec3 c1, c2;
-        const bool active = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2);
-        if (ka != TP_NO_SLOT) slots[sb[la] + ka] = active ? F4(c1, 1.0f) : make_float4(0, 0, 0, 0);
-        if (kb != TP_NO_SLOT) slots[sb[lb] + kb] = active ? F4(c2, 1.0f) : make_float4(0, 0, 0, 0);
-    }
+    // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
+#pragma unroll
+    for (int j = 0; j < IT_SR; j++)
+        if (tid + j * T < td.nStretch) stretch_to_slots(srec[j], sp, slots, T);
+    for (unsigned c = tid + IT_SR * T; c < td.nStretch; c += T)  // irregular meshes: remaining chunks
+        stretch_to_slots(__ldg(plan.stretchRec + td.stretchOff + c), sp, slots, T);
     __syncthreads();
 
     vec3 delta = V3(0, 0, 0);
     float count = 0;
     if (owner) {
-        const unsigned s1 = sb[tid + 1];
-        for (unsigned s = sb[tid]; s < s1; s++) {
-            const float4 v = slots[s];
+        for (unsigned k = 0; k < cntS; k++) {
+            const float4 v = slots[k * T + tid];
             if (v.w != 0) {
                 delta += V3(v);
                 count += 1.0f;
@@ -209,28 +250,18 @@ __global__ void __launch_bounds__(VT_MAX_TILE) iterate_tile_kernel(const float4*
     }
     __syncthreads();  // slots are reused by the bending phase
 
-    // SolveBending_Kernel, L128-188
+    // ---- SolveBending_Kernel, L128-188
     const float xpbd_bend = fp->xpbdBend;
-    for (unsigned c = tid; c < td.nBend; c += blockDim.x) {
-        const uint4 r = __ldg(plan.bendRec + td.bendOff + c);
-        const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
-        const float4 p0 = sp[e0 >> TP_ORD_BITS], p1 = sp[e1 >> TP_ORD_BITS], p2 = sp[e2 >> TP_ORD_BITS],
-                     p3 = sp[e3 >> TP_ORD_BITS];
-        vec3 c0, c1, c2, c3;
-        const bool active = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z),
-                                      xpbd_bend, c0, c1, c2, c3);
-        const float4 zero = make_float4(0, 0, 0, 0);
-        if ((e0 & 31u) != TP_NO_SLOT) slots[bb[e0 >> TP_ORD_BITS] + (e0 & 31u)] = active ? F4(c0, 1.0f) : zero;
-        if ((e1 & 31u) != TP_NO_SLOT) slots[bb[e1 >> TP_ORD_BITS] + (e1 & 31u)] = active ? F4(c1, 1.0f) : zero;
-        if ((e2 & 31u) != TP_NO_SLOT) slots[bb[e2 >> TP_ORD_BITS] + (e2 & 31u)] = active ? F4(c2, 1.0f) : zero;
-        if ((e3 & 31u) != TP_NO_SLOT) slots[bb[e3 >> TP_ORD_BITS] + (e3 & 31u)] = active ? F4(c3, 1.0f) : zero;
-    }
+#pragma unroll
+    for (int j = 0; j < IT_BR; j++)
+        if (tid + j * T < td.nBend) bend_to_slots(brec[j], sp, slots, T, xpbd_bend);
+    for (unsigned c = tid + IT_BR * T; c < td.nBend; c += T)
+        bend_to_slots(__ldg(plan.bendRec + td.bendOff + c), sp, slots, T, xpbd_bend);
     __syncthreads();
 
     if (owner) {
-        const unsigned s1 = bb[tid + 1];
-        for (unsigned s = bb[tid]; s < s1; s++) {
-            const float4 v = slots[s];
+        for (unsigned k = 0; k < cntB; k++) {
+            const float4 v = slots[k * T + tid];
             if (v.w != 0) {
                 delta += V3(v);
                 count += 1.0f;
@@ -324,7 +355,7 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
 {
-    return sizeof(float4) * ((size_t)plan.maxLocals + plan.maxSlots) + sizeof(uint16_t) * 2 * ((size_t)plan.tileSize + 2);
+    return sizeof(float4) * ((size_t)plan.maxLocals + (size_t)plan.maxK * plan.tileSize);
 }
 
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,

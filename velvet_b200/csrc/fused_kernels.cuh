@@ -21,13 +21,13 @@ struct TilePlanDev {
     const TileDesc* tiles;
     const unsigned* ownedIds;
     const unsigned* haloIds;
-    const uint16_t* sBase;
-    const uint16_t* bBase;
+    const uint8_t* sCnt;
+    const uint8_t* bCnt;
     const unsigned* attOff;
     const uint2* stretchRec;
     const uint4* bendRec;
     const uint2* attachRec;
-    unsigned numTiles, maxLocals, maxSlots, tileSize;
+    unsigned numTiles, maxLocals, maxK, tileSize;
     unsigned hasAttach;
 };
 

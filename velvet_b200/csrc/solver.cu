@@ -412,8 +412,8 @@ void VtClothSolverGPU::ensureFusedResources()
     m_dTiles.upload(m_plan.tiles, st);
     m_dOwned.upload(m_plan.ownedIds, st);
     m_dHalo.upload(m_plan.haloIds, st);
-    m_dSBase.upload(m_plan.sBase, st);
-    m_dBBase.upload(m_plan.bBase, st);
+    m_dSCnt.upload(m_plan.sCnt, st);
+    m_dBCnt.upload(m_plan.bCnt, st);
     m_dAttOff.upload(m_plan.attOff, st);
     m_dStretchRec.upload(reinterpret_cast<const uint2*>(m_plan.stretchRec.data()), m_plan.stretchRec.size(), st);
     m_dBendRec.upload(reinterpret_cast<const uint4*>(m_plan.bendRec.data()), m_plan.bendRec.size(), st);
@@ -421,15 +421,15 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.tiles = m_dTiles;
     m_planDev.ownedIds = m_dOwned;
     m_planDev.haloIds = m_dHalo;
-    m_planDev.sBase = m_dSBase;
-    m_planDev.bBase = m_dBBase;
+    m_planDev.sCnt = m_dSCnt;
+    m_planDev.bCnt = m_dBCnt;
     m_planDev.attOff = m_dAttOff;
     m_planDev.stretchRec = m_dStretchRec;
     m_planDev.bendRec = m_dBendRec;
     m_planDev.attachRec = m_dAttachRec;
     m_planDev.numTiles = (uint)m_plan.tiles.size();
     m_planDev.maxLocals = m_plan.maxLocals;
-    m_planDev.maxSlots = std::max(m_plan.maxSlots, 1u);
+    m_planDev.maxK = std::max(m_plan.maxK, 1u);
     m_planDev.tileSize = (uint)m_plan.tileSize;
     m_planDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
     const size_t smem = iterate_smem_bytes(m_planDev);

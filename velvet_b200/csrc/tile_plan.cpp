@@ -145,8 +145,8 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
     plan.stretchRec.resize(sList.size());
     plan.bendRec.resize(bList.size());
     plan.attachRec.resize(aList.size());
-    plan.sBase.resize((size_t)N + numTiles);
-    plan.bBase.resize((size_t)N + numTiles);
+    plan.sCnt.resize(N);
+    plan.bCnt.resize(N);
     plan.attOff.resize((size_t)N + numTiles);
     plan.haloIds.clear();
     std::vector<unsigned> haloStamp(N, 0xffffffffu), haloLocal(N);
@@ -201,18 +201,12 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
         if (overflow) return fail("a particle has more than 30 stretch or bend constraints");
         if (td.nOwned + td.nHalo > TP_MAX_LOCALS) return fail("tile halo too large (more than 2047 local particles)");
 
-        // slot bases
-        unsigned accS = 0, accB = 0;
+        // per-particle constraint counts (the slot of ordinal k of particle l is slots[k * T + l])
         for (unsigned l = 0; l < td.nOwned; l++) {
-            plan.sBase[td.baseOff + l] = (uint16_t)accS;
-            plan.bBase[td.baseOff + l] = (uint16_t)accB;
-            accS += cntS[l];
-            accB += cntB[l];
+            plan.sCnt[td.ownedOff + l] = (uint8_t)cntS[l];
+            plan.bCnt[td.ownedOff + l] = (uint8_t)cntB[l];
+            plan.maxK = std::max(plan.maxK, std::max(cntS[l], cntB[l]));
         }
-        if (accS > 65535u || accB > 65535u) return fail("too many slots in a tile");
-        plan.sBase[td.baseOff + td.nOwned] = (uint16_t)accS;
-        plan.bBase[td.baseOff + td.nOwned] = (uint16_t)accB;
-        plan.maxSlots = std::max(plan.maxSlots, std::max(accS, accB));
         plan.maxLocals = std::max(plan.maxLocals, td.nOwned + td.nHalo);
 
         // attach: CSR by owned particle, ascending constraint id inside each particle

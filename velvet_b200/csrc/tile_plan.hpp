@@ -10,6 +10,8 @@
 //
 // Constraints that straddle tiles are evaluated by each owning tile (same inputs, same code, same bits);
 // only owned endpoints receive a slot.  Particles referenced but not owned form the tile's halo.
+// Slot of (particle local index l, ordinal k) is slots[k * tileSize + l]: consecutive particles read consecutive
+// 16-byte words, so the per-particle sums are free of shared-memory bank conflicts.
 #pragma once
 
 #include <cstdint>
@@ -23,7 +25,7 @@ struct TileDesc {
     unsigned haloOff, nHalo;        // range in haloIds
     unsigned stretchOff, nStretch;  // range in stretchRec
     unsigned bendOff, nBend;        // range in bendRec
-    unsigned baseOff;               // first of nOwned+1 entries in sBase / bBase / attOff
+    unsigned baseOff;               // first of nOwned+1 entries in attOff
     unsigned attachOff, nAttach;    // range in attachRec
     unsigned pad;
 };
@@ -46,13 +48,13 @@ struct TilePlan {
     int tileSize = 0;
     std::vector<TileDesc> tiles;
     std::vector<unsigned> ownedIds, haloIds;
-    std::vector<uint16_t> sBase, bBase;  // slot bases per owned particle (+1 terminator per tile)
+    std::vector<uint8_t> sCnt, bCnt;     // stretch / bend constraints incident to each owned particle (index = ownedOff + local)
     std::vector<unsigned> attOff;        // attach CSR per owned particle (+1 per tile), relative to attachOff
     std::vector<Rec2> stretchRec;        // {ea | eb << 16, restLength bits}
     std::vector<Rec4> bendRec;           // {e0 | e1 << 16, e2 | e3 << 16, restAngle bits, constraint id}
     std::vector<Rec2> attachRec;         // {slot id, distance bits}
     unsigned maxLocals = 0;              // max over tiles of nOwned + nHalo
-    unsigned maxSlots = 0;               // max over tiles of max(stretch slots, bend slots)
+    unsigned maxK = 0;                   // max constraints of one type on one particle: slots are laid out [k][local]
     // statistics
     size_t numStretchEvaluated = 0, numBendEvaluated = 0, numHalo = 0;
 };
