@@ -80,10 +80,11 @@ def test_cfg1_sixty_frames(pipeline):
     pos = g.download("positions")
     assert np.isfinite(pos).all()
     if pipeline == vb.PIPELINE_SEAM:
-        # The reference-order pipeline scatters with float atomics exactly like the reference, so its summation
-        # order changes from run to run; contact on/off decisions amplify that noise over 60 frames (measured
-        # 3.2e-3 on B200).  It is the compatibility path, not the product path: a loose envelope only.
-        assert max_abs_diff(pos, o.buffer("positions")) <= 5 * TOL_60
+        # The reference-order pipeline scatters with float atomics exactly like the reference, so its summation order
+        # changes from run to run and contact decisions amplify that noise: on B200 two runs of the REFERENCE's own
+        # kernels on identical inputs end up 1.3e-2 apart by frame 20 of this scene (tests/test_ref_cuda_gpu.py).
+        # It is the compatibility path: only a loose envelope is asserted here.
+        assert max_abs_diff(pos, o.buffer("positions")) <= 0.05
         return
     assert_fused_parity(g, o, TOL_60)
     path = os.path.join(GOLDEN, "cfg1_frame60.npz")

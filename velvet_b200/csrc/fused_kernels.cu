@@ -406,6 +406,18 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
         neighbors, particleIndex, cellStart, cellEnd, PosFloat4{pred}, PosFloat4{init4}, hp);
 }
 
+bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
+                                   const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
+                                   const float4* init4, float4* sortedPos, float4* sortedInit, VtHashParams hp)
+{
+    if (hp.tableSize <= 0) return false;
+    const unsigned n = L.numParticles;
+    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sortedPos, sortedInit, particleIndex, pred, init4, n);
+    cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
+        neighbors, cellStart, cellEnd, sortedPos, sortedInit, hp, make_fastmod((unsigned)hp.tableSize));
+    return true;
+}
+
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n)
 {
     if (n) pack_float4_kernel<<<pgrid(n), PB, 0, L.stream>>>(packed3, out, n);

@@ -79,6 +79,11 @@ void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned*
 void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                             const unsigned* cellStart, const unsigned* cellEnd, const float4* pred, const float4* init4,
                             VtHashParams hp);
+// Restructured H4 (see hash_kernels.cuh): reorder pass + sorted-order candidate walk.  Returns false when it cannot
+// run (degenerate table); the caller then uses launch_cache_neighbors.
+bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
+                                   const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
+                                   const float4* init4, float4* sortedPos, float4* sortedInit, VtHashParams hp);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
 
 }  // namespace velvet

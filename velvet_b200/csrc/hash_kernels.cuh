@@ -96,4 +96,124 @@ __global__ void __launch_bounds__(256) cache_neighbors_kernel(unsigned* __restri
     if (neighborIndex < limit) neighbors[neighborIndex] = 0xffffffffu;
 }
 
+
+// ---------------------------------------------------------------- fused-pipeline variant of H4
+//
+// Same result as cache_neighbors_kernel, bit for bit, restructured for the SIMT machine (ncu on the direct
+// transcription: 9 300 thread-instructions per particle, instruction-bound by divergent 27-cell loops and a runtime `%`):
+//   * reorder pass: sortedPos[i] = (pred[particleIndex[i]], particle id in .w), sortedInit[i] likewise, so the
+//     candidates of a bucket are contiguous 16-byte loads instead of an index -> position dependent gather;
+//   * abs(h % tableSize) == |h| mod tableSize is computed with an exact multiply-high reduction (Lemire fastmod);
+//   * phase 1 writes the non-empty bucket ranges of the 27 cells (x, y, z order) to a shared-memory strip,
+//     phase 2 is ONE flat loop over all candidates, so a warp only diverges on the accept branches.
+struct FastMod {
+    unsigned long long M;  // ceil(2^64 / d)
+    unsigned d;
+};
+inline FastMod make_fastmod(unsigned d)
+{
+    FastMod f;
+    f.d = d;
+    f.M = 0xFFFFFFFFFFFFFFFFull / d + 1;
+    return f;
+}
+__device__ __forceinline__ unsigned fastmod_u32(unsigned a, const FastMod f)
+{
+    const unsigned long long low = f.M * a;
+    return (unsigned)__umul64hi(low, (unsigned long long)f.d);
+}
+__device__ __forceinline__ unsigned hash_key_fast(int hx, int hy, int hz, const FastMod f)
+{
+    const int h = hx ^ hy ^ hz;
+    const unsigned mag = h < 0 ? (unsigned)(-(long long)h) : (unsigned)h;  // |h|, INT_MIN -> 2^31
+    return fastmod_u32(mag, f);
+}
+
+static __global__ void __launch_bounds__(256) reorder_sorted_kernel(float4* __restrict__ sortedPos,
+                                                                    float4* __restrict__ sortedInit,
+                                                                    const unsigned* __restrict__ particleIndex,
+                                                                    const float4* __restrict__ pred,
+                                                                    const float4* __restrict__ init4, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned id = particleIndex[i];
+    float4 p = __ldg(pred + id);
+    p.w = __uint_as_float(id);
+    sortedPos[i] = p;
+    sortedInit[i] = __ldg(init4 + id);
+}
+
+constexpr int CN_THREADS = 256;
+
+// The reference's hash maps many cells to one bucket when tableSize is a power of two (measured on a flat 256^2 sheet:
+// 12 996 cells -> 8 734 buckets, mean bucket 7.5, ~100 candidates per particle), and two of the 27 cells may share a
+// bucket, which is then scanned twice: all of that defines the lists and is kept.
+//
+// Thread t handles the particle in sorted slot t (the reference's mapping, SpatialHashGPU.cu L87-88): the lanes of a
+// warp sit in the same bucket, walk the same candidate runs (convergent loops, broadcast loads), and the scattered
+// 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
+static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
+    unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
+    const float4* __restrict__ sortedPos, const float4* __restrict__ sortedInit, VtHashParams hp, FastMod fm)
+{
+    const unsigned t = blockIdx.x * CN_THREADS + threadIdx.x;
+    if (t >= hp.numObjects) return;
+    const float4 me = __ldg(sortedPos + t);
+    const unsigned id = __float_as_uint(me.w);
+    const vec3 position = V3(me);
+    const vec3 originalPos = V3(__ldg(sortedInit + t));
+    const int ix = int_coord(position.x, hp.cellSpacing);
+    const int iy = int_coord(position.y, hp.cellSpacing);
+    const int iz = int_coord(position.z, hp.cellSpacing);
+    const int hx0 = (int)((unsigned)(ix - 1) * 92837111u), hx1 = (int)((unsigned)ix * 92837111u), hx2 = (int)((unsigned)(ix + 1) * 92837111u);
+    const int hy0 = (int)((unsigned)(iy - 1) * 689287499u), hy1 = (int)((unsigned)iy * 689287499u), hy2 = (int)((unsigned)(iy + 1) * 689287499u);
+    const int hz0 = (int)((unsigned)(iz - 1) * 283923481u), hz1 = (int)((unsigned)iz * 283923481u), hz2 = (int)((unsigned)(iz + 1) * 283923481u);
+
+    // phase 1: which of the 27 buckets (x, y, z traversal order = bit order) are non-empty; 27 independent loads in flight
+    unsigned mask = 0;
+#pragma unroll
+    for (int b = 0; b < 27; b++) {
+        const int hx = (b / 9) == 0 ? hx0 : (b / 9) == 1 ? hx1 : hx2;
+        const int hy = ((b / 3) % 3) == 0 ? hy0 : ((b / 3) % 3) == 1 ? hy1 : hy2;
+        const int hz = (b % 3) == 0 ? hz0 : (b % 3) == 1 ? hz1 : hz2;
+        if (__ldg(cellStart + hash_key_fast(hx, hy, hz, fm)) != 0xffffffffu) mask |= 1u << b;
+    }
+
+    // phase 2: walk the non-empty buckets in traversal order
+    const unsigned N = hp.numObjects, K = hp.maxNumNeighbors;
+    unsigned* out = neighbors + id;
+    unsigned k = 0;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int a = b / 9, m = (b / 3) % 3, c = b % 3;
+        const int hx = a == 0 ? hx0 : a == 1 ? hx1 : hx2;
+        const int hy = m == 0 ? hy0 : m == 1 ? hy1 : hy2;
+        const int hz = c == 0 ? hz0 : c == 1 ? hz1 : hz2;
+        const unsigned key = hash_key_fast(hx, hy, hz, fm);
+        unsigned cur = __ldg(cellStart + key);
+        unsigned end = __ldg(cellEnd + key);
+        if (cur + K < end) end = cur + K;
+        // four candidate loads in flight per trip: the walk is latency-bound otherwise (ncu: 56% of stalls on the load)
+        for (; cur < end; cur += 4) {
+            float4 q[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) q[j] = __ldg(sortedPos + (cur + j < end ? cur + j : cur));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (cur + j >= end) break;
+                const unsigned nb = __float_as_uint(q[j].w);
+                if (nb != id && length2(position - V3(q[j])) < hp.cellSpacing2) {
+                    if (length2(originalPos - V3(__ldg(sortedInit + cur + j))) > hp.particleDiameter2) {
+                        out[(size_t)k * N] = nb;
+                        if (++k >= K) return;
+                    }
+                }
+            }
+        }
+    }
+    if (k < K) out[(size_t)k * N] = 0xffffffffu;
+}
+
 }  // namespace velvet

@@ -458,6 +458,8 @@ void VtClothSolverGPU::ensureFusedResources()
     m_predA.allocate(N);
     m_predB.allocate(N);
     m_init4.allocate(N);
+    m_sortedPos.allocate(N);
+    m_sortedInit.allocate(N);
     m_keysAlt.allocate(N);
     m_valsAlt.allocate(N);
     m_prepared.allocate(VT_MAX_COLLIDERS);
@@ -558,9 +560,14 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashCache");
-            launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
-                                   H.MakeParams(N, P.particleDiameter));
-            launches++;
+            if (launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
+                                              m_sortedPos, m_sortedInit, H.MakeParams(N, P.particleDiameter))) {
+                launches += 2;
+            } else {
+                launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
+                                       H.MakeParams(N, P.particleDiameter));
+                launches++;
+            }
             STAGE_END(t);
         }
         STAGE_BEGIN(t, "Solver_CollideParticles");  // + ApplyDeltas + CollideSDFs
