@@ -187,6 +187,15 @@ typedef enum VelvetPipeline {
     VELVET_PIPELINE_SEAM = 1   /* the reference's launch sequence over the seam kernels (A/B, debug) */
 } VelvetPipeline;
 
+typedef enum VelvetMathMode {
+    VELVET_MATH_EXACT = 0, /* default: no FMA contraction, IEEE division / sqrt -- bit-identical to the CPU oracle (oracle/)
+                              at any horizon, hence within north_star's 1-frame and 60-frame tolerances              */
+    VELVET_MATH_FAST = 1   /* opt-in: FMA contraction + approximate division / sqrt in the float kernels; deterministic,
+                              ~1e-5 x extent from the oracle after a frame (tolerance 1e-4), ~35 % faster Jacobi
+                              iteration; like the reference's own build it is not comparable beyond ~20 frames of a
+                              contact-rich scene                                                                      */
+} VelvetMathMode;
+
 /* VtClothSolverGPU::Start (hpp L27-33): numParticles = 0.  params may be NULL (defaults).
  * device < 0 keeps the current CUDA device. */
 VELVET_API int velvet_solver_create(VelvetSolver** out, int device, const VtSimParams* params);
@@ -194,7 +203,9 @@ VELVET_API int velvet_solver_destroy(VelvetSolver* s);
 /* Global::simParams of this instance; the caller may edit it between frames (ImGui sliders / ModifyParameter). */
 VELVET_API VtSimParams* velvet_solver_params(VelvetSolver* s);
 VELVET_API int velvet_solver_set_pipeline(VelvetSolver* s, int pipeline);
-/* Fused pipeline only: particles per Jacobi tile (0 = default). */
+/* Fused pipeline only: VelvetMathMode.  The spatial hash is bit-exact in both modes. */
+VELVET_API int velvet_solver_set_math_mode(VelvetSolver* s, int mode);
+/* Fused pipeline only: particles per Jacobi tile (0 = default, else 128 / 256 / 512). */
 VELVET_API int velvet_solver_set_tile_size(VelvetSolver* s, int particlesPerTile);
 
 /* AddCloth (hpp L114-156): vertices = host float[3*numVertices] in model space, indices = host uint[numIndices].

@@ -140,7 +140,7 @@ def test_moving_attach_slot_and_disabled_self_collision():
 def test_two_cloths_and_cube_collider():
     """'Multiple Object' scene (main.cpp L232-268): cloths registered one after another on one solver + cube SDF."""
     p = gpu_params(numSubsteps=5, numIterations=5, friction=0.6)
-    g = vb.VtClothSolverGPU(p)
+    g = vb.VtClothSolverGPU(p, math_mode=vb.MATH_EXACT)
     o = o1.O1Solver(__import__("util").to_o1_params(p))
     for height in (1.5, 1.8):
         R = 24
@@ -208,14 +208,117 @@ def test_256_one_frame_and_tile_sizes():
         assert np.array_equal(g.download("positions").reshape(-1), ref), tile  # contract: <= TOL_1
 
 
+# ------------------------------------------------------------------ FAST math mode (opt-in): tolerance parity
+def _assert_within(g, o, tol):
+    for name, scale in (("positions", 1.0), ("predicted", 1.0), ("velocities", 300.0)):
+        assert max_abs_diff(g.download(name), o.buffer(name)) <= tol * scale, name
+
+
+def test_fast_math_cfg1_one_frame_and_hash():
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(31, p, position=(0, 2.5, 0), rotation=(0, 0, 0), attached=[0, 31], math_mode=vb.MATH_FAST)
+    _run_cfg1(g, o, 1)
+    _assert_within(g, o, TOL_1)
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= 0.25 * TOL_1, "measured 1.6e-5 on B200"
+    # the spatial hash is compiled exactly in every mode: bit-exact on identical input
+    pred = o.buffer("predicted").copy()
+    g.upload("predicted", pred)
+    g.Hash()
+    o.hash()
+    assert np.array_equal(g.download("particleHash"), o.buffer("particleHash"))
+    assert np.array_equal(g.download("particleIndex"), o.buffer("particleIndex"))
+    assert np.array_equal(valid_prefix_table(g.download("neighbors"), 1024, 64), valid_prefix_table(o.buffer("neighbors"), 1024, 64))
+
+
+@pytest.mark.parametrize("frames,tol", [(1, TOL_1), (20, TOL_60)])
+def test_fast_math_drape_64(frames, tol):
+    """Measured drift of the FAST mode from the oracle on this scene (B200): 1.0e-5 after 1 frame, 1.6e-4 after 20 --
+    the same distance the reference's own CUDA build keeps from the oracle (1.9e-4 after 20 frames, test_ref_cuda_gpu).
+    Past frame ~22 the cloth buckles over the sphere and every non-bit-identical implementation, the reference
+    against itself included, departs by centimetres; only the EXACT mode (bit-identical) can be checked there."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(63, p, math_mode=vb.MATH_FAST)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    for _ in range(frames):
+        g.Simulate()
+        o.simulate()
+    _assert_within(g, o, tol)
+
+
+def test_fast_math_corner_attach_and_cube_scenes():
+    R = 40
+    corners = [0, R, (R + 1) * (R + 1) - 1, (R + 1) * R]
+    g, o = make_pair(R, gpu_params(), attached=corners, math_mode=vb.MATH_FAST)
+    set_colliders(g, o, vb.sphere_plane_colliders(radius=0.5))
+    for _ in range(20):
+        g.Simulate()
+        o.simulate()
+    _assert_within(g, o, TOL_60)
+    p = gpu_params(numSubsteps=5, numIterations=5, friction=0.6)
+    g, o = make_pair(24, p, position=(0, 1.5, 1.0), math_mode=vb.MATH_FAST)
+    cube = ColliderTrack(vb.COLLIDER_CUBE, (0, 0.5, 0), (1, 1, 1), (0, 15, 0))
+    set_colliders(g, o, [vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1)), cube.collider()])
+    for _ in range(25):
+        g.Simulate()
+        o.simulate()
+    _assert_within(g, o, TOL_60)
+
+
+def test_fast_math_ten_frames_then_envelope():
+    """Config 1 with the sphere parked away (no collider contact at all).  Even so the Jacobi dynamics amplify last-bit
+    differences: measured FAST-vs-oracle drift on B200 is 3.6e-5 after 1 frame, 1.9e-4 after 10, 7.7e-3 after 20.
+    north_star's 60-frame tolerance is therefore asserted on the EXACT mode (bit-identical, test_cfg1_sixty_frames);
+    here: strict for 10 frames, finite and bounded after 60."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(31, p, position=(0, 8.0, 0), rotation=(0, 0, 0), attached=[0, 31], math_mode=vb.MATH_FAST)
+    cols = [vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1)),
+            vb.MakeCollider(vb.COLLIDER_SPHERE, (0, 0.6, -3.0), (0.6, 0.6, 0.6))]
+    set_colliders(g, o, cols)
+    for fr in range(60):
+        g.Simulate()
+        o.simulate()
+        if fr < 10:
+            assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_60 * (fr + 1) / 10, fr
+    pos = g.download("positions")
+    assert np.isfinite(pos).all() and max_abs_diff(pos, o.buffer("positions")) <= 0.25
+
+
+def test_fast_math_256_one_frame():
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(255, p, math_mode=vb.MATH_FAST)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    g.Simulate()
+    o.simulate()
+    _assert_within(g, o, TOL_1)
+
+
+def test_fast_math_cfg1_sixty_frames_envelope():
+    """Chaotic scene (see tests/test_ref_cuda_gpu.py): strict while contact-free, bounded afterwards."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(31, p, position=(0, 2.5, 0), rotation=(0, 0, 0), attached=[0, 31], math_mode=vb.MATH_FAST)
+    sphere = ColliderTrack(vb.COLLIDER_SPHERE, (0, 0.6, -1.0), (0.6, 0.6, 0.6))
+    plane = vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1))
+    for fr in range(60):
+        sphere.move((0, 0.6, -math.cos(2 * fr / 60.0)))
+        set_colliders(g, o, [plane, sphere.collider()])
+        g.Simulate()
+        o.simulate()
+        if fr < 15:
+            assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_1, fr
+    pos = g.download("positions")
+    assert np.isfinite(pos).all()
+    assert max_abs_diff(pos, o.buffer("positions")) <= 0.05
+
+
 def test_fused_is_deterministic_and_matches_seam_at_1m():
     """Headline size (1024x1024, 1M particles): properties that do not need the CPU oracle.
     Two independent fused runs are bit-identical (deterministic summation); the fused pipeline agrees with the
     reference-order seam pipeline (float atomics) within the 1-frame tolerance; hash outputs agree bit-exactly."""
     p = gpu_params(numSubsteps=5, numIterations=10)
     outs = []
-    for pipeline in (vb.PIPELINE_FUSED, vb.PIPELINE_FUSED, vb.PIPELINE_SEAM):
-        g, _ = make_pair(1023, p, pipeline=pipeline, oracle=False)
+    for pipeline, mode in ((vb.PIPELINE_FUSED, vb.MATH_EXACT), (vb.PIPELINE_FUSED, vb.MATH_EXACT), (vb.PIPELINE_SEAM, vb.MATH_EXACT),
+                           (vb.PIPELINE_FUSED, vb.MATH_FAST), (vb.PIPELINE_FUSED, vb.MATH_FAST)):
+        g, _ = make_pair(1023, p, pipeline=pipeline, oracle=False, math_mode=mode)
         g.UpdateColliders(vb.sphere_plane_colliders())
         g.Simulate()
         g.Simulate()
@@ -229,6 +332,9 @@ def test_fused_is_deterministic_and_matches_seam_at_1m():
     # sortedness / permutation properties at full size
     assert np.all(np.diff(outs[0][2].astype(np.int64)) >= 0)
     assert np.array_equal(np.sort(outs[0][1]), np.arange(1 << 20, dtype=np.uint32))
+    # the FAST math mode is deterministic too (fixed summation order) and within tolerance of the EXACT one
+    assert np.array_equal(outs[3][0], outs[4][0]), "fast math mode is run-to-run deterministic"
+    assert max_abs_diff(outs[3][0], outs[0][0]) <= TOL_1
 
 
 def test_empty_solver_and_error_convention():

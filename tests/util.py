@@ -51,10 +51,12 @@ class ColliderTrack:
 
 
 def make_pair(resolution, params=None, position=(0, 1.5, 1.0), rotation=(90, 0, 0), attached=(), pipeline=vb.PIPELINE_FUSED,
-              tile_size=0, oracle=True):
-    """Same grid cloth registered in the CUDA solver and (optionally) in the O1 oracle."""
+              tile_size=0, oracle=True, math_mode=vb.MATH_EXACT):
+    """Same grid cloth registered in the CUDA solver and (optionally) in the O1 oracle.  EXACT math (the library default)
+    is bit-identical to the oracle; the opt-in FAST mode is tested at tolerance."""
     params = params or gpu_params()
-    g = vb.build_scene(resolution, params, position, rotation, attached, pipeline=pipeline, tile_size=tile_size)
+    g = vb.build_scene(resolution, params, position, rotation, attached, pipeline=pipeline, tile_size=tile_size,
+                       math_mode=math_mode)
     o = None
     if oracle:
         o = o1.O1Solver(to_o1_params(params))

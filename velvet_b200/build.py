@@ -33,11 +33,15 @@ if VARIANT:
     OBJDIR = os.path.join(HERE, f"build_{VARIANT}")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
-    *(["-fmad=true", "-prec-div=false", "-prec-sqrt=false"] if VARIANT == "fast" else ["-fmad=false"]),
+    *(["-fmad=true", "-prec-div=false", "-prec-sqrt=false"] if VARIANT.startswith("fast") else ["-fmad=false"]),
+    *([f"-DVT_IT_REGCAP_BLOCKS={VARIANT[-1]}"] if VARIANT[-2:-1] == "b" else []),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-Wall,-Wno-unused-function",
     "-I", INCLUDE,
 ]
+
+
+FAST_FLAGS = [f for f in FLAGS if f != "-fmad=false"] + ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-DVT_FAST_MATH=1"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -54,12 +58,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(INCLUDE, "velvet_b200.h"))
     headers.append(os.path.abspath(__file__))
     objs, jobs = [], []
-    for src in SOURCES:
+    units = [(src, src + ".o", FLAGS) for src in SOURCES]
+    # the float kernels a second time with relaxed math (namespace fast_math, see fused_kernels.cuh)
+    units.append(("fused_kernels.cu", "fused_kernels_fast.cu.o", FAST_FLAGS))
+    for src, objname, flags in units:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJDIR, src + ".o")
+        obj = os.path.join(OBJDIR, objname)
         objs.append(obj)
         if force or _stale(obj, [path] + headers):
-            cmd = [NVCC, *FLAGS, "-x", "cu", "-c", path, "-o", obj]
+            cmd = [NVCC, *flags, "-x", "cu", "-c", path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

@@ -126,6 +126,14 @@ int velvet_solver_set_pipeline(VelvetSolver* s, int pipeline)
     VT_API_END
 }
 
+int velvet_solver_set_math_mode(VelvetSolver* s, int mode)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.setMathMode(mode);
+    VT_API_END
+}
+
 int velvet_solver_set_tile_size(VelvetSolver* s, int n)
 {
     VT_API_BEGIN

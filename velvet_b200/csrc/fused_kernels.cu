@@ -22,7 +22,17 @@
 #include "hash_kernels.cuh"
 #include "vt_buffer.hpp"
 
+#ifndef VT_FAST_MATH
+#define VT_FAST_MATH 0
+#endif
+#if VT_FAST_MATH
+#define VT_MATH_NS fast_math
+#else
+#define VT_MATH_NS exact_math
+#endif
+
 namespace velvet {
+namespace VT_MATH_NS {
 
 namespace {
 
@@ -144,52 +154,89 @@ __global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ 
 // All global loads of a tile (positions, halo, constraint records) are issued before the first barrier so that their
 // latencies overlap; on a grid cloth one chunk covers the whole tile.
 constexpr int IT_SR = 5;  // stretch records per thread per chunk
-constexpr int IT_BR = 2;  // bend records per thread per chunk
 
-__device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots,
-                                                 unsigned T)
+// slot index of an encoded endpoint: row = ordinal (low 5 bits), column = local particle index
+template <int LOG2T>
+__device__ __forceinline__ unsigned slot_of(unsigned e)
+{
+    return ((e & 31u) << LOG2T) + ((e >> TP_ORD_BITS) & ((1u << LOG2T) - 1u));  // halo columns wrap inside the dump row
+}
+
+__device__ __forceinline__ void cp_async_16(void* smemDst, const void* gmemSrc)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmemSrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int LOG2T>
+__device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots)
 {
     const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
-    const unsigned la = ea >> TP_ORD_BITS, ka = ea & 31u, lb = eb >> TP_ORD_BITS, kb = eb & 31u;
-    const float4 pa = sp[la], pb = sp[lb];
+    const float4 pa = sp[ea >> TP_ORD_BITS], pb = sp[eb >> TP_ORD_BITS];
+#if VT_FAST_MATH
     vec3 c1, c2;
-    const bool active = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2);
-    const float4 zero = make_float4(0, 0, 0, 0);
-    if (ka != TP_NO_SLOT) slots[ka * T + la] = active ? F4(c1, 1.0f) : zero;
-    if (kb != TP_NO_SLOT) slots[kb * T + lb] = active ? F4(c2, 1.0f) : zero;
+    const float flag = stretch_eval_flagged(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2) ? 1.0f : 0.0f;
+#else
+    vec3 c1 = V3(0, 0, 0), c2 = c1;
+    const float flag = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2) ? 1.0f : 0.0f;
+#endif
+    slots[slot_of<LOG2T>(ea)] = F4(c1, flag);  // halo endpoints land in the dump row
+    slots[slot_of<LOG2T>(eb)] = F4(c2, flag);
 }
 
+template <int LOG2T>
 __device__ __forceinline__ void bend_to_slots(const uint4 r, const float4* __restrict__ sp, float4* __restrict__ slots,
-                                              unsigned T, float xpbd_bend)
+                                              float xpbd_bend)
 {
     const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
-    const unsigned l0 = e0 >> TP_ORD_BITS, l1 = e1 >> TP_ORD_BITS, l2 = e2 >> TP_ORD_BITS, l3 = e3 >> TP_ORD_BITS;
-    const float4 p0 = sp[l0], p1 = sp[l1], p2 = sp[l2], p3 = sp[l3];
-    vec3 c0, c1, c2, c3;
-    const bool active = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
-                                  c0, c1, c2, c3);
-    const float4 zero = make_float4(0, 0, 0, 0);
-    if ((e0 & 31u) != TP_NO_SLOT) slots[(e0 & 31u) * T + l0] = active ? F4(c0, 1.0f) : zero;
-    if ((e1 & 31u) != TP_NO_SLOT) slots[(e1 & 31u) * T + l1] = active ? F4(c1, 1.0f) : zero;
-    if ((e2 & 31u) != TP_NO_SLOT) slots[(e2 & 31u) * T + l2] = active ? F4(c2, 1.0f) : zero;
-    if ((e3 & 31u) != TP_NO_SLOT) slots[(e3 & 31u) * T + l3] = active ? F4(c3, 1.0f) : zero;
+    const float4 p0 = sp[e0 >> TP_ORD_BITS], p1 = sp[e1 >> TP_ORD_BITS], p2 = sp[e2 >> TP_ORD_BITS], p3 = sp[e3 >> TP_ORD_BITS];
+    vec3 c0 = V3(0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
+    const float flag = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
+                                 c0, c1, c2, c3) ? 1.0f : 0.0f;
+    slots[slot_of<LOG2T>(e0)] = F4(c0, flag);
+    slots[slot_of<LOG2T>(e1)] = F4(c1, flag);
+    slots[slot_of<LOG2T>(e2)] = F4(c2, flag);
+    slots[slot_of<LOG2T>(e3)] = F4(c3, flag);
 }
 
-__global__ void __launch_bounds__(VT_MAX_TILE) iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut,
-                                                                   const TilePlanDev plan,
-                                                                   const float* __restrict__ attachSlotPositions,
-                                                                   const FrameParams* __restrict__ fp)
+// Sum of a particle's slots in ordinal (= constraint id) order.  Inactive slots add +0, which is bit-neutral because the
+// accumulator starts at +0 and can never become -0.
+template <int LOG2T>
+__device__ __forceinline__ void sum_slots(const float4* __restrict__ slots, unsigned tid, unsigned n, vec3& delta, float& count)
 {
+    for (unsigned k = 0; k < n; k++) {
+        const float4 v = slots[(k << LOG2T) + tid];
+        const bool on = v.w != 0;
+        delta.x += on ? v.x : 0.0f;
+        delta.y += on ? v.y : 0.0f;
+        delta.z += on ? v.z : 0.0f;
+        count += v.w;
+    }
+}
+
+template <int LOG2T>
+#ifndef VT_IT_REGCAP_BLOCKS
+#define VT_IT_REGCAP_BLOCKS 4  // resident 256-thread CTAs per SM the register budget is sized for
+#endif
+__global__ void __launch_bounds__(1 << LOG2T, (VT_IT_REGCAP_BLOCKS * 256) >> LOG2T)
+iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut, const TilePlanDev plan,
+                    const float* __restrict__ attachSlotPositions, const FrameParams* __restrict__ fp)
+{
+    constexpr unsigned T = 1u << LOG2T;
     extern __shared__ float4 s_mem[];
     float4* sp = s_mem;
     float4* slots = s_mem + plan.maxLocals;
+    const unsigned slotRows = (plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB) + 1;  // + the dump row
+    uint4* s_brec = reinterpret_cast<uint4*>(slots + (slotRows << LOG2T));
 
     const TileDesc td = plan.tiles[blockIdx.x];
     const unsigned tid = threadIdx.x;
-    const unsigned T = blockDim.x;
     const bool owner = tid < td.nOwned;
 
-    // ---- issue every global load of the tile up front
+    // ---- issue every global load of the tile up front; bend records go straight to shared memory (cp.async, no
+    //      registers held across the stretch phase)
+    for (unsigned c = tid; c < td.nBend; c += T) cp_async_16(s_brec + c, plan.bendRec + td.bendOff + c);
     unsigned gid = 0, cntS = 0, cntB = 0;
     float4 mine = make_float4(0, 0, 0, 0);
     if (owner) {
@@ -203,37 +250,26 @@ __global__ void __launch_bounds__(VT_MAX_TILE) iterate_tile_kernel(const float4*
         const unsigned c = tid + j * T;
         srec[j] = c < td.nStretch ? __ldg(plan.stretchRec + td.stretchOff + c) : make_uint2(0, 0);
     }
-    uint4 brec[IT_BR];
-#pragma unroll
-    for (int j = 0; j < IT_BR; j++) {
-        const unsigned c = tid + j * T;
-        brec[j] = c < td.nBend ? __ldg(plan.bendRec + td.bendOff + c) : make_uint4(0, 0, 0, 0);
-    }
     if (owner) {
         mine = predIn[gid];
         sp[tid] = mine;
     }
     for (unsigned i = tid; i < td.nHalo; i += T) sp[td.nOwned + i] = predIn[__ldg(plan.haloIds + td.haloOff + i)];
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
 #pragma unroll
     for (int j = 0; j < IT_SR; j++)
-        if (tid + j * T < td.nStretch) stretch_to_slots(srec[j], sp, slots, T);
+        if (tid + j * T < td.nStretch) stretch_to_slots<LOG2T>(srec[j], sp, slots);
     for (unsigned c = tid + IT_SR * T; c < td.nStretch; c += T)  // irregular meshes: remaining chunks
-        stretch_to_slots(__ldg(plan.stretchRec + td.stretchOff + c), sp, slots, T);
+        stretch_to_slots<LOG2T>(__ldg(plan.stretchRec + td.stretchOff + c), sp, slots);
     __syncthreads();
 
     vec3 delta = V3(0, 0, 0);
     float count = 0;
     if (owner) {
-        for (unsigned k = 0; k < cntS; k++) {
-            const float4 v = slots[k * T + tid];
-            if (v.w != 0) {
-                delta += V3(v);
-                count += 1.0f;
-            }
-        }
+        sum_slots<LOG2T>(slots, tid, cntS, delta, count);
         // SolveAttachment_Kernel, L218-234: per-particle, no slot needed
         if (plan.hasAttach) {
             const float lrs = fp->P.longRangeStretchiness;
@@ -252,21 +288,11 @@ __global__ void __launch_bounds__(VT_MAX_TILE) iterate_tile_kernel(const float4*
 
     // ---- SolveBending_Kernel, L128-188
     const float xpbd_bend = fp->xpbdBend;
-#pragma unroll
-    for (int j = 0; j < IT_BR; j++)
-        if (tid + j * T < td.nBend) bend_to_slots(brec[j], sp, slots, T, xpbd_bend);
-    for (unsigned c = tid + IT_BR * T; c < td.nBend; c += T)
-        bend_to_slots(__ldg(plan.bendRec + td.bendOff + c), sp, slots, T, xpbd_bend);
+    for (unsigned c = tid; c < td.nBend; c += T) bend_to_slots<LOG2T>(s_brec[c], sp, slots, xpbd_bend);
     __syncthreads();
 
     if (owner) {
-        for (unsigned k = 0; k < cntB; k++) {
-            const float4 v = slots[k * T + tid];
-            if (v.w != 0) {
-                delta += V3(v);
-                count += 1.0f;
-            }
-        }
+        sum_slots<LOG2T>(slots, tid, cntB, delta, count);
         // ApplyDeltas_Kernel, L257-263
         vec3 p = V3(mine);
         if (count > 0) p += delta / count * fp->P.relaxationFactor;
@@ -355,19 +381,29 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
 {
-    return sizeof(float4) * ((size_t)plan.maxLocals + (size_t)plan.maxK * plan.tileSize);
+    // sp[maxLocals] + slot rows + a dump row; halo endpoints store to (dumpRow * T + local) with local < maxLocals,
+    // so the dump row is maxLocals wide
+    const size_t rows = (size_t)(plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB) + 1;
+    return sizeof(float4) * ((size_t)plan.maxLocals + rows * plan.tileSize + plan.maxBendPerTile);
 }
 
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp)
 {
-    iterate_tile_kernel<<<plan.numTiles, plan.tileSize, iterate_smem_bytes(plan), L.stream>>>(predIn, predOut, plan,
-                                                                                               attachSlotPositions, fp);
+    const size_t smem = iterate_smem_bytes(plan);
+    switch (plan.tileSize) {
+    case 128: iterate_tile_kernel<7><<<plan.numTiles, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
+    case 256: iterate_tile_kernel<8><<<plan.numTiles, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
+    case 512: iterate_tile_kernel<9><<<plan.numTiles, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
+    default: throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
+    }
 }
 
 void configure_iterate_kernel(size_t smemBytes)
 {
-    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
 }
 
 void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext, bool last,
@@ -383,6 +419,7 @@ void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* in
     normals_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(pos4, indices, vtxTriOff, vtxTris, normalsOut, L.numParticles);
 }
 
+#if !VT_FAST_MATH  // the spatial hash is integer work: one (exact) build only
 void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
                            int tableSize)
 {
@@ -422,5 +459,7 @@ void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out,
 {
     if (n) pack_float4_kernel<<<pgrid(n), PB, 0, L.stream>>>(packed3, out, n);
 }
+#endif
 
+}  // namespace VT_MATH_NS
 }  // namespace velvet

@@ -27,7 +27,7 @@ struct TilePlanDev {
     const uint2* stretchRec;
     const uint4* bendRec;
     const uint2* attachRec;
-    unsigned numTiles, maxLocals, maxK, tileSize;
+    unsigned numTiles, maxLocals, maxKS, maxKB, tileSize, maxBendPerTile;
     unsigned hasAttach;
 };
 
@@ -38,6 +38,15 @@ struct FusedLaunch {
     cudaStream_t stream;
     unsigned numParticles;
 };
+
+// The floating-point kernels are compiled twice from the same source (fused_kernels.cu):
+//   exact_math  -fmad=false, IEEE division / square root: bit-identical to the CPU oracle (oracle/ref_jacobi_cpu.c)
+//   fast_math   FMA contraction + approximate division / square root (nvcc -fmad=true -prec-div=false
+//               -prec-sqrt=false): ~35 % fewer instructions in the Jacobi kernel, still deterministic (no atomics,
+//               fixed summation order), within north_star's tolerance of the oracle but not bit-identical to it.
+// The spatial-hash kernels exist only in exact_math: cell keys, sorted order and neighbour lists are integer work
+// and must be bit-exact in every mode.
+namespace exact_math {
 
 // Per-frame inputs the host may have rewritten in managed memory: colliders (prepared once, with
 // lastTransform * invCurTransform hoisted) and attach slot positions (copied to device scratch).
@@ -85,5 +94,65 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
                                    const float4* init4, float4* sortedPos, float4* sortedInit, VtHashParams hp);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
+
+}  // namespace exact_math
+
+namespace fast_math {
+
+// Per-frame inputs the host may have rewritten in managed memory: colliders (prepared once, with
+// lastTransform * invCurTransform hoisted) and attach slot positions (copied to device scratch).
+void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders, PreparedCollider* prepared,
+                           const float* slotPositions, float* slotPositionsOut, unsigned numSlotFloats,
+                           const FrameParams* fp);
+
+// AoS import + pre-stabilisation SDF pass (frame dt) + PredictPositions of substep 0.
+void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
+                        float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders,
+                        const FrameParams* fp);
+
+// CollideParticles + ApplyDeltas + CollideSDF (substep dt): predIn -> predOut.
+void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
+                    const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp,
+                    bool selfCollision);
+
+// One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
+void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
+                    const float* attachSlotPositions, const FrameParams* fp);
+size_t iterate_smem_bytes(const TilePlanDev& plan);
+void configure_iterate_kernel(size_t smemBytes);  // opt in to > 48 KB dynamic shared memory
+
+// Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
+// of positions / velocities / predicted to the public packed-float3 buffers).
+void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext,
+                        bool last, float* positionsOut, float* velocitiesOut, float* predictedOut,
+                        const FrameParams* fp);
+
+// ComputeNormal as a per-vertex gather over incident triangles (ascending triangle id).
+void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
+                    const unsigned* vtxTris, float* normalsOut);
+
+}  // namespace fast_math
+
+// run-time selection of the math build
+struct FusedOps {
+    decltype(&exact_math::launch_prepare_inputs) prepare_inputs;
+    decltype(&exact_math::launch_begin_frame) begin_frame;
+    decltype(&exact_math::launch_collide) collide;
+    decltype(&exact_math::launch_iterate) iterate;
+    decltype(&exact_math::iterate_smem_bytes) iterate_smem_bytes;
+    decltype(&exact_math::configure_iterate_kernel) configure_iterate_kernel;
+    decltype(&exact_math::launch_end_substep) end_substep;
+    decltype(&exact_math::launch_normals) normals;
+};
+inline FusedOps fused_ops(bool fastMath)
+{
+    if (fastMath)
+        return FusedOps{&fast_math::launch_prepare_inputs, &fast_math::launch_begin_frame, &fast_math::launch_collide,
+                        &fast_math::launch_iterate, &fast_math::iterate_smem_bytes, &fast_math::configure_iterate_kernel,
+                        &fast_math::launch_end_substep, &fast_math::launch_normals};
+    return FusedOps{&exact_math::launch_prepare_inputs, &exact_math::launch_begin_frame, &exact_math::launch_collide,
+                    &exact_math::launch_iterate, &exact_math::iterate_smem_bytes, &exact_math::configure_iterate_kernel,
+                    &exact_math::launch_end_substep, &exact_math::launch_normals};
+}
 
 }  // namespace velvet

@@ -168,10 +168,16 @@ void VtClothSolverGPU::setPipeline(int pipeline)
     m_pipeline = pipeline;
 }
 
+void VtClothSolverGPU::setMathMode(int mode)
+{
+    if (mode != VELVET_MATH_FAST && mode != VELVET_MATH_EXACT) throw Error(VELVET_ERR_INVALID_ARGUMENT, "unknown math mode");
+    m_mathMode = mode;  // the graph key includes the mode: the next Simulate re-captures, nothing else is rebuilt
+}
+
 void VtClothSolverGPU::setTileSize(int particlesPerTile)
 {
-    if (particlesPerTile != 0 && (particlesPerTile < 32 || particlesPerTile > VT_MAX_TILE || particlesPerTile % 32))
-        throw Error(VELVET_ERR_INVALID_ARGUMENT, "tile size must be 0 or a multiple of 32 in [32,512]");
+    if (particlesPerTile != 0 && particlesPerTile != 128 && particlesPerTile != 256 && particlesPerTile != 512)
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "tile size must be 0 (default), 128, 256 or 512");
     m_tileSize = particlesPerTile;
     invalidate();
 }
@@ -388,7 +394,7 @@ void VtClothSolverGPU::ensureFusedResources()
         return;
     }
 
-    const int tileSize = m_tileSize ? m_tileSize : 256;
+    const int tileSize = m_tileSize ? m_tileSize : 256;  // power of two: the kernel is specialised on log2(tile)
     m_plan = build_tile_plan(N, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), stretchIndices.data(),
                              stretchLengths.data(), stretchLengths.size(), bendIndices.data(), bendAngles.data(),
                              bendAngles.size(), attachParticleIDs.data(), attachSlotIDs.data(), attachDistances.data(),
@@ -429,15 +435,18 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.attachRec = m_dAttachRec;
     m_planDev.numTiles = (uint)m_plan.tiles.size();
     m_planDev.maxLocals = m_plan.maxLocals;
-    m_planDev.maxK = std::max(m_plan.maxK, 1u);
+    m_planDev.maxKS = m_plan.maxKS;
+    m_planDev.maxKB = m_plan.maxKB;
+    m_planDev.maxBendPerTile = m_plan.maxBendPerTile;
     m_planDev.tileSize = (uint)m_plan.tileSize;
     m_planDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
-    const size_t smem = iterate_smem_bytes(m_planDev);
+    const size_t smem = exact_math::iterate_smem_bytes(m_planDev);
     if (smem > 200 * 1024) {
         m_fallbackReason = "tile needs more than 200 KB of shared memory";
         return;
     }
-    configure_iterate_kernel(smem);
+    exact_math::configure_iterate_kernel(smem);
+    fast_math::configure_iterate_kernel(smem);
 
     // vertex -> incident triangles, ascending triangle id
     {
@@ -467,7 +476,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_slotsDev.allocate(std::max<size_t>(3 * attachSlotPositions.size(), 3));
     m_sorter.reserve(N);
     FusedLaunch L{st, N};
-    launch_pack_float4(L, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4, N);
+    exact_math::launch_pack_float4(L, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4, N);
 
     // the big public buffers live in managed memory (reference contract): make them device-resident now
     auto prefetch = [&](const void* p, size_t bytes) {
@@ -512,6 +521,7 @@ unsigned long long VtClothSolverGPU::topologyKey() const
     mix(attachSlotPositions.generation());
     mix(attachSlotPositions.size());
     mix((unsigned long long)(uintptr_t)m_spatialHash.get());
+    mix((unsigned)m_mathMode);
     return h;
 }
 
@@ -523,10 +533,11 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
     FusedLaunch L{m_stream, N};
     const FrameParams* fp = m_frameParams;
     SpatialHashGPU& H = *m_spatialHash;
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
     int launches = 0;
 
     STAGE_BEGIN(t, "Solver_SetParams");
-    launch_prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()),
+    ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()),
                           m_slotsDev, (uint)(3 * attachSlotPositions.size()), fp);
     launches++;
     STAGE_END(t);
@@ -534,7 +545,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
     float4* cur = m_predA;
     float4* other = m_predB;
     STAGE_BEGIN(t, "Solver_Predict");  // import + pre-stabilisation + predict(0)
-    launch_begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()),
+    ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()),
                        invMasses, m_pos4, m_vel4, cur, m_prepared, fp);
     launches++;
     STAGE_END(t);
@@ -548,7 +559,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
             STAGE_BEGIN(t, "Solver_HashParticle");
-            launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize());
+            exact_math::launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize());
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashSort");
@@ -556,29 +567,29 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             launches += m_sorter.lastLaunchCount();
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashBuildCell");
-            launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashCache");
-            if (launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
+            if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
                                               m_sortedPos, m_sortedInit, H.MakeParams(N, P.particleDiameter))) {
                 launches += 2;
             } else {
-                launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
+                exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
                                        H.MakeParams(N, P.particleDiameter));
                 launches++;
             }
             STAGE_END(t);
         }
         STAGE_BEGIN(t, "Solver_CollideParticles");  // + ApplyDeltas + CollideSDFs
-        launch_collide(L, cur, other, m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0);
+        ops.collide(L, cur, other, m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0);
         launches++;
         std::swap(cur, other);
         STAGE_END(t);
 
         STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
         for (int iteration = 0; iteration < P.numIterations; iteration++) {
-            launch_iterate(L, cur, other, m_planDev, m_slotsDev, fp);
+            ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp);
             launches++;
             std::swap(cur, other);
         }
@@ -586,14 +597,14 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
 
         STAGE_BEGIN(t, "Solver_Finalize");  // + Predict of the next substep / export on the last one
         const bool last = substep == P.numSubsteps - 1;
-        launch_end_substep(L, cur, m_pos4, m_vel4, other, last, reinterpret_cast<float*>(positions.data()),
+        ops.end_substep(L, cur, m_pos4, m_vel4, other, last, reinterpret_cast<float*>(positions.data()),
                            reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
         launches++;
         if (!last) std::swap(cur, other);
         STAGE_END(t);
     }
     STAGE_BEGIN(t, "Solver_UpdateNormals");
-    launch_normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()));
+    ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()));
     launches++;
     STAGE_END(t);
     VT_CUDA(cudaGetLastError());

@@ -116,6 +116,8 @@ public:
     void setPipeline(int pipeline);
     int pipeline() const { return m_pipeline; }
     void setTileSize(int particlesPerTile);
+    void setMathMode(int mode);  // VELVET_MATH_EXACT (default) or VELVET_MATH_FAST
+    int mathMode() const { return m_mathMode; }
     cudaStream_t stream() const { return m_stream; }
     int device() const { return m_device; }
     int lastLaunchCount() const { return m_lastLaunches; }
@@ -134,6 +136,7 @@ private:
     cudaStream_t m_stream = nullptr;
     int m_pipeline = 0;
     int m_tileSize = 0;
+    int m_mathMode = VELVET_MATH_EXACT;
     int m_lastLaunches = 0;
     std::shared_ptr<SpatialHashGPU> m_spatialHash;
 

@@ -205,9 +205,11 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
         for (unsigned l = 0; l < td.nOwned; l++) {
             plan.sCnt[td.ownedOff + l] = (uint8_t)cntS[l];
             plan.bCnt[td.ownedOff + l] = (uint8_t)cntB[l];
-            plan.maxK = std::max(plan.maxK, std::max(cntS[l], cntB[l]));
+            plan.maxKS = std::max(plan.maxKS, cntS[l]);
+            plan.maxKB = std::max(plan.maxKB, cntB[l]);
         }
         plan.maxLocals = std::max(plan.maxLocals, td.nOwned + td.nHalo);
+        plan.maxBendPerTile = std::max(plan.maxBendPerTile, td.nBend);
 
         // attach: CSR by owned particle, ascending constraint id inside each particle
         for (unsigned i = 0; i < td.nAttach; i++) cntA[localOf[(unsigned)attachParticleIDs[aList[td.attachOff + i]]]]++;
@@ -223,6 +225,15 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
             const unsigned l = localOf[(unsigned)attachParticleIDs[c]];
             plan.attachRec[td.attachOff + cntA[l]++] = Rec2{(unsigned)attachSlotIDs[c], float_bits(attachDistances[c])};
         }
+    }
+    // halo endpoints: replace the NO_SLOT marker by the dump-row ordinal of their constraint type
+    if (plan.maxKS >= TP_NO_SLOT || plan.maxKB >= TP_NO_SLOT) return fail("a particle has more than 30 stretch or bend constraints");
+    auto redirect = [](unsigned e, unsigned dumpRow) { return (e & 31u) == TP_NO_SLOT ? ((e & ~31u) | dumpRow) : e; };
+    for (Rec2& r : plan.stretchRec)
+        r.x = redirect(r.x & 0xffffu, plan.maxKS) | (redirect(r.x >> 16, plan.maxKS) << 16);
+    for (Rec4& r : plan.bendRec) {
+        r.x = redirect(r.x & 0xffffu, plan.maxKB) | (redirect(r.x >> 16, plan.maxKB) << 16);
+        r.y = redirect(r.y & 0xffffu, plan.maxKB) | (redirect(r.y >> 16, plan.maxKB) << 16);
     }
     plan.numStretchEvaluated = sList.size();
     plan.numBendEvaluated = bList.size();

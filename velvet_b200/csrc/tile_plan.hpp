@@ -37,7 +37,8 @@ struct Rec4 {
     unsigned x, y, z, w;
 };
 
-// endpoint encoding inside a record: (localIndex << 5) | slotOrdinal, slotOrdinal 31 = halo (no slot)
+// endpoint encoding inside a record: (localIndex << 5) | slotOrdinal.  Halo endpoints (no slot of their own) carry the
+// ordinal of a dump row (= maxKS for stretch, maxKB for bend) so that kernels can store unconditionally.
 constexpr unsigned TP_ORD_BITS = 5;
 constexpr unsigned TP_NO_SLOT = 31;
 constexpr unsigned TP_MAX_LOCALS = 2047;
@@ -54,7 +55,8 @@ struct TilePlan {
     std::vector<Rec4> bendRec;           // {e0 | e1 << 16, e2 | e3 << 16, restAngle bits, constraint id}
     std::vector<Rec2> attachRec;         // {slot id, distance bits}
     unsigned maxLocals = 0;              // max over tiles of nOwned + nHalo
-    unsigned maxK = 0;                   // max constraints of one type on one particle: slots are laid out [k][local]
+    unsigned maxBendPerTile = 0;         // max over tiles of nBend (bend records are staged in shared memory)
+    unsigned maxKS = 0, maxKB = 0;       // max stretch / bend constraints on one particle; slot rows are [k][local], plus a dump row
     // statistics
     size_t numStretchEvaluated = 0, numBendEvaluated = 0, numHalo = 0;
 };

@@ -15,7 +15,7 @@ import math
 import numpy as np
 
 from . import _capi
-from ._capi import (BUFFER_IDS, COLLIDER_CUBE, COLLIDER_PLANE, COLLIDER_SPHERE, PIPELINE_FUSED, PIPELINE_SEAM,
+from ._capi import (BUFFER_IDS, COLLIDER_CUBE, COLLIDER_PLANE, COLLIDER_SPHERE, MATH_EXACT, MATH_FAST, PIPELINE_FUSED, PIPELINE_SEAM,
                     VtHashParams, VtSDFCollider, VtSimParams, check)
 
 _BUF_DTYPE = {
@@ -80,7 +80,7 @@ def _collider_array(colliders):
 
 class VtClothSolverGPU:
     def __init__(self, params: VtSimParams | None = None, device: int = -1, pipeline: int = PIPELINE_FUSED,
-                 tile_size: int = 0):
+                 tile_size: int = 0, math_mode: int = MATH_EXACT):
         self._L = _capi.load()
         h = C.c_void_p()
         check(self._L.velvet_solver_create(C.byref(h), device, C.byref(params) if params is not None else None))
@@ -89,6 +89,11 @@ class VtClothSolverGPU:
             self.SetPipeline(pipeline)
         if tile_size:
             check(self._L.velvet_solver_set_tile_size(self._h, tile_size))
+        if math_mode != MATH_EXACT:
+            self.SetMathMode(math_mode)
+
+    def SetMathMode(self, mode: int):
+        check(self._L.velvet_solver_set_math_mode(self._h, mode))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -266,9 +271,10 @@ class SpatialHashGPU:
 
 
 def build_scene(resolution: int, params: VtSimParams | None = None, position=(0, 1.5, 1.0), rotation=(90, 0, 0),
-                attached=(), pipeline: int = PIPELINE_FUSED, device: int = -1, tile_size: int = 0) -> VtClothSolverGPU:
+                attached=(), pipeline: int = PIPELINE_FUSED, device: int = -1, tile_size: int = 0,
+                math_mode: int = MATH_EXACT) -> VtClothSolverGPU:
     """SpawnCloth + Initialize + VtClothObjectGPU::Start for one grid cloth (Scene.hpp L251-291, main.cpp L141)."""
-    solver = VtClothSolverGPU(params, device=device, pipeline=pipeline, tile_size=tile_size)
+    solver = VtClothSolverGPU(params, device=device, pipeline=pipeline, tile_size=tile_size, math_mode=math_mode)
     v, idx = GenerateClothMesh(resolution)
     obj = VtClothObjectGPU(resolution, solver)
     obj.SetAttachedIndices(attached)
