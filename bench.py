@@ -155,14 +155,11 @@ def velvet_main(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the velvet_b200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from velvet_b200.distributed import Group, instance_model_height
+    group = Group("nccl", device=torch.device("cuda", local_rank))
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        group.barrier()
         torch.cuda.synchronize()
 
     R = args.resolution
@@ -170,7 +167,7 @@ def velvet_main(args, rank, world, local_rank):
     p.numSubsteps, p.numIterations = SUBSTEPS, ITERATIONS
     t0 = time.perf_counter()
     math_mode = vb.MATH_FAST if args.math == "fast" else vb.MATH_EXACT
-    g = vb.build_scene(R, p, position=(0, 1.5 + 0.01 * rank, 1.0), rotation=(90, 0, 0), device=local_rank,
+    g = vb.build_scene(R, p, position=(0, instance_model_height(rank), 1.0), rotation=(90, 0, 0), device=local_rank,
                        tile_size=args.tile, math_mode=math_mode)
     cols = vb.sphere_plane_colliders()
     raw = b"".join(bytes(c) for c in cols)
@@ -206,11 +203,7 @@ def velvet_main(args, rank, world, local_rank):
     wall = time.perf_counter() - wall0
     barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = group.max(ev0.elapsed_time(ev1))
     ms_per_step = ms / args.steps
     value = world * N * SUBSTEPS * args.steps / (ms * 1e-3)
 
@@ -232,17 +225,13 @@ def velvet_main(args, rank, world, local_rank):
     e1.record(stream)
     g.Synchronize()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = group.max(e0.elapsed_time(e1))
     e2e_value = world * N * SUBSTEPS * args.steps / (e2e_ms * 1e-3)
     finite = bool(torch.isfinite(host_pos).all())
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        group.barrier()  # rank 0 is still measuring stages / the CPU baseline
+        group.close()
         return 0
 
     # ---- roofline of the dominant kernel (tile-fused Jacobi iteration), CUDA events around each stage
@@ -322,8 +311,8 @@ def velvet_main(args, rank, world, local_rank):
         "other_math_mode": other,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    group.barrier()
+    group.close()
     return 0
 
 
