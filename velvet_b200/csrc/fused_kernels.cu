@@ -445,13 +445,14 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 
 bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedPos, float4* sortedInit, VtHashParams hp)
+                                   const float4* init4, float4* sortedScratch, VtHashParams hp)
 {
     if (hp.tableSize <= 0) return false;
     const unsigned n = L.numParticles;
-    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sortedPos, sortedInit, particleIndex, pred, init4, n);
+    SortedParticle* sorted = reinterpret_cast<SortedParticle*>(sortedScratch);
+    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n);
     cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
-        neighbors, cellStart, cellEnd, sortedPos, sortedInit, hp, make_fastmod((unsigned)hp.tableSize));
+        neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize));
     return true;
 }
 

@@ -92,7 +92,7 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 // run (degenerate table); the caller then uses launch_cache_neighbors.
 bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedPos, float4* sortedInit, VtHashParams hp);
+                                   const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
 
 }  // namespace exact_math

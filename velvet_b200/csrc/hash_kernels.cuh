@@ -129,8 +129,14 @@ __device__ __forceinline__ unsigned hash_key_fast(int hx, int hy, int hz, const 
     return fastmod_u32(mag, f);
 }
 
-static __global__ void __launch_bounds__(256) reorder_sorted_kernel(float4* __restrict__ sortedPos,
-                                                                    float4* __restrict__ sortedInit,
+// One 32-byte record per sorted slot: {predicted xyz, particle id} {registration-time xyz, unused}.  Both distance tests
+// of a candidate read the same 32-byte sector.
+struct __align__(32) SortedParticle {
+    float4 pos;   // w = particle id bits
+    float4 init;
+};
+
+static __global__ void __launch_bounds__(256) reorder_sorted_kernel(SortedParticle* __restrict__ sorted,
                                                                     const unsigned* __restrict__ particleIndex,
                                                                     const float4* __restrict__ pred,
                                                                     const float4* __restrict__ init4, unsigned n)
@@ -140,29 +146,29 @@ static __global__ void __launch_bounds__(256) reorder_sorted_kernel(float4* __re
     const unsigned id = particleIndex[i];
     float4 p = __ldg(pred + id);
     p.w = __uint_as_float(id);
-    sortedPos[i] = p;
-    sortedInit[i] = __ldg(init4 + id);
+    sorted[i].pos = p;
+    sorted[i].init = __ldg(init4 + id);
 }
 
 constexpr int CN_THREADS = 256;
 
-// The reference's hash maps many cells to one bucket when tableSize is a power of two (measured on a flat 256^2 sheet:
-// 12 996 cells -> 8 734 buckets, mean bucket 7.5, ~100 candidates per particle), and two of the 27 cells may share a
+// The reference's hash maps many cells to one bucket when tableSize is a power of two (measured on a flat 1024^2 sheet:
+// 207 936 cells -> 138 605 buckets, mean bucket 7.6, ~105 candidates per particle), and two of the 27 cells may share a
 // bucket, which is then scanned twice: all of that defines the lists and is kept.
 //
 // Thread t handles the particle in sorted slot t (the reference's mapping, SpatialHashGPU.cu L87-88): the lanes of a
-// warp sit in the same bucket, walk the same candidate runs (convergent loops, broadcast loads), and the scattered
-// 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
+// warp sit in the same few buckets and walk the same candidate runs (mostly convergent loops, broadcast loads); the
+// scattered 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
 static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
     unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
-    const float4* __restrict__ sortedPos, const float4* __restrict__ sortedInit, VtHashParams hp, FastMod fm)
+    const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm)
 {
     const unsigned t = blockIdx.x * CN_THREADS + threadIdx.x;
     if (t >= hp.numObjects) return;
-    const float4 me = __ldg(sortedPos + t);
+    const float4 me = __ldg(&sorted[t].pos);
     const unsigned id = __float_as_uint(me.w);
     const vec3 position = V3(me);
-    const vec3 originalPos = V3(__ldg(sortedInit + t));
+    const vec3 originalPos = V3(__ldg(&sorted[t].init));
     const int ix = int_coord(position.x, hp.cellSpacing);
     const int iy = int_coord(position.y, hp.cellSpacing);
     const int iz = int_coord(position.z, hp.cellSpacing);
@@ -182,6 +188,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
 
     // phase 2: walk the non-empty buckets in traversal order
     const unsigned N = hp.numObjects, K = hp.maxNumNeighbors;
+    const float cs2 = hp.cellSpacing2, pd2 = hp.particleDiameter2;
     unsigned* out = neighbors + id;
     unsigned k = 0;
     while (mask) {
@@ -195,21 +202,23 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
         unsigned cur = __ldg(cellStart + key);
         unsigned end = __ldg(cellEnd + key);
         if (cur + K < end) end = cur + K;
-        // four candidate loads in flight per trip: the walk is latency-bound otherwise (ncu: 56% of stalls on the load)
-        for (; cur < end; cur += 4) {
-            float4 q[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) q[j] = __ldg(sortedPos + (cur + j < end ? cur + j : cur));
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (cur + j >= end) break;
-                const unsigned nb = __float_as_uint(q[j].w);
-                if (nb != id && length2(position - V3(q[j])) < hp.cellSpacing2) {
-                    if (length2(originalPos - V3(__ldg(sortedInit + cur + j))) > hp.particleDiameter2) {
-                        out[(size_t)k * N] = nb;
-                        if (++k >= K) return;
-                    }
-                }
+        // two candidates (4 x 16 bytes) in flight per trip; both distance tests are evaluated unconditionally: the
+        // second vector sits in the same 32-byte sector and a branch-free body keeps the warp converged
+        for (; cur < end; cur += 2) {
+            const bool two = cur + 1 < end;
+            const SortedParticle* c0 = sorted + cur;
+            const SortedParticle* c1 = sorted + (two ? cur + 1 : cur);
+            const float4 q0 = __ldg(&c0->pos), o0 = __ldg(&c0->init), q1 = __ldg(&c1->pos), o1 = __ldg(&c1->init);
+            const unsigned nb0 = __float_as_uint(q0.w), nb1 = __float_as_uint(q1.w);
+            const bool hit0 = nb0 != id && length2(position - V3(q0)) < cs2 && length2(originalPos - V3(o0)) > pd2;
+            const bool hit1 = two && nb1 != id && length2(position - V3(q1)) < cs2 && length2(originalPos - V3(o1)) > pd2;
+            if (hit0) {
+                out[(size_t)k * N] = nb0;
+                if (++k >= K) return;
+            }
+            if (hit1) {
+                out[(size_t)k * N] = nb1;
+                if (++k >= K) return;
             }
         }
     }

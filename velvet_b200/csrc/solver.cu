@@ -467,8 +467,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_predA.allocate(N);
     m_predB.allocate(N);
     m_init4.allocate(N);
-    m_sortedPos.allocate(N);
-    m_sortedInit.allocate(N);
+    m_sorted.allocate(2 * (size_t)N);
     m_keysAlt.allocate(N);
     m_valsAlt.allocate(N);
     m_prepared.allocate(VT_MAX_COLLIDERS);
@@ -572,7 +571,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashCache");
             if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
-                                              m_sortedPos, m_sortedInit, H.MakeParams(N, P.particleDiameter))) {
+                                              m_sorted, H.MakeParams(N, P.particleDiameter))) {
                 launches += 2;
             } else {
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
