@@ -337,6 +337,83 @@ def test_fused_is_deterministic_and_matches_seam_at_1m():
     assert max_abs_diff(outs[3][0], outs[0][0]) <= TOL_1
 
 
+def _register_generic(g, o, vertices, tri_indices, model, stretch, bends, attach_slots, attaches, diameter):
+    """Registers an arbitrary mesh through the element-wise API (AddCloth / AddStretch / AddBend / AddAttach*), the
+    way a maintainer's own cloth component would, on both the CUDA solver and the oracle."""
+    g.AddCloth(vertices, tri_indices, model, diameter)
+    o.add_cloth(vertices, tri_indices, model, diameter)
+    for (a, b, d) in stretch:
+        g.AddStretch(a, b, d); o.add_stretch(a, b, d)
+    for slot in attach_slots:
+        g.AddAttachSlot(slot); o.add_attach_slot(slot)
+    for (pid, slot, d) in attaches:
+        g.AddAttach(pid, slot, d); o.add_attach(pid, slot, d)
+    for (a, b, c, d) in bends:
+        g.AddBend(a, b, c, d, 0.0); o.add_bend(a, b, c, d, 0.0)
+
+
+def _shuffled_grid(R, seed):
+    """A grid cloth whose vertices are stored in random order: constraint indices have no locality at all, which is
+    what the Morton tiling of the Jacobi kernel has to cope with on arbitrary meshes."""
+    rng = np.random.default_rng(seed)
+    v, idx = vb.GenerateClothMesh(R)
+    n = len(v)
+    perm = rng.permutation(n)          # new index of old vertex i
+    inv = np.empty(n, np.int64); inv[perm] = np.arange(n)
+    v2 = v[inv]
+    idx2 = perm[idx.astype(np.int64)].astype(np.uint32)
+    S = R + 1
+    world = (vb.TransformMatrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1)).reshape(4, 4).T @ np.c_[v, np.ones(n)].T).T[:, :3].astype(np.float32)
+    stretch = []
+    at = lambda x, y: x * S + y
+    for x in range(S):
+        for y in range(S):
+            pairs = []
+            if y != R: pairs.append((at(x, y), at(x, y + 1)))
+            if x != R: pairs.append((at(x, y), at(x + 1, y)))
+            if y != R and x != R: pairs += [(at(x, y), at(x + 1, y + 1)), (at(x, y + 1), at(x + 1, y))]
+            for a, b in pairs:
+                stretch.append((int(perm[a]), int(perm[b]), float(np.float32(np.linalg.norm(world[a] - world[b])))))
+    bends = [(int(perm[idx[i]]), int(perm[idx[i + 5]]), int(perm[idx[i + 2]]), int(perm[idx[i + 1]])) for i in range(0, len(idx), 6)]
+    return v2, idx2, stretch, bends
+
+
+def test_shuffled_vertex_order_mesh_is_still_bit_identical():
+    R = 40
+    p = gpu_params(numSubsteps=3, numIterations=6)
+    v2, idx2, stretch, bends = _shuffled_grid(R, seed=5)
+    g = vb.VtClothSolverGPU(p)
+    o = o1.O1Solver(__import__("util").to_o1_params(p))
+    M = vb.TransformMatrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1))
+    D = float(np.float32(2.0 / R * 1.5))
+    _register_generic(g, o, v2, idx2, M, stretch, bends, [], [], D)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    for _ in range(20):
+        g.Simulate(); o.simulate()
+    assert_fused_parity(g, o, TOL_60)
+    assert g.lastLaunchCount < 200, "the fused pipeline (not the seam fallback) must have been used"
+
+
+def test_high_valence_mesh_falls_back_to_the_reference_order_pipeline():
+    """A hub particle with 40 stretch constraints exceeds the 30 slots a tile gives one particle: Simulate() must fall
+    back to the seam pipeline on its own and still agree with the oracle (float atomics: tolerance, not bit-identity)."""
+    rng = np.random.default_rng(9)
+    n = 60
+    v = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32); v[:, 1] += 2.0
+    tri = np.array([0, 1, 2], np.uint32)
+    p = gpu_params(enableSelfCollision=0)
+    g = vb.VtClothSolverGPU(p); o = o1.O1Solver(__import__("util").to_o1_params(p))
+    M = vb.TransformMatrix()
+    stretch = [(0, j, float(np.float32(np.linalg.norm(v[0] - v[j])))) for j in range(1, 41)]
+    stretch += [(j, j + 1, float(np.float32(np.linalg.norm(v[j] - v[j + 1])))) for j in range(1, n - 1)]
+    _register_generic(g, o, v, tri, M, stretch, [], [(0.0, 2.5, 0.0)], [(0, 0, 0.0)], 0.05)
+    set_colliders(g, o, [vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1))])
+    for _ in range(5):
+        g.Simulate(); o.simulate()
+    assert g.lastLaunchCount > 0
+    assert max_abs_diff(g.download("positions"), o.buffer("positions")) <= TOL_1
+
+
 def test_empty_solver_and_error_convention():
     g = vb.VtClothSolverGPU()
     g.Simulate()  # no cloth registered: silently nothing to do (CUDA_CALL early-out)

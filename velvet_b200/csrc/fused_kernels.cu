@@ -170,7 +170,8 @@ __device__ __forceinline__ void cp_async_16(void* smemDst, const void* gmemSrc)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int LOG2T>
-__device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots)
+__device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots,
+                                                 unsigned dumpRow)
 {
     const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
     const float4 pa = sp[ea >> TP_ORD_BITS], pb = sp[eb >> TP_ORD_BITS];
@@ -181,23 +182,25 @@ __device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __
     vec3 c1 = V3(0, 0, 0), c2 = c1;
     const float flag = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2) ? 1.0f : 0.0f;
 #endif
-    slots[slot_of<LOG2T>(ea)] = F4(c1, flag);  // halo endpoints land in the dump row
-    slots[slot_of<LOG2T>(eb)] = F4(c2, flag);
+    // halo endpoints carry the dump-row ordinal and are simply not stored (a store into a shared dump row would be a
+    // benign write-write race, but it would drown compute-sanitizer racecheck in false positives)
+    if ((ea & 31u) != dumpRow) slots[slot_of<LOG2T>(ea)] = F4(c1, flag);
+    if ((eb & 31u) != dumpRow) slots[slot_of<LOG2T>(eb)] = F4(c2, flag);
 }
 
 template <int LOG2T>
 __device__ __forceinline__ void bend_to_slots(const uint4 r, const float4* __restrict__ sp, float4* __restrict__ slots,
-                                              float xpbd_bend)
+                                              float xpbd_bend, unsigned dumpRow)
 {
     const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
     const float4 p0 = sp[e0 >> TP_ORD_BITS], p1 = sp[e1 >> TP_ORD_BITS], p2 = sp[e2 >> TP_ORD_BITS], p3 = sp[e3 >> TP_ORD_BITS];
     vec3 c0 = V3(0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
     const float flag = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
                                  c0, c1, c2, c3) ? 1.0f : 0.0f;
-    slots[slot_of<LOG2T>(e0)] = F4(c0, flag);
-    slots[slot_of<LOG2T>(e1)] = F4(c1, flag);
-    slots[slot_of<LOG2T>(e2)] = F4(c2, flag);
-    slots[slot_of<LOG2T>(e3)] = F4(c3, flag);
+    if ((e0 & 31u) != dumpRow) slots[slot_of<LOG2T>(e0)] = F4(c0, flag);
+    if ((e1 & 31u) != dumpRow) slots[slot_of<LOG2T>(e1)] = F4(c1, flag);
+    if ((e2 & 31u) != dumpRow) slots[slot_of<LOG2T>(e2)] = F4(c2, flag);
+    if ((e3 & 31u) != dumpRow) slots[slot_of<LOG2T>(e3)] = F4(c3, flag);
 }
 
 // Sum of a particle's slots in ordinal (= constraint id) order.  Inactive slots add +0, which is bit-neutral because the
@@ -261,9 +264,9 @@ iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ pred
     // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
 #pragma unroll
     for (int j = 0; j < IT_SR; j++)
-        if (tid + j * T < td.nStretch) stretch_to_slots<LOG2T>(srec[j], sp, slots);
+        if (tid + j * T < td.nStretch) stretch_to_slots<LOG2T>(srec[j], sp, slots, plan.maxKS);
     for (unsigned c = tid + IT_SR * T; c < td.nStretch; c += T)  // irregular meshes: remaining chunks
-        stretch_to_slots<LOG2T>(__ldg(plan.stretchRec + td.stretchOff + c), sp, slots);
+        stretch_to_slots<LOG2T>(__ldg(plan.stretchRec + td.stretchOff + c), sp, slots, plan.maxKS);
     __syncthreads();
 
     vec3 delta = V3(0, 0, 0);
@@ -288,7 +291,7 @@ iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ pred
 
     // ---- SolveBending_Kernel, L128-188
     const float xpbd_bend = fp->xpbdBend;
-    for (unsigned c = tid; c < td.nBend; c += T) bend_to_slots<LOG2T>(s_brec[c], sp, slots, xpbd_bend);
+    for (unsigned c = tid; c < td.nBend; c += T) bend_to_slots<LOG2T>(s_brec[c], sp, slots, xpbd_bend, plan.maxKB);
     __syncthreads();
 
     if (owner) {
@@ -384,14 +387,14 @@ size_t iterate_smem_bytes(const TilePlanDev& plan)
     // sp[maxLocals] + slot rows + a dump row; halo endpoints store to (dumpRow * T + local) with local < maxLocals,
     // so the dump row is maxLocals wide
     const size_t rows = (size_t)(plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB) + 1;
-    return sizeof(float4) * ((size_t)plan.maxLocals + rows * plan.tileSize + plan.maxBendPerTile);
+    return sizeof(float4) * ((size_t)plan.maxLocals + rows * plan.threads + plan.maxBendPerTile);
 }
 
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp)
 {
     const size_t smem = iterate_smem_bytes(plan);
-    switch (plan.tileSize) {
+    switch (plan.threads) {
     case 128: iterate_tile_kernel<7><<<plan.numTiles, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
     case 256: iterate_tile_kernel<8><<<plan.numTiles, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
     case 512: iterate_tile_kernel<9><<<plan.numTiles, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;

@@ -28,6 +28,7 @@ struct TilePlanDev {
     const uint4* bendRec;
     const uint2* attachRec;
     unsigned numTiles, maxLocals, maxKS, maxKB, tileSize, maxBendPerTile;
+    unsigned threads;  // CTA size: the power of two >= tileSize (slot rows are `threads` wide)
     unsigned hasAttach;
 };
 

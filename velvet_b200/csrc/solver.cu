@@ -176,8 +176,8 @@ void VtClothSolverGPU::setMathMode(int mode)
 
 void VtClothSolverGPU::setTileSize(int particlesPerTile)
 {
-    if (particlesPerTile != 0 && particlesPerTile != 128 && particlesPerTile != 256 && particlesPerTile != 512)
-        throw Error(VELVET_ERR_INVALID_ARGUMENT, "tile size must be 0 (default), 128, 256 or 512");
+    if (particlesPerTile != 0 && (particlesPerTile < 32 || particlesPerTile > VT_MAX_TILE || particlesPerTile % 32))
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "tile size must be 0 (default) or a multiple of 32 in [32, 512]");
     m_tileSize = particlesPerTile;
     invalidate();
 }
@@ -439,6 +439,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.maxKB = m_plan.maxKB;
     m_planDev.maxBendPerTile = m_plan.maxBendPerTile;
     m_planDev.tileSize = (uint)m_plan.tileSize;
+    m_planDev.threads = m_plan.tileSize <= 128 ? 128u : (m_plan.tileSize <= 256 ? 256u : 512u);
     m_planDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
     const size_t smem = exact_math::iterate_smem_bytes(m_planDev);
     if (smem > 200 * 1024) {
