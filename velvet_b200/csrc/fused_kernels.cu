@@ -117,24 +117,39 @@ __global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ 
         const vec3 vel_i = pred_i - pos_i;
         const float D = P.particleDiameter;
         const unsigned maxK = (unsigned)P.maxNumNeighbors;
+        // The column walk is a chain of dependent loads (id -> predicted[id]); four ids and four gathers are kept in
+        // flight per trip.  Contributions are still accumulated in list order.
         const unsigned* col = neighbors + id;
-        for (unsigned k = 0; k < maxK; k++, col += N) {
-            const unsigned j = __ldg(col);
-            if (j > N) break;
-            const float4 pj4 = __ldg(predIn + j);
-            const float denom = w_i + pj4.w;
-            if (denom <= 0) continue;
-            const vec3 pred_j = V3(pj4);
-            const vec3 diff = pred_i - pred_j;
-            const float distance = length(diff);
-            if (distance >= D) continue;
-            const vec3 gradient = diff / (distance + VT_EPSILON);
-            const float lambda = (distance - D) / denom;
-            const vec3 common = lambda * gradient;
-            deltaCount++;
-            positionDelta -= w_i * common;
-            const vec3 relativeVelocity = vel_i - (pred_j - V3(__ldg(pos4 + j)));
-            positionDelta += w_i * compute_friction(P.friction, common, relativeVelocity);
+        bool done = false;
+        for (unsigned k0 = 0; k0 < maxK && !done; k0 += 4, col += 4 * (size_t)N) {
+            unsigned j[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) j[i] = (k0 + i < maxK) ? __ldg(col + (size_t)i * N) : 0xffffffffu;
+            float4 pj[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) pj[i] = (j[i] <= N) ? __ldg(predIn + (j[i] < N ? j[i] : 0)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (done) break;
+                if (j[i] > N) {  // terminator (or end of the table): the reference's `if (j > numParticles) break`
+                    done = true;
+                    break;
+                }
+                const float4 pj4 = pj[i];
+                const float denom = w_i + pj4.w;
+                if (denom <= 0) continue;
+                const vec3 pred_j = V3(pj4);
+                const vec3 diff = pred_i - pred_j;
+                const float distance = length(diff);
+                if (distance >= D) continue;
+                const vec3 gradient = diff / (distance + VT_EPSILON);
+                const float lambda = (distance - D) / denom;
+                const vec3 common = lambda * gradient;
+                deltaCount++;
+                positionDelta -= w_i * common;
+                const vec3 relativeVelocity = vel_i - (pred_j - V3(__ldg(pos4 + j[i])));
+                positionDelta += w_i * compute_friction(P.friction, common, relativeVelocity);
+            }
         }
         // ApplyDeltas_Kernel, L257-263
         const float count = (float)deltaCount;
