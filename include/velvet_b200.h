@@ -258,6 +258,14 @@ VELVET_API int velvet_cloth_object_start(VelvetSolver* s, int resolution, const 
                                          const unsigned* indices, const float* modelMatrix16,
                                          const int* attachedIndices, int numAttached, int* offset);
 
+/* Batched independent cloths (BASELINE config 4, "batched instances shard with no communication"): numInstances copies
+ * of one grid cloth of `resolution`, instance i placed by modelMatrices16 + 16*i.  Instances never interact (own hash-table
+ * rows, own neighbour lists, own attach slots) and share one constraint set built from instance 0.  Must be the only
+ * registration call on the handle; fused pipeline only.  Particle p of instance i is global particle i*(R+1)^2 + p. */
+VELVET_API int velvet_solver_add_cloth_instances(VelvetSolver* s, int resolution, const float* vertices,
+                                                 const unsigned* indices, const float* modelMatrices16, int numInstances,
+                                                 const int* attachedIndices, int numAttached);
+
 /* ---- SpatialHashGPU as its own object (SpatialHashGPU.hpp L15-60) */
 typedef struct VelvetSpatialHash VelvetSpatialHash;
 VELVET_API int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects,

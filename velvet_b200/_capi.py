@@ -65,7 +65,7 @@ EXPORTED_SYMBOLS = [
     "velvet_solver_synchronize", "velvet_solver_hash", "velvet_solver_buffer", "velvet_solver_download",
     "velvet_solver_upload", "velvet_solver_readback_async", "velvet_solver_stream",
     "velvet_solver_last_launch_count", "velvet_solver_simulate_timed", "velvet_generate_cloth_mesh",
-    "velvet_transform_matrix", "velvet_cloth_object_start", "velvet_hash_create", "velvet_hash_destroy",
+    "velvet_transform_matrix", "velvet_cloth_object_start", "velvet_solver_add_cloth_instances", "velvet_hash_create", "velvet_hash_destroy",
     "velvet_hash_set_initial_positions", "velvet_hash_hash", "velvet_hash_buffer",
 ]
 
@@ -140,6 +140,7 @@ def load():
         "velvet_generate_cloth_mesh": [i, v, v],
         "velvet_transform_matrix": [v, v, v, v],
         "velvet_cloth_object_start": [v, i, v, v, v, v, i, C.POINTER(i)],
+        "velvet_solver_add_cloth_instances": [v, i, v, v, v, i, v, i],
         "velvet_hash_create": [C.POINTER(v), f, i, f, i],
         "velvet_hash_destroy": [v],
         "velvet_hash_set_initial_positions": [v, v, C.c_size_t],

@@ -337,6 +337,15 @@ int velvet_cloth_object_start(VelvetSolver* s, int resolution, const float* vert
     VT_API_END
 }
 
+int velvet_solver_add_cloth_instances(VelvetSolver* s, int resolution, const float* vertices, const unsigned* indices,
+                                      const float* modelMatrices16, int numInstances, const int* attachedIndices, int numAttached)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.AddClothInstances(resolution, vertices, indices, modelMatrices16, numInstances, attachedIndices, numAttached);
+    VT_API_END
+}
+
 int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects, float hashCellSizeScalar,
                        int maxNumNeighbors)
 {

@@ -239,9 +239,13 @@ template <int LOG2T>
 #endif
 __global__ void __launch_bounds__(1 << LOG2T, (VT_IT_REGCAP_BLOCKS * 256) >> LOG2T)
 iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut, const TilePlanDev plan,
-                    const float* __restrict__ attachSlotPositions, const FrameParams* __restrict__ fp)
+                    const float* __restrict__ attachSlotPositions, const FrameParams* __restrict__ fp, const Instancing inst)
 {
     constexpr unsigned T = 1u << LOG2T;
+    // batched independent cloths: blockIdx.y selects the instance; the plan (tiles, records) is shared by all of them
+    predIn += (size_t)blockIdx.y * inst.particles;
+    predOut += (size_t)blockIdx.y * inst.particles;
+    attachSlotPositions += (size_t)blockIdx.y * inst.slots * 3;
     extern __shared__ float4 s_mem[];
     float4* sp = s_mem;
     float4* slots = s_mem + plan.maxLocals;
@@ -356,6 +360,8 @@ __global__ void __launch_bounds__(PB) normals_kernel(const float4* __restrict__ 
 {
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
+    pos4 += (size_t)blockIdx.y * n;  // instance (indices / CSR are per-instance local)
+    normalsOut += (size_t)blockIdx.y * n * 3;
     vec3 sum = V3(0, 0, 0);
     const unsigned t1 = __ldg(vtxTriOff + id + 1);
     for (unsigned t = __ldg(vtxTriOff + id); t < t1; t++) {
@@ -406,13 +412,14 @@ size_t iterate_smem_bytes(const TilePlanDev& plan)
 }
 
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
-                    const float* attachSlotPositions, const FrameParams* fp)
+                    const float* attachSlotPositions, const FrameParams* fp, Instancing inst)
 {
+    const dim3 grid(plan.numTiles, inst.count);
     const size_t smem = iterate_smem_bytes(plan);
     switch (plan.threads) {
-    case 128: iterate_tile_kernel<7><<<plan.numTiles, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
-    case 256: iterate_tile_kernel<8><<<plan.numTiles, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
-    case 512: iterate_tile_kernel<9><<<plan.numTiles, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp); break;
+    case 128: iterate_tile_kernel<7><<<grid, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst); break;
+    case 256: iterate_tile_kernel<8><<<grid, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst); break;
+    case 512: iterate_tile_kernel<9><<<grid, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst); break;
     default: throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
     }
 }
@@ -432,17 +439,18 @@ void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4
 }
 
 void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
-                    const unsigned* vtxTris, float* normalsOut)
+                    const unsigned* vtxTris, float* normalsOut, Instancing inst)
 {
-    normals_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(pos4, indices, vtxTriOff, vtxTris, normalsOut, L.numParticles);
+    normals_kernel<<<dim3(pgrid(inst.particles), inst.count), PB, 0, L.stream>>>(pos4, indices, vtxTriOff, vtxTris, normalsOut,
+                                                                                   inst.particles);
 }
 
 #if !VT_FAST_MATH  // the spatial hash is integer work: one (exact) build only
 void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
-                           int tableSize)
+                           int tableSizePerInstance, Instancing inst)
 {
     hash_particles_kernel<PosFloat4><<<pgrid(L.numParticles), PB, 0, L.stream>>>(keys, vals, PosFloat4{pred}, L.numParticles,
-                                                                                 cellSpacing, tableSize);
+                                                                                 cellSpacing, tableSizePerInstance, inst.particles);
 }
 
 void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash,
@@ -463,14 +471,14 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 
 bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedScratch, VtHashParams hp)
+                                   const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst)
 {
     if (hp.tableSize <= 0) return false;
     const unsigned n = L.numParticles;
     SortedParticle* sorted = reinterpret_cast<SortedParticle*>(sortedScratch);
     reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n);
     cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
-        neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize));
+        neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles);
     return true;
 }
 

@@ -37,7 +37,16 @@ constexpr int VT_MAX_TILE = 512;           // particles (= threads) per Jacobi t
 
 struct FusedLaunch {
     cudaStream_t stream;
-    unsigned numParticles;
+    unsigned numParticles;  // all instances together
+};
+
+// Batched independent cloths (BASELINE config 4): `count` copies of one cloth topology, `particles` particles each.
+// All instances share ONE tile plan / constraint set (it stays L2-resident) and differ only in their state, hash-table
+// rows and attach-slot positions.  A plain solver is {1, numParticles, numSlots}.
+struct Instancing {
+    unsigned count;
+    unsigned particles;
+    unsigned slots;  // attach slots per instance
 };
 
 // The floating-point kernels are compiled twice from the same source (fused_kernels.cu):
@@ -67,7 +76,7 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 
 // One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
-                    const float* attachSlotPositions, const FrameParams* fp);
+                    const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
 void configure_iterate_kernel(size_t smemBytes);  // opt in to > 48 KB dynamic shared memory
 
@@ -79,11 +88,11 @@ void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4
 
 // ComputeNormal as a per-vertex gather over incident triangles (ascending triangle id).
 void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
-                    const unsigned* vtxTris, float* normalsOut);
+                    const unsigned* vtxTris, float* normalsOut, Instancing inst);
 
 // spatial hash on float4 positions (keys/vals may be the alternate sort buffers)
 void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
-                           int tableSize);
+                           int tableSizePerInstance, Instancing inst);
 void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash,
                             int tableSize);
 void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
@@ -93,7 +102,8 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 // run (degenerate table); the caller then uses launch_cache_neighbors.
 bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp);
+                                   const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp,
+                                   Instancing inst);  // hp.tableSize = rows per instance
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
 
 }  // namespace exact_math
@@ -118,7 +128,7 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 
 // One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
-                    const float* attachSlotPositions, const FrameParams* fp);
+                    const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
 void configure_iterate_kernel(size_t smemBytes);  // opt in to > 48 KB dynamic shared memory
 
@@ -130,7 +140,7 @@ void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4
 
 // ComputeNormal as a per-vertex gather over incident triangles (ascending triangle id).
 void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
-                    const unsigned* vtxTris, float* normalsOut);
+                    const unsigned* vtxTris, float* normalsOut, Instancing inst);
 
 }  // namespace fast_math
 

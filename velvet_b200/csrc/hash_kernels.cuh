@@ -23,13 +23,18 @@ struct PosFloat4 {
 template <class Pos>
 __global__ void __launch_bounds__(256) hash_particles_kernel(unsigned* __restrict__ particleHash,
                                                              unsigned* __restrict__ particleIndex, Pos positions,
-                                                             unsigned n, float cellSpacing, int tableSize)
+                                                             unsigned n, float cellSpacing, int tableSize,
+                                                             unsigned instanceParticles)
 {
+    // Batched independent cloths: instance i = id / instanceParticles owns table rows [i*tableSize, (i+1)*tableSize), so
+    // one global sort orders every instance separately and instances never see each other's particles.  A single cloth
+    // (or several interacting cloths, the reference's case) is instance 0 with instanceParticles == n.
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
     const vec3 p = positions(id);
     particleHash[id] = (unsigned)hash_coords(int_coord(p.x, cellSpacing), int_coord(p.y, cellSpacing),
-                                             int_coord(p.z, cellSpacing), tableSize);
+                                             int_coord(p.z, cellSpacing), tableSize) +
+                       (id / instanceParticles) * (unsigned)tableSize;
     particleIndex[id] = id;
 }
 
@@ -161,12 +166,13 @@ constexpr int CN_THREADS = 256;
 // scattered 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
 static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
     unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
-    const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm)
+    const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles)
 {
     const unsigned t = blockIdx.x * CN_THREADS + threadIdx.x;
     if (t >= hp.numObjects) return;
     const float4 me = __ldg(&sorted[t].pos);
     const unsigned id = __float_as_uint(me.w);
+    const unsigned tableBase = (id / instanceParticles) * (unsigned)hp.tableSize;  // this instance's rows of the table
     const vec3 position = V3(me);
     const vec3 originalPos = V3(__ldg(&sorted[t].init));
     const int ix = int_coord(position.x, hp.cellSpacing);
@@ -183,7 +189,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
         const int hx = (b / 9) == 0 ? hx0 : (b / 9) == 1 ? hx1 : hx2;
         const int hy = ((b / 3) % 3) == 0 ? hy0 : ((b / 3) % 3) == 1 ? hy1 : hy2;
         const int hz = (b % 3) == 0 ? hz0 : (b % 3) == 1 ? hz1 : hz2;
-        if (__ldg(cellStart + hash_key_fast(hx, hy, hz, fm)) != 0xffffffffu) mask |= 1u << b;
+        if (__ldg(cellStart + tableBase + hash_key_fast(hx, hy, hz, fm)) != 0xffffffffu) mask |= 1u << b;
     }
 
     // phase 2: walk the non-empty buckets in traversal order
@@ -198,7 +204,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
         const int hx = a == 0 ? hx0 : a == 1 ? hx1 : hx2;
         const int hy = m == 0 ? hy0 : m == 1 ? hy1 : hy2;
         const int hz = c == 0 ? hz0 : c == 1 ? hz1 : hz2;
-        const unsigned key = hash_key_fast(hx, hy, hz, fm);
+        const unsigned key = tableBase + hash_key_fast(hx, hy, hz, fm);
         unsigned cur = __ldg(cellStart + key);
         unsigned end = __ldg(cellEnd + key);
         if (cur + K < end) end = cur + K;

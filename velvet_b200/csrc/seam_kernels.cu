@@ -371,7 +371,7 @@ void HashObjects(unsigned* particleHash, unsigned* particleIndex, unsigned* cell
     unsigned* v0 = odd ? g_valsAlt.data() : particleIndex;
     unsigned* k1 = odd ? particleHash : g_keysAlt.data();
     unsigned* v1 = odd ? particleIndex : g_valsAlt.data();
-    hash_particles_kernel<PosPacked3><<<grid_for(n), BLOCK, 0, st>>>(k0, v0, PosPacked3{positions}, n, hp.cellSpacing, hp.tableSize);
+    hash_particles_kernel<PosPacked3><<<grid_for(n), BLOCK, 0, st>>>(k0, v0, PosPacked3{positions}, n, hp.cellSpacing, hp.tableSize, n);
     g_sorter.sort(k0, v0, k1, v1, n, maxBit, st);
     VT_CUDA(cudaMemsetAsync(cellStart, 0xff, sizeof(unsigned) * (size_t)hp.tableSize, st));
     find_cell_start_kernel<<<grid_for(n), BLOCK, 0, st>>>(cellStart, cellEnd, particleHash, n);

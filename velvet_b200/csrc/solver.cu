@@ -187,6 +187,7 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
 {
     if (!vertices || numVertices <= 0 || !modelMatrix16 || numIndices < 0 || (numIndices && !meshIndices))
         throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddCloth: bad argument");
+    if (m_instanced) throw Error(VELVET_ERR_STATE, "AddCloth: the solver holds batched instances (AddClothInstances)");
     VT_CUDA(cudaSetDevice(m_device));
     Synchronize();
     const int prevNumParticles = (int)simParams.numParticles;
@@ -221,6 +222,66 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
     m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
     invalidate();
     return prevNumParticles;
+}
+
+void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uint* meshIndices, const float* models,
+                                         int numInstances, const int* attachedIndices, int numAttached)
+{
+    if (R <= 0 || !vertices || !meshIndices || !models || numInstances <= 0 || numAttached < 0 || (numAttached && !attachedIndices))
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: bad argument");
+    if (numInstances > 65535) throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: at most 65535 instances");
+    if (simParams.numParticles != 0) throw Error(VELVET_ERR_STATE, "AddClothInstances must be the only registration on a solver");
+    VT_CUDA(cudaSetDevice(m_device));
+    Synchronize();
+    const size_t n = (size_t)(R + 1) * (R + 1);
+    const size_t ni = (size_t)6 * R * R;
+    const size_t total = n * (size_t)numInstances;
+    if (total >= (1ull << 31)) throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: too many particles");
+    const std::vector<int> attached(attachedIndices, attachedIndices + numAttached);
+    for (int a : attached)
+        if (a < 0 || (size_t)a >= n) throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: attached index out of range");
+
+    const GridConstraints g = GenerateGridConstraints(R, vertices, meshIndices, models, attached, simParams.particleDiameterScalar, 0);
+    simParams.numParticles = (uint)total;
+    simParams.particleDiameter = g.particleDiameter;
+    simParams.deltaTime = kFixedDeltaTime;
+    simParams.maxSpeed = 2 * g.particleDiameter / kFixedDeltaTime * simParams.numSubsteps;
+
+    // state for every instance; mesh indices / constraints once (per-instance local indices)
+    for (int k = 0; k < numInstances; k++) {
+        positions.registerNewBuffer(reinterpret_cast<const vec3*>(vertices), n);
+        normals.registerNewBuffer(nullptr, n);
+    }
+    indices.append(meshIndices, ni);
+    velocities.push_back(total, V3(0, 0, 0));
+    predicted.push_back(total, V3(0, 0, 0));
+    deltas.push_back(total, V3(0, 0, 0));
+    deltaCounts.push_back(total, 0);
+    invMasses.push_back(total, 1.0f);
+    for (int k = 0; k < numInstances; k++)
+        seam::InitializePositions(reinterpret_cast<float*>(positions.data()), (int)(k * n), (int)n, models + 16 * (size_t)k, m_stream);
+    Synchronize();
+
+    stretchIndices.append(g.stretchIdx.data(), g.stretchIdx.size());
+    stretchLengths.append(g.stretchLen.data(), g.stretchLen.size());
+    bendIndices.append(g.bendIdx.data(), g.bendIdx.size());
+    bendAngles.append(g.bendAngle.data(), g.bendAngle.size());
+    attachParticleIDs.append(g.attachPid.data(), g.attachPid.size());
+    attachSlotIDs.append(g.attachSlot.data(), g.attachSlot.size());
+    attachDistances.append(g.attachDist.data(), g.attachDist.size());
+    // slot positions of every instance: the world position of the attached vertex under that instance's matrix
+    for (int k = 0; k < numInstances; k++)
+        for (int a : attached) attachSlotPositions.push_back(positions[k * n + (size_t)a]);
+    for (size_t c = 0; c < g.attachDist.size(); c++)
+        if (g.attachDist[c] == 0)  // hpp L172, in every instance
+            for (int k = 0; k < numInstances; k++) invMasses[k * n + (size_t)g.attachPid[c]] = 0;
+
+    m_spatialHash = std::make_shared<SpatialHashGPU>(g.particleDiameter, (int)total, simParams.hashCellSizeScalar,
+                                                     simParams.maxNumNeighbors);
+    m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
+    m_instancing = Instancing{(uint)numInstances, (uint)n, (uint)numAttached};
+    m_instanced = true;
+    invalidate();
 }
 
 void VtClothSolverGPU::AddStretch(int idx1, int idx2, float distance)
@@ -378,6 +439,8 @@ void VtClothSolverGPU::ensureFusedResources()
     if (!m_topologyDirty) return;
     Synchronize();
     const uint N = simParams.numParticles;
+    if (!m_instanced) m_instancing = Instancing{1u, N, (uint)attachSlotPositions.size()};
+    const uint planN = m_instancing.particles;  // the tile plan / vertex CSR cover one instance
     m_fusedUsable = false;
     m_fallbackReason.clear();
     if (m_graphExec) {
@@ -395,7 +458,7 @@ void VtClothSolverGPU::ensureFusedResources()
     }
 
     const int tileSize = m_tileSize ? m_tileSize : 256;  // power of two: the kernel is specialised on log2(tile)
-    m_plan = build_tile_plan(N, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), stretchIndices.data(),
+    m_plan = build_tile_plan(planN, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), stretchIndices.data(),
                              stretchLengths.data(), stretchLengths.size(), bendIndices.data(), bendAngles.data(),
                              bendAngles.size(), attachParticleIDs.data(), attachSlotIDs.data(), attachDistances.data(),
                              attachParticleIDs.size(), tileSize);
@@ -404,12 +467,12 @@ void VtClothSolverGPU::ensureFusedResources()
         return;
     }
     for (size_t i = 0; i < attachSlotIDs.size(); i++)
-        if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= attachSlotPositions.size()) {
+        if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= (size_t)m_instancing.slots) {
             m_fallbackReason = "attach slot index out of range";
             return;
         }
     for (size_t i = 0; i < indices.size(); i++)
-        if (indices[i] >= N) {
+        if (indices[i] >= planN) {
             m_fallbackReason = "triangle index out of range";
             return;
         }
@@ -452,9 +515,9 @@ void VtClothSolverGPU::ensureFusedResources()
     // vertex -> incident triangles, ascending triangle id
     {
         const size_t T = indices.size() / 3;
-        std::vector<uint> off((size_t)N + 1, 0), tris(3 * T);
+        std::vector<uint> off((size_t)planN + 1, 0), tris(3 * T);
         for (size_t i = 0; i < 3 * T; i++) off[indices[i] + 1]++;
-        for (uint v = 0; v < N; v++) off[v + 1] += off[v];
+        for (uint v = 0; v < planN; v++) off[v + 1] += off[v];
         std::vector<uint> cur(off.begin(), off.end() - 1);
         for (size_t tIdx = 0; tIdx < T; tIdx++)
             for (int k = 0; k < 3; k++) tris[cur[indices[3 * tIdx + k]]++] = (uint)tIdx;
@@ -559,7 +622,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
             STAGE_BEGIN(t, "Solver_HashParticle");
-            exact_math::launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize());
+            exact_math::launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing);
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashSort");
@@ -571,12 +634,13 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashCache");
+            VtHashParams hp = H.MakeParams(N, P.particleDiameter);
+            hp.tableSize = H.tableSize() / (int)m_instancing.count;  // rows per instance
             if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
-                                              m_sorted, H.MakeParams(N, P.particleDiameter))) {
+                                                          m_sorted, hp, m_instancing)) {
                 launches += 2;
             } else {
-                exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
-                                       H.MakeParams(N, P.particleDiameter));
+                exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4, hp);
                 launches++;
             }
             STAGE_END(t);
@@ -589,7 +653,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
 
         STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
         for (int iteration = 0; iteration < P.numIterations; iteration++) {
-            ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp);
+            ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp, m_instancing);
             launches++;
             std::swap(cur, other);
         }
@@ -604,7 +668,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
         STAGE_END(t);
     }
     STAGE_BEGIN(t, "Solver_UpdateNormals");
-    ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()));
+    ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()), m_instancing);
     launches++;
     STAGE_END(t);
     VT_CUDA(cudaGetLastError());
@@ -628,6 +692,9 @@ void VtClothSolverGPU::Simulate(float frameTime)
         if (!m_fusedUsable || sdfColliders.size() > VT_MAX_COLLIDERS) fused = false;
     }
     if (!fused) {
+        if (m_instanced)
+            throw Error(VELVET_ERR_UNSUPPORTED, "batched instances need the fused pipeline (" +
+                                                    (m_fallbackReason.empty() ? std::string("seam pipeline selected") : m_fallbackReason) + ")");
         simulateSeam(frameTime, nullptr);
         return;
     }
@@ -677,6 +744,7 @@ StageTiming VtClothSolverGPU::SimulateTimed()
         ensureFusedResources();
         if (!m_fusedUsable || sdfColliders.size() > VT_MAX_COLLIDERS) fused = false;
     }
+    if (!fused && m_instanced) throw Error(VELVET_ERR_UNSUPPORTED, "batched instances need the fused pipeline");
     timing.begin("Solver_Total");
     if (!fused) {
         simulateSeam(kFixedDeltaTime, &timing);
@@ -841,16 +909,15 @@ void MakeCollider(int type, const float* position3, const float* scale3, const f
 
 // ------------------------------------------------------------------------------------------------ VtClothObjectGPU
 
-void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, const float* M)
+GridConstraints GenerateGridConstraints(int R, const float* vertices, const uint* meshIndices, const float* M,
+                                        const std::vector<int>& attachedIndices, float particleDiameterScalar, int off)
 {
-    const int R = m_resolution;
+    GridConstraints g;
     const int side = R + 1;
     const size_t nv = (size_t)side * side;
     const size_t ni = (size_t)6 * R * R;
     auto vtx = [&](size_t i) { return load3(vertices, i); };
-    m_particleDiameter = length(vtx(0) - vtx(1)) * m_solver->simParams.particleDiameterScalar;  // L49
-    m_indexOffset = m_solver->AddCloth(vertices, (int)nv, meshIndices, (int)ni, M, m_particleDiameter);
-    const int off = m_indexOffset;
+    g.particleDiameter = length(vtx(0) - vtx(1)) * particleDiameterScalar;  // VtClothObjectGPU.hpp L49
 
     // ApplyTransform (L67-73): host copy of the world-space positions, used for rest lengths only
     std::vector<vec3> world(nv);
@@ -859,14 +926,12 @@ void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, con
     auto at = [side](int x, int y) { return x * side + y; };
 
     // GenerateStretch (L75-116): structural (y, x) then the two shear diagonals, in that emission order
-    std::vector<int> sIdx;
-    std::vector<float> sLen;
-    sIdx.reserve(2 * (size_t)(4 * R * R + 2 * R));
-    sLen.reserve((size_t)(4 * R * R + 2 * R));
+    g.stretchIdx.reserve(2 * (size_t)(4 * R * R + 2 * R));
+    g.stretchLen.reserve((size_t)(4 * R * R + 2 * R));
     auto emit = [&](int a, int b) {
-        sIdx.push_back(off + a);
-        sIdx.push_back(off + b);
-        sLen.push_back(dist(a, b));
+        g.stretchIdx.push_back(off + a);
+        g.stretchIdx.push_back(off + b);
+        g.stretchLen.push_back(dist(a, b));
     };
     for (int x = 0; x < side; x++)
         for (int y = 0; y < side; y++) {
@@ -877,35 +942,49 @@ void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, con
                 emit(at(x, y + 1), at(x + 1, y));
             }
         }
-    m_solver->AddStretchBulk(sIdx.data(), sLen.data(), sLen.size());
 
     // GenerateAttach (L134-148): every particle gets a long-range attachment to every slot
-    for (size_t slot = 0; slot < m_attachedIndices.size(); slot++) {
-        const vec3 slotPos = world[(size_t)m_attachedIndices[slot]];
-        const float sp[3] = {slotPos.x, slotPos.y, slotPos.z};
-        m_solver->AddAttachSlot(sp);
-        std::vector<int> pid(nv), sid(nv, (int)slot);
-        std::vector<float> d(nv);
+    for (size_t slot = 0; slot < attachedIndices.size(); slot++) {
+        const vec3 slotPos = world[(size_t)attachedIndices[slot]];
+        g.slotPositions.push_back(slotPos.x);
+        g.slotPositions.push_back(slotPos.y);
+        g.slotPositions.push_back(slotPos.z);
         for (size_t i = 0; i < nv; i++) {
-            pid[i] = off + (int)i;
-            d[i] = length(slotPos - world[i]);
+            g.attachPid.push_back(off + (int)i);
+            g.attachSlot.push_back((int)slot);
+            g.attachDist.push_back(length(slotPos - world[i]));
         }
-        m_solver->AddAttachBulk(pid.data(), sid.data(), d.data(), nv);
     }
 
     // GenerateBending (L118-132): one dihedral per quad, indices (i, i+5, i+2, i+1), rest angle 0
-    std::vector<uint> bIdx;
-    std::vector<float> bAng;
-    bIdx.reserve(4 * (size_t)R * R);
-    bAng.reserve((size_t)R * R);
+    g.bendIdx.reserve(4 * (size_t)R * R);
+    g.bendAngle.reserve((size_t)R * R);
     for (size_t i = 0; i + 5 < ni; i += 6) {
-        bIdx.push_back((uint)off + meshIndices[i]);
-        bIdx.push_back((uint)off + meshIndices[i + 5]);
-        bIdx.push_back((uint)off + meshIndices[i + 2]);
-        bIdx.push_back((uint)off + meshIndices[i + 1]);
-        bAng.push_back(0.0f);
+        g.bendIdx.push_back((uint)off + meshIndices[i]);
+        g.bendIdx.push_back((uint)off + meshIndices[i + 5]);
+        g.bendIdx.push_back((uint)off + meshIndices[i + 2]);
+        g.bendIdx.push_back((uint)off + meshIndices[i + 1]);
+        g.bendAngle.push_back(0.0f);
     }
-    m_solver->AddBendBulk(bIdx.data(), bAng.data(), bAng.size());
+    return g;
+}
+
+void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, const float* M)
+{
+    const int R = m_resolution;
+    const size_t nv = (size_t)(R + 1) * (R + 1);
+    const size_t ni = (size_t)6 * R * R;
+    m_particleDiameter = length(load3(vertices, 0) - load3(vertices, 1)) * m_solver->simParams.particleDiameterScalar;  // L49
+    m_indexOffset = m_solver->AddCloth(vertices, (int)nv, meshIndices, (int)ni, M, m_particleDiameter);
+    const GridConstraints g = GenerateGridConstraints(R, vertices, meshIndices, M, m_attachedIndices,
+                                                      m_solver->simParams.particleDiameterScalar, m_indexOffset);
+    m_solver->AddStretchBulk(g.stretchIdx.data(), g.stretchLen.data(), g.stretchLen.size());
+    // AddAttachSlot then that slot's AddAttach calls, slot by slot (L134-148)
+    for (size_t slot = 0; slot < m_attachedIndices.size(); slot++) {
+        m_solver->AddAttachSlot(&g.slotPositions[3 * slot]);
+        m_solver->AddAttachBulk(&g.attachPid[slot * nv], &g.attachSlot[slot * nv], &g.attachDist[slot * nv], nv);
+    }
+    m_solver->AddBendBulk(g.bendIdx.data(), g.bendAngle.data(), g.bendAngle.size());
 }
 
 }  // namespace velvet

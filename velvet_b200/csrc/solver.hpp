@@ -81,6 +81,15 @@ public:
     void Synchronize();
     void OnDestroy();  // L50-54
 
+    // Batched independent cloths (north_star mode 1 / BASELINE config 4): `numInstances` copies of one grid cloth of
+    // `resolution`, instance i placed by modelMatrices16[i].  Instances never interact: each has its own rows of the
+    // hash table, its own neighbour lists and attach-slot positions; they share ONE constraint set / tile plan, built
+    // from instance 0 (rest lengths are those of instance 0's world-space mesh).  Must be the only registration call
+    // on the solver; fused pipeline only.  Particle i of instance k is global particle k * (R+1)^2 + i.
+    void AddClothInstances(int resolution, const float* vertices, const uint* meshIndices, const float* modelMatrices16,
+                           int numInstances, const int* attachedIndices, int numAttached);
+    int numInstances() const { return (int)m_instancing.count; }
+
     // bulk variants (one memcpy instead of a managed-memory push_back per element)
     void AddStretchBulk(const int* idxPairs, const float* distances, size_t n);
     void AddBendBulk(const uint* idxQuads, const float* angles, size_t n);
@@ -137,6 +146,8 @@ private:
     int m_pipeline = 0;
     int m_tileSize = 0;
     int m_mathMode = VELVET_MATH_EXACT;
+    Instancing m_instancing{1, 0, 0};
+    bool m_instanced = false;
     int m_lastLaunches = 0;
     std::shared_ptr<SpatialHashGPU> m_spatialHash;
 
@@ -184,6 +195,20 @@ private:
     std::vector<int> m_attachedIndices;
     float m_particleDiameter = 0;
 };
+
+// The constraint lists VtClothObjectGPU::Start generates for a grid cloth (VtClothObjectGPU.hpp L75-148), as arrays.
+struct GridConstraints {
+    float particleDiameter = 0;
+    std::vector<int> stretchIdx;
+    std::vector<float> stretchLen;
+    std::vector<uint> bendIdx;
+    std::vector<float> bendAngle;
+    std::vector<float> slotPositions;  // 3 per attach slot
+    std::vector<int> attachPid, attachSlot;
+    std::vector<float> attachDist;
+};
+GridConstraints GenerateGridConstraints(int resolution, const float* vertices, const uint* meshIndices, const float* modelMatrix16,
+                                        const std::vector<int>& attachedIndices, float particleDiameterScalar, int indexOffset);
 
 // Scene.hpp L131-168, Transform.hpp L22-29 (+ Helper.cpp L8-15), glm::inverse, VtClothSolverGPU.hpp L195-203
 void GenerateClothMesh(int resolution, float* vertices, uint* meshIndices);

@@ -134,6 +134,15 @@ class VtClothSolverGPU:
     def AddBend(self, idx1: int, idx2: int, idx3: int, idx4: int, angle: float = 0.0):
         check(self._L.velvet_solver_add_bend(self._h, idx1, idx2, idx3, idx4, float(np.float32(angle))))
 
+    def AddClothInstances(self, resolution: int, vertices, indices, modelMatrices, attached=()):
+        """Batched independent cloths: one grid cloth topology, len(modelMatrices) instances (see velvet_b200.h)."""
+        vertices = np.ascontiguousarray(vertices, np.float32)
+        indices = np.ascontiguousarray(indices, np.uint32)
+        models = np.ascontiguousarray(modelMatrices, np.float32).reshape(-1, 16)
+        att = np.asarray(list(attached), np.int32)
+        check(self._L.velvet_solver_add_cloth_instances(self._h, resolution, _ptr(vertices), _ptr(indices), _ptr(models),
+                                                        len(models), _ptr(att), len(att)))
+
     def UpdateColliders(self, colliders):
         arr = _collider_array(colliders)
         check(self._L.velvet_solver_update_colliders(self._h, C.cast(arr, C.c_void_p), len(colliders)))
