@@ -266,6 +266,41 @@ VELVET_API int velvet_solver_add_cloth_instances(VelvetSolver* s, int resolution
                                                  const unsigned* indices, const float* modelMatrices16, int numInstances,
                                                  const int* attachedIndices, int numAttached);
 
+/* ---- One large cloth decomposed over several GPUs (north_star mode 2).  Every rank (one process per GPU) registers the
+ * same cloth on its own handle and calls velvet_solver_dd_setup(rank, world); rank r then owns a contiguous range of the
+ * Morton-ordered Jacobi tiles.  A frame is driven step by step with velvet_solver_dd_step; the caller moves the bytes:
+ *   ITERATE_OWNED  -> send sendBuf[sendOffsets[q] .. sendOffsets[q+1]) to rank q, receive recvBuf[recvOffsets[q] ..) from q
+ *   ITERATE_FINISH
+ *   GATHER_PACK    -> all-gather gatherSend (maxOwnedCount float4 per rank) into gatherRecv -> GATHER_UNPACK
+ * (torch.distributed/NCCL in velvet_b200/decomposed.py).  Results are bit-identical to the single-GPU solver. */
+typedef enum VelvetDDOp {
+    VELVET_DD_FRAME_BEGIN = 0,   /* arg unused, farg = frame time                                   */
+    VELVET_DD_SUBSTEP_BEGIN = 1, /* arg = substep: [hash rebuild] + collide (replicated)            */
+    VELVET_DD_ITERATE_OWNED = 2, /* Jacobi iteration on the owned tiles + pack of the boundary      */
+    VELVET_DD_ITERATE_FINISH = 3,/* unpack of the received halo                                      */
+    VELVET_DD_GATHER_PACK = 4,
+    VELVET_DD_GATHER_UNPACK = 5,
+    VELVET_DD_SUBSTEP_END = 6,   /* arg = substep: Finalize (+ next Predict / export)                */
+    VELVET_DD_FRAME_END = 7      /* normals                                                          */
+} VelvetDDOp;
+typedef struct VelvetDDInfo {
+    int rank, world;
+    unsigned tileBegin, tileEnd, numTiles;
+    unsigned ownedCount, maxOwnedCount; /* particles owned by this rank / the largest such count        */
+    unsigned sendTotal, recvTotal;      /* float4 elements in sendBuf / recvBuf                          */
+    void *sendBuf, *recvBuf, *gatherSend, *gatherRecv; /* device pointers, float4 elements              */
+} VelvetDDInfo;
+VELVET_API int velvet_solver_dd_setup(VelvetSolver* s, int rank, int world);
+VELVET_API int velvet_solver_dd_info(VelvetSolver* s, VelvetDDInfo* out);
+/* per-peer element offsets into sendBuf / recvBuf: arrays of world + 1 entries */
+VELVET_API int velvet_solver_dd_offsets(VelvetSolver* s, unsigned* sendOffsets, unsigned* recvOffsets);
+VELVET_API int velvet_solver_dd_step(VelvetSolver* s, int op, int arg, float farg);
+/* Host-only: the exchange lists of `rank` for a grid cloth of `resolution` cut into `world` ranks with tiles of
+ * `tileSize` particles (what dd_setup computes), for tests without a GPU.  ids arrays may be NULL to query counts only:
+ * counts[q] / counts[world + q] = number of particle ids sent to / received from rank q. */
+VELVET_API int velvet_dd_plan_grid(int resolution, int tileSize, int rank, int world, unsigned* counts, unsigned* sendIds,
+                                   unsigned* recvIds, unsigned* ownedRange2);
+
 /* ---- SpatialHashGPU as its own object (SpatialHashGPU.hpp L15-60) */
 typedef struct VelvetSpatialHash VelvetSpatialHash;
 VELVET_API int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects,

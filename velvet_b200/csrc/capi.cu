@@ -346,6 +346,106 @@ int velvet_solver_add_cloth_instances(VelvetSolver* s, int resolution, const flo
     VT_API_END
 }
 
+int velvet_solver_dd_setup(VelvetSolver* s, int rank, int world)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.ddSetup(rank, world);
+    VT_API_END
+}
+
+int velvet_solver_dd_info(VelvetSolver* s, VelvetDDInfo* out)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && out, "bad argument");
+    const ExchangePlan& x = s->impl.ddPlan();
+    const VtClothSolverGPU::DDBuffers b = s->impl.ddBuffers();
+    out->rank = x.rank;
+    out->world = x.world;
+    out->tileBegin = x.tileBegin;
+    out->tileEnd = x.tileEnd;
+    out->numTiles = (unsigned)s->impl.tilePlan().tiles.size();
+    out->ownedCount = b.ownedCount;
+    out->maxOwnedCount = b.maxOwnedCount;
+    out->sendTotal = b.sendTotal;
+    out->recvTotal = b.recvTotal;
+    out->sendBuf = b.sendBuf;
+    out->recvBuf = b.recvBuf;
+    out->gatherSend = b.gatherSend;
+    out->gatherRecv = b.gatherRecv;
+    VT_API_END
+}
+
+int velvet_solver_dd_offsets(VelvetSolver* s, unsigned* sendOffsets, unsigned* recvOffsets)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && sendOffsets && recvOffsets, "bad argument");
+    s->impl.ddBuffers();  // throws unless set up
+    const ExchangePlan& x = s->impl.ddPlan();
+    unsigned so = 0, ro = 0;
+    for (int q = 0; q < x.world; q++) {
+        sendOffsets[q] = so;
+        recvOffsets[q] = ro;
+        so += (unsigned)x.sendIds[q].size();
+        ro += (unsigned)x.recvIds[q].size();
+    }
+    sendOffsets[x.world] = so;
+    recvOffsets[x.world] = ro;
+    VT_API_END
+}
+
+int velvet_solver_dd_step(VelvetSolver* s, int op, int arg, float farg)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    switch (op) {
+    case VELVET_DD_FRAME_BEGIN: s->impl.ddFrameBegin(farg > 0 ? farg : kFixedDeltaTime); break;
+    case VELVET_DD_SUBSTEP_BEGIN: s->impl.ddSubstepBegin(arg); break;
+    case VELVET_DD_ITERATE_OWNED: s->impl.ddIterateOwned(); break;
+    case VELVET_DD_ITERATE_FINISH: s->impl.ddIterateFinish(); break;
+    case VELVET_DD_GATHER_PACK: s->impl.ddGatherPack(); break;
+    case VELVET_DD_GATHER_UNPACK: s->impl.ddGatherUnpack(); break;
+    case VELVET_DD_SUBSTEP_END: s->impl.ddSubstepEnd(arg); break;
+    case VELVET_DD_FRAME_END: s->impl.ddFrameEnd(); break;
+    default: return set_error(VELVET_ERR_INVALID_ARGUMENT, "unknown decomposition step");
+    }
+    VT_API_END
+}
+
+int velvet_dd_plan_grid(int resolution, int tileSize, int rank, int world, unsigned* counts, unsigned* sendIds, unsigned* recvIds,
+                        unsigned* ownedRange2)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(resolution > 0 && world > 0 && rank >= 0 && rank < world && counts, "dd_plan_grid: bad argument");
+    const int R = resolution;
+    const size_t n = (size_t)(R + 1) * (R + 1);
+    std::vector<float> v(3 * n);
+    std::vector<unsigned> idx((size_t)6 * R * R);
+    GenerateClothMesh(R, v.data(), idx.data());
+    const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const GridConstraints g = GenerateGridConstraints(R, v.data(), idx.data(), identity, {}, 1.5f, 0);
+    const TilePlan plan = build_tile_plan((unsigned)n, v.data(), g.stretchIdx.data(), g.stretchLen.data(), g.stretchLen.size(),
+                                          g.bendIdx.data(), g.bendAngle.data(), g.bendAngle.size(), nullptr, nullptr, nullptr, 0,
+                                          tileSize ? tileSize : 256);
+    if (!plan.valid) return set_error(VELVET_ERR_UNSUPPORTED, plan.whyInvalid);
+    VT_REQUIRE((size_t)world <= plan.tiles.size(), "dd_plan_grid: more ranks than tiles");
+    const ExchangePlan x = build_exchange_plan(plan, (unsigned)n, rank, world);
+    size_t so = 0, ro = 0;
+    for (int q = 0; q < world; q++) {
+        counts[q] = (unsigned)x.sendIds[q].size();
+        counts[world + q] = (unsigned)x.recvIds[q].size();
+        if (sendIds) std::memcpy(sendIds + so, x.sendIds[q].data(), 4 * x.sendIds[q].size());
+        if (recvIds) std::memcpy(recvIds + ro, x.recvIds[q].data(), 4 * x.recvIds[q].size());
+        so += x.sendIds[q].size();
+        ro += x.recvIds[q].size();
+    }
+    if (ownedRange2) {
+        ownedRange2[0] = x.tileBegin * (unsigned)plan.tileSize;
+        ownedRange2[1] = (unsigned)std::min<size_t>((size_t)x.tileEnd * plan.tileSize, n);
+    }
+    VT_API_END
+}
+
 int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects, float hashCellSizeScalar,
                        int maxNumNeighbors)
 {

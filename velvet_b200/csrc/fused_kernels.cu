@@ -374,6 +374,20 @@ __global__ void __launch_bounds__(PB) normals_kernel(const float4* __restrict__ 
     store3(normalsOut, id, normalize(sum));
 }
 
+__global__ void __launch_bounds__(PB) gather_by_id_kernel(const float4* __restrict__ src, const unsigned* __restrict__ ids, unsigned n,
+                                                          float4* __restrict__ out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[ids[i]];
+}
+
+__global__ void __launch_bounds__(PB) scatter_by_id_kernel(const float4* __restrict__ in, const unsigned* __restrict__ ids, unsigned n,
+                                                           float4* __restrict__ dst)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[ids[i]] = in[i];
+}
+
 __global__ void __launch_bounds__(PB) pack_float4_kernel(const float* __restrict__ packed3, float4* __restrict__ out, unsigned n)
 {
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,6 +499,16 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n)
 {
     if (n) pack_float4_kernel<<<pgrid(n), PB, 0, L.stream>>>(packed3, out, n);
+}
+
+void launch_gather_by_id(const FusedLaunch& L, const float4* src, const unsigned* ids, unsigned n, float4* out)
+{
+    if (n) gather_by_id_kernel<<<pgrid(n), PB, 0, L.stream>>>(src, ids, n, out);
+}
+
+void launch_scatter_by_id(const FusedLaunch& L, const float4* in, const unsigned* ids, unsigned n, float4* dst)
+{
+    if (n) scatter_by_id_kernel<<<pgrid(n), PB, 0, L.stream>>>(in, ids, n, dst);
 }
 #endif
 

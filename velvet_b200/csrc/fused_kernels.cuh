@@ -105,6 +105,9 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
                                    const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp,
                                    Instancing inst);  // hp.tableSize = rows per instance
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
+// halo exchange plumbing of the domain-decomposed mode: out[i] = src[ids[i]]  /  dst[ids[i]] = in[i]
+void launch_gather_by_id(const FusedLaunch& L, const float4* src, const unsigned* ids, unsigned n, float4* out);
+void launch_scatter_by_id(const FusedLaunch& L, const float4* in, const unsigned* ids, unsigned n, float4* dst);
 
 }  // namespace exact_math
 

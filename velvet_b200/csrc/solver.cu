@@ -675,6 +675,163 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
     m_graphLaunches = launches;
 }
 
+// ------------------------------------------------------------------------------------------------ domain decomposition
+
+void VtClothSolverGPU::ddSetup(int rank, int world)
+{
+    if (world < 1 || rank < 0 || rank >= world) throw Error(VELVET_ERR_INVALID_ARGUMENT, "ddSetup: bad rank/world");
+    if (m_instanced) throw Error(VELVET_ERR_UNSUPPORTED, "ddSetup: batched instances are sharded, not decomposed");
+    VT_CUDA(cudaSetDevice(m_device));
+    if (simParams.numParticles == 0) throw Error(VELVET_ERR_STATE, "ddSetup: no cloth registered");
+    ensureFusedResources();
+    if (!m_fusedUsable) throw Error(VELVET_ERR_UNSUPPORTED, "ddSetup: the fused pipeline is unavailable (" + m_fallbackReason + ")");
+    if ((unsigned)world > m_plan.tiles.size()) throw Error(VELVET_ERR_INVALID_ARGUMENT, "ddSetup: more ranks than tiles");
+    const uint N = simParams.numParticles;
+    m_dd = build_exchange_plan(m_plan, N, rank, world);
+    const unsigned T = (unsigned)m_plan.tileSize;
+    m_ddOwnedBegin.assign(world, 0);
+    m_ddOwnedCount.assign(world, 0);
+    m_ddMaxOwned = 0;
+    for (int r = 0; r < world; r++) {
+        m_ddOwnedBegin[r] = m_dd.tileBeginOf[r] * T;
+        const unsigned end = std::min<unsigned long long>((unsigned long long)m_dd.tileBeginOf[r + 1] * T, N);
+        m_ddOwnedCount[r] = end - m_ddOwnedBegin[r];
+        m_ddMaxOwned = std::max(m_ddMaxOwned, m_ddOwnedCount[r]);
+    }
+    std::vector<uint> sendIds, recvIds;
+    m_ddSendOff.assign(world + 1, 0);
+    m_ddRecvOff.assign(world + 1, 0);
+    for (int q = 0; q < world; q++) {
+        sendIds.insert(sendIds.end(), m_dd.sendIds[q].begin(), m_dd.sendIds[q].end());
+        recvIds.insert(recvIds.end(), m_dd.recvIds[q].begin(), m_dd.recvIds[q].end());
+        m_ddSendOff[q + 1] = (unsigned)sendIds.size();
+        m_ddRecvOff[q + 1] = (unsigned)recvIds.size();
+    }
+    if (sendIds.empty()) sendIds.push_back(0);
+    if (recvIds.empty()) recvIds.push_back(0);
+    m_ddSendIds.upload(sendIds, m_stream);
+    m_ddRecvIds.upload(recvIds, m_stream);
+    m_ddSendBuf.allocate(std::max<size_t>(m_ddSendOff[world], 1));
+    m_ddRecvBuf.allocate(std::max<size_t>(m_ddRecvOff[world], 1));
+    m_ddGatherSend.allocate(m_ddMaxOwned);
+    m_ddGatherRecv.allocate((size_t)m_ddMaxOwned * world);
+    Synchronize();
+    m_ddReady = true;
+}
+
+VtClothSolverGPU::DDBuffers VtClothSolverGPU::ddBuffers() const
+{
+    if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
+    return DDBuffers{m_ddSendBuf.data(), m_ddRecvBuf.data(), m_ddGatherSend.data(), m_ddGatherRecv.data(),
+                     m_ddSendOff[m_dd.world], m_ddRecvOff[m_dd.world], m_ddOwnedCount[m_dd.rank], m_ddMaxOwned};
+}
+
+void VtClothSolverGPU::ddFrameBegin(float frameTime)
+{
+    if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
+    VT_CUDA(cudaSetDevice(m_device));
+    if (m_topologyDirty) throw Error(VELVET_ERR_STATE, "the cloth changed after ddSetup: call ddSetup again");
+    FrameParams hp;
+    hp.P = simParams;
+    hp.frameTime = frameTime;
+    hp.substepTime = frameTime / (float)simParams.numSubsteps;
+    hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
+    hp.numColliders = (uint)sdfColliders.size();
+    VT_CUDA(cudaMemcpyAsync(m_frameParams.data(), &hp, sizeof(hp), cudaMemcpyHostToDevice, m_stream));
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, simParams.numParticles};
+    ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()), m_slotsDev,
+                       (uint)(3 * attachSlotPositions.size()), m_frameParams);
+    m_ddCur = m_predA;
+    m_ddOther = m_predB;
+    ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
+                    m_pos4, m_vel4, m_ddCur, m_prepared, m_frameParams);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddSubstepBegin(int substep)
+{
+    const VtSimParams& P = simParams;
+    const uint N = P.numParticles;
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, N};
+    SpatialHashGPU& H = *m_spatialHash;
+    if (P.enableSelfCollision && substep % P.interleavedHash == 0) {  // replicated on every rank (for now)
+        const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
+        const bool odd = RadixSorter::numPasses(maxBit) & 1;
+        uint* k0 = odd ? m_keysAlt.data() : H.particleHash.data();
+        uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
+        uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
+        uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
+        exact_math::launch_hash_particles(L, k0, v0, m_ddCur, H.spacing(), H.tableSize(), m_instancing);
+        m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
+        exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+        VtHashParams hp = H.MakeParams(N, P.particleDiameter);
+        if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4,
+                                                       m_sorted, hp, m_instancing))
+            exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4, hp);
+    }
+    ops.collide(L, m_ddCur, m_ddOther, m_pos4, H.neighbors, m_prepared, m_frameParams, P.enableSelfCollision != 0);
+    std::swap(m_ddCur, m_ddOther);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddIterateOwned()
+{
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, simParams.numParticles};
+    TilePlanDev sub = m_planDev;  // this rank's tile range of the shared plan
+    sub.tiles = m_planDev.tiles + m_dd.tileBegin;
+    sub.numTiles = m_dd.tileEnd - m_dd.tileBegin;
+    if (sub.numTiles) ops.iterate(L, m_ddCur, m_ddOther, sub, m_slotsDev, m_frameParams, m_instancing);
+    // boundary particles this rank owns and a peer reads next iteration
+    exact_math::launch_gather_by_id(L, m_ddOther, m_ddSendIds, m_ddSendOff[m_dd.world], m_ddSendBuf);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddIterateFinish()
+{
+    FusedLaunch L{m_stream, simParams.numParticles};
+    exact_math::launch_scatter_by_id(L, m_ddRecvBuf, m_ddRecvIds, m_ddRecvOff[m_dd.world], m_ddOther);
+    std::swap(m_ddCur, m_ddOther);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddGatherPack()
+{
+    FusedLaunch L{m_stream, simParams.numParticles};
+    exact_math::launch_gather_by_id(L, m_ddCur, m_dOwned.data() + m_ddOwnedBegin[m_dd.rank], m_ddOwnedCount[m_dd.rank], m_ddGatherSend);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddGatherUnpack()
+{
+    FusedLaunch L{m_stream, simParams.numParticles};
+    for (int q = 0; q < m_dd.world; q++)
+        exact_math::launch_scatter_by_id(L, m_ddGatherRecv.data() + (size_t)q * m_ddMaxOwned, m_dOwned.data() + m_ddOwnedBegin[q],
+                                         m_ddOwnedCount[q], m_ddCur);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddSubstepEnd(int substep)
+{
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, simParams.numParticles};
+    const bool last = substep == simParams.numSubsteps - 1;
+    ops.end_substep(L, m_ddCur, m_pos4, m_vel4, m_ddOther, last, reinterpret_cast<float*>(positions.data()),
+                    reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), m_frameParams);
+    if (!last) std::swap(m_ddCur, m_ddOther);
+    VT_CUDA(cudaGetLastError());
+}
+
+void VtClothSolverGPU::ddFrameEnd()
+{
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, simParams.numParticles};
+    ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()), m_instancing);
+    VT_CUDA(cudaGetLastError());
+}
+
 void VtClothSolverGPU::Simulate() { Simulate(kFixedDeltaTime); }
 
 void VtClothSolverGPU::Simulate(float frameTime)

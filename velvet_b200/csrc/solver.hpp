@@ -90,6 +90,27 @@ public:
                            int numInstances, const int* attachedIndices, int numAttached);
     int numInstances() const { return (int)m_instancing.count; }
 
+    // ---- one cloth decomposed over `world` ranks (north_star mode 2).  Every rank registers the same cloth; rank r owns
+    // the tile range ddPlan().tileBegin..tileEnd of the (identical) Morton-ordered plan and runs the Jacobi iterations of
+    // those tiles only.  The frame is driven step by step; between ddIterateOwned and ddIterateFinish the caller moves
+    // ddSendBuf -> peers' ddRecvBuf (per-peer ranges from ddPeerRanges), and between ddGatherPack and ddGatherUnpack it
+    // all-gathers ddGatherSend into ddGatherRecv.  Stages other than the iterations are replicated on every rank (for now).
+    struct DDBuffers {
+        float4 *sendBuf, *recvBuf, *gatherSend, *gatherRecv;
+        unsigned sendTotal, recvTotal, ownedCount, maxOwnedCount;
+    };
+    void ddSetup(int rank, int world);
+    const ExchangePlan& ddPlan() const { return m_dd; }
+    DDBuffers ddBuffers() const;
+    void ddFrameBegin(float frameTime);
+    void ddSubstepBegin(int substep);
+    void ddIterateOwned();
+    void ddIterateFinish();
+    void ddGatherPack();
+    void ddGatherUnpack();
+    void ddSubstepEnd(int substep);
+    void ddFrameEnd();
+
     // bulk variants (one memcpy instead of a managed-memory push_back per element)
     void AddStretchBulk(const int* idxPairs, const float* distances, size_t n);
     void AddBendBulk(const uint* idxQuads, const float* angles, size_t n);
@@ -147,6 +168,14 @@ private:
     int m_tileSize = 0;
     int m_mathMode = VELVET_MATH_EXACT;
     Instancing m_instancing{1, 0, 0};
+    // domain decomposition state
+    ExchangePlan m_dd;
+    bool m_ddReady = false;
+    std::vector<unsigned> m_ddSendOff, m_ddRecvOff, m_ddOwnedBegin, m_ddOwnedCount;  // per peer / per rank
+    unsigned m_ddMaxOwned = 0;
+    DeviceBuffer<uint> m_ddSendIds, m_ddRecvIds;
+    DeviceBuffer<float4> m_ddSendBuf, m_ddRecvBuf, m_ddGatherSend, m_ddGatherRecv;
+    float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
     bool m_instanced = false;
     int m_lastLaunches = 0;
     std::shared_ptr<SpatialHashGPU> m_spatialHash;

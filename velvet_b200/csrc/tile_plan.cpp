@@ -243,4 +243,49 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
     return plan;
 }
 
+ExchangePlan build_exchange_plan(const TilePlan& plan, unsigned N, int rank, int world)
+{
+    ExchangePlan x;
+    x.rank = rank;
+    x.world = world;
+    const unsigned numTiles = (unsigned)plan.tiles.size();
+    x.tileBeginOf.resize((size_t)world + 1);
+    for (int r = 0; r <= world; r++) x.tileBeginOf[r] = (unsigned)((unsigned long long)numTiles * r / world);
+    x.tileBegin = x.tileBeginOf[rank];
+    x.tileEnd = x.tileBeginOf[rank + 1];
+    x.recvIds.assign(world, {});
+    x.sendIds.assign(world, {});
+
+    // owner rank of every particle: its tile's rank
+    std::vector<int> rankOfTile(numTiles);
+    for (int r = 0; r < world; r++)
+        for (unsigned t = x.tileBeginOf[r]; t < x.tileBeginOf[r + 1]; t++) rankOfTile[t] = r;
+    std::vector<int> ownerRank(N);
+    for (unsigned t = 0; t < numTiles; t++)
+        for (unsigned i = 0; i < plan.tiles[t].nOwned; i++) ownerRank[plan.ownedIds[plan.tiles[t].ownedOff + i]] = rankOfTile[t];
+
+    // needs(r) = halo particles of r's tiles owned elsewhere; every rank evaluates every r, so both sides of each
+    // message agree on its contents and order (ascending particle id) without any negotiation
+    std::vector<unsigned char> seen(N);
+    for (int r = 0; r < world; r++) {
+        std::fill(seen.begin(), seen.end(), 0);
+        std::vector<std::vector<unsigned>> need(world);
+        for (unsigned t = x.tileBeginOf[r]; t < x.tileBeginOf[r + 1]; t++) {
+            const TileDesc& td = plan.tiles[t];
+            for (unsigned i = 0; i < td.nHalo; i++) {
+                const unsigned p = plan.haloIds[td.haloOff + i];
+                const int q = ownerRank[p];
+                if (q != r && !seen[p]) {
+                    seen[p] = 1;
+                    need[q].push_back(p);
+                }
+            }
+        }
+        for (int q = 0; q < world; q++) std::sort(need[q].begin(), need[q].end());
+        if (r == rank) x.recvIds = need;
+        else x.sendIds[r] = need[rank];
+    }
+    return x;
+}
+
 }  // namespace velvet

@@ -67,4 +67,16 @@ TilePlan build_tile_plan(unsigned numParticles, const float* positions, const in
                          const float* bendAngles, size_t numBend, const int* attachParticleIDs,
                          const int* attachSlotIDs, const float* attachDistances, size_t numAttach, int tileSize);
 
+// ---- domain decomposition of ONE cloth over `world` ranks (north_star mode 2): rank r owns the contiguous tile range
+// [tileBegin(r), tileEnd(r)) of the Morton-ordered plan, i.e. a spatially compact patch.  Before every Jacobi iteration a
+// rank needs the predicted positions of the halo particles of its tiles that another rank owns.
+struct ExchangePlan {
+    int rank = 0, world = 1;
+    unsigned tileBegin = 0, tileEnd = 0;
+    std::vector<unsigned> tileBeginOf;              // [world + 1] tile range of every rank
+    std::vector<std::vector<unsigned>> recvIds;     // [world] particle ids owned by peer q that this rank reads (ascending)
+    std::vector<std::vector<unsigned>> sendIds;     // [world] particle ids owned by this rank that peer q reads (ascending)
+};
+ExchangePlan build_exchange_plan(const TilePlan& plan, unsigned numParticles, int rank, int world);
+
 }  // namespace velvet

@@ -1,0 +1,116 @@
+"""One large cloth decomposed over several GPUs (north_star mode 2): one process per GPU (torchrun), every rank registers
+the same cloth, rank r runs the Jacobi iterations of its own tile range, and the boundary particles move over
+NVLink with torch.distributed (NCCL) once per iteration; predicted positions are all-gathered once per substep.
+
+The solver's stepped C ABI (velvet_solver_dd_*) does the compute on the solver's stream; this module only moves bytes
+between tensors that alias the solver's device buffers.  Results are bit-identical to the single-GPU solver.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _capi
+from ._capi import check
+
+DD_FRAME_BEGIN, DD_SUBSTEP_BEGIN, DD_ITERATE_OWNED, DD_ITERATE_FINISH = 0, 1, 2, 3
+DD_GATHER_PACK, DD_GATHER_UNPACK, DD_SUBSTEP_END, DD_FRAME_END = 4, 5, 6, 7
+
+
+class VelvetDDInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("tileBegin", C.c_uint), ("tileEnd", C.c_uint), ("numTiles", C.c_uint),
+                ("ownedCount", C.c_uint), ("maxOwnedCount", C.c_uint), ("sendTotal", C.c_uint), ("recvTotal", C.c_uint),
+                ("sendBuf", C.c_void_p), ("recvBuf", C.c_void_p), ("gatherSend", C.c_void_p), ("gatherRecv", C.c_void_p)]
+
+
+def plan_grid(resolution: int, rank: int, world: int, tile_size: int = 0):
+    """Host-only exchange lists of `rank` (no GPU): (send {peer: ids}, recv {peer: ids}, (ownedBegin, ownedEnd))."""
+    import numpy as np
+    L = _capi.load()
+    L.velvet_dd_plan_grid.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    counts = np.zeros(2 * world, np.uint32)
+    check(L.velvet_dd_plan_grid(resolution, tile_size, rank, world, counts.ctypes.data_as(C.c_void_p), None, None, None))
+    send = np.zeros(max(int(counts[:world].sum()), 1), np.uint32)
+    recv = np.zeros(max(int(counts[world:].sum()), 1), np.uint32)
+    owned = np.zeros(2, np.uint32)
+    check(L.velvet_dd_plan_grid(resolution, tile_size, rank, world, counts.ctypes.data_as(C.c_void_p), send.ctypes.data_as(C.c_void_p),
+                                recv.ctypes.data_as(C.c_void_p), owned.ctypes.data_as(C.c_void_p)))
+    so = np.concatenate([[0], np.cumsum(counts[:world])]).astype(int)
+    ro = np.concatenate([[0], np.cumsum(counts[world:])]).astype(int)
+    return ({q: send[so[q]:so[q + 1]].copy() for q in range(world)}, {q: recv[ro[q]:ro[q + 1]].copy() for q in range(world)},
+            (int(owned[0]), int(owned[1])))
+
+
+class _DevicePtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it (no copy)."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class DecomposedCloth:
+    def __init__(self, solver, device_index: int):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (backend nccl) before decomposing a cloth")
+        self.torch, self.dist = torch, dist
+        self.solver = solver
+        self._L = _capi.load()
+        self._L.velvet_solver_dd_setup.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self._L.velvet_solver_dd_info.argtypes = [C.c_void_p, C.POINTER(VelvetDDInfo)]
+        self._L.velvet_solver_dd_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._L.velvet_solver_dd_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        check(self._L.velvet_solver_dd_setup(solver._h, self.rank, self.world))
+        self.info = VelvetDDInfo()
+        check(self._L.velvet_solver_dd_info(solver._h, C.byref(self.info)))
+        so = (C.c_uint * (self.world + 1))()
+        ro = (C.c_uint * (self.world + 1))()
+        check(self._L.velvet_solver_dd_offsets(solver._h, so, ro))
+        self.send_off, self.recv_off = list(so), list(ro)
+        dev = torch.device("cuda", device_index)
+        self.stream = torch.cuda.ExternalStream(solver.stream, device=dev)
+        alias = lambda ptr, n: torch.as_tensor(_DevicePtr(ptr, 4 * max(n, 1)), device=dev)
+        self.send = alias(self.info.sendBuf, self.info.sendTotal)
+        self.recv = alias(self.info.recvBuf, self.info.recvTotal)
+        self.gather_send = alias(self.info.gatherSend, self.info.maxOwnedCount)
+        self.gather_recv = alias(self.info.gatherRecv, self.info.maxOwnedCount * self.world)
+        self.halo_bytes_per_iteration = 16 * (self.info.sendTotal + self.info.recvTotal)
+
+    def _step(self, op: int, arg: int = 0, farg: float = 0.0):
+        check(self._L.velvet_solver_dd_step(self.solver._h, op, arg, farg))
+
+    def _exchange_halo(self):
+        dist = self.dist
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            s0, s1 = 4 * self.send_off[q], 4 * self.send_off[q + 1]
+            r0, r1 = 4 * self.recv_off[q], 4 * self.recv_off[q + 1]
+            if s1 > s0:
+                ops.append(dist.P2POp(dist.isend, self.send[s0:s1], q))
+            if r1 > r0:
+                ops.append(dist.P2POp(dist.irecv, self.recv[r0:r1], q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()  # orders the solver stream after the transfer; does not block the host
+
+    def Simulate(self, dt: float = 1.0 / 60.0, sync: bool = True):
+        P = self.solver.simParams
+        with self.torch.cuda.stream(self.stream):
+            self._step(DD_FRAME_BEGIN, 0, dt)
+            for s in range(P.numSubsteps):
+                self._step(DD_SUBSTEP_BEGIN, s)
+                for _ in range(P.numIterations):
+                    self._step(DD_ITERATE_OWNED)
+                    self._exchange_halo()
+                    self._step(DD_ITERATE_FINISH)
+                if P.numIterations > 0 and self.world > 1:
+                    self._step(DD_GATHER_PACK)
+                    self.dist.all_gather_into_tensor(self.gather_recv, self.gather_send)
+                    self._step(DD_GATHER_UNPACK)
+                self._step(DD_SUBSTEP_END, s)
+            self._step(DD_FRAME_END)
+        if sync:
+            self.solver.Synchronize()
