@@ -275,7 +275,8 @@ VELVET_API int velvet_solver_add_cloth_instances(VelvetSolver* s, int resolution
  * (torch.distributed/NCCL in velvet_b200/decomposed.py).  Results are bit-identical to the single-GPU solver. */
 typedef enum VelvetDDOp {
     VELVET_DD_FRAME_BEGIN = 0,   /* arg unused, farg = frame time                                   */
-    VELVET_DD_SUBSTEP_BEGIN = 1, /* arg = substep: [hash rebuild] + collide (replicated)            */
+    VELVET_DD_SUBSTEP_BEGIN = 1, /* arg = substep: [hash rebuild] + collide of the owned particles + pack; follow with
+                                    the same exchange as an iteration and ITERATE_FINISH              */
     VELVET_DD_ITERATE_OWNED = 2, /* Jacobi iteration on the owned tiles + pack of the boundary      */
     VELVET_DD_ITERATE_FINISH = 3,/* unpack of the received halo                                      */
     VELVET_DD_GATHER_PACK = 4,

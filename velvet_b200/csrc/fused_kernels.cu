@@ -96,13 +96,16 @@ __global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ 
                                                      const float4* __restrict__ pos4,
                                                      const unsigned* __restrict__ neighbors,
                                                      const PreparedCollider* __restrict__ colliders,
-                                                     const FrameParams* __restrict__ fp, unsigned N, int selfCollision)
+                                                     const FrameParams* __restrict__ fp, unsigned N, int selfCollision,
+                                                     const unsigned* __restrict__ subset, unsigned subsetCount)
 {
     __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
     const unsigned nc = fp->numColliders;
     stage_colliders(s_col, colliders, nc);
-    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= N) return;
+    // subset != nullptr: only the listed particles (the ones this rank owns in the domain-decomposed mode)
+    const unsigned tidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tidx >= (subset ? subsetCount : N)) return;
+    const unsigned id = subset ? __ldg(subset + tidx) : tidx;
     const VtSimParams& P = fp->P;
     const float4 pi4 = predIn[id];
     const float4 xi4 = pos4[id];
@@ -411,10 +414,13 @@ void launch_begin_frame(const FusedLaunch& L, const float* positions, const floa
 }
 
 void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
-                    const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision)
+                    const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision,
+                    const unsigned* subset, unsigned subsetCount)
 {
-    collide_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp,
-                                                               L.numParticles, selfCollision ? 1 : 0);
+    const unsigned n = subset ? subsetCount : L.numParticles;
+    if (!n) return;
+    collide_kernel<<<pgrid(n), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
+                                                  selfCollision ? 1 : 0, subset, subsetCount);
 }
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
@@ -485,14 +491,15 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 
 bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst)
+                                   const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst,
+                                   const unsigned char* ownedMask)
 {
     if (hp.tableSize <= 0) return false;
     const unsigned n = L.numParticles;
     SortedParticle* sorted = reinterpret_cast<SortedParticle*>(sortedScratch);
     reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n);
     cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
-        neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles);
+        neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, ownedMask);
     return true;
 }
 

@@ -72,7 +72,7 @@ void launch_begin_frame(const FusedLaunch& L, const float* positions, const floa
 // CollideParticles + ApplyDeltas + CollideSDF (substep dt): predIn -> predOut.
 void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
                     const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp,
-                    bool selfCollision);
+                    bool selfCollision, const unsigned* subset = nullptr, unsigned subsetCount = 0);
 
 // One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
@@ -103,7 +103,8 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                    const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
                                    const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp,
-                                   Instancing inst);  // hp.tableSize = rows per instance
+                                   Instancing inst,  // hp.tableSize = rows per instance
+                                   const unsigned char* ownedMask = nullptr);  // decomposed mode: lists of owned particles only
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
 // halo exchange plumbing of the domain-decomposed mode: out[i] = src[ids[i]]  /  dst[ids[i]] = in[i]
 void launch_gather_by_id(const FusedLaunch& L, const float4* src, const unsigned* ids, unsigned n, float4* out);
@@ -127,7 +128,7 @@ void launch_begin_frame(const FusedLaunch& L, const float* positions, const floa
 // CollideParticles + ApplyDeltas + CollideSDF (substep dt): predIn -> predOut.
 void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
                     const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp,
-                    bool selfCollision);
+                    bool selfCollision, const unsigned* subset = nullptr, unsigned subsetCount = 0);
 
 // One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,

@@ -166,12 +166,14 @@ constexpr int CN_THREADS = 256;
 // scattered 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
 static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
     unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
-    const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles)
+    const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles,
+    const unsigned char* __restrict__ ownedMask)
 {
     const unsigned t = blockIdx.x * CN_THREADS + threadIdx.x;
     if (t >= hp.numObjects) return;
     const float4 me = __ldg(&sorted[t].pos);
     const unsigned id = __float_as_uint(me.w);
+    if (ownedMask && !__ldg(ownedMask + id)) return;  // domain-decomposed mode: another rank builds this particle's list
     const unsigned tableBase = (id / instanceParticles) * (unsigned)hp.tableSize;  // this instance's rows of the table
     const vec3 position = V3(me);
     const vec3 originalPos = V3(__ldg(&sorted[t].init));

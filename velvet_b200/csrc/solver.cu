@@ -646,7 +646,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             STAGE_END(t);
         }
         STAGE_BEGIN(t, "Solver_CollideParticles");  // + ApplyDeltas + CollideSDFs
-        ops.collide(L, cur, other, m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0);
+        ops.collide(L, cur, other, m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0, nullptr, 0);
         launches++;
         std::swap(cur, other);
         STAGE_END(t);
@@ -713,6 +713,11 @@ void VtClothSolverGPU::ddSetup(int rank, int world)
     m_ddRecvIds.upload(recvIds, m_stream);
     m_ddSendBuf.allocate(std::max<size_t>(m_ddSendOff[world], 1));
     m_ddRecvBuf.allocate(std::max<size_t>(m_ddRecvOff[world], 1));
+    {
+        std::vector<unsigned char> mask(N, 0);
+        for (unsigned i = 0; i < m_ddOwnedCount[rank]; i++) mask[m_plan.ownedIds[m_ddOwnedBegin[rank] + i]] = 1;
+        m_ddOwnedMask.upload(mask, m_stream);
+    }
     m_ddGatherSend.allocate(m_ddMaxOwned);
     m_ddGatherRecv.allocate((size_t)m_ddMaxOwned * world);
     Synchronize();
@@ -767,12 +772,15 @@ void VtClothSolverGPU::ddSubstepBegin(int substep)
         m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
         exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
         VtHashParams hp = H.MakeParams(N, P.particleDiameter);
+        // keys / sort / cell table are replicated; the expensive candidate walk only for the particles this rank owns
         if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4,
-                                                       m_sorted, hp, m_instancing))
+                                                       m_sorted, hp, m_instancing, m_ddOwnedMask))
             exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4, hp);
     }
-    ops.collide(L, m_ddCur, m_ddOther, m_pos4, H.neighbors, m_prepared, m_frameParams, P.enableSelfCollision != 0);
-    std::swap(m_ddCur, m_ddOther);
+    // collide only the owned particles, then hand the boundary to the peers exactly like after an iteration
+    ops.collide(L, m_ddCur, m_ddOther, m_pos4, H.neighbors, m_prepared, m_frameParams, P.enableSelfCollision != 0,
+                m_dOwned.data() + m_ddOwnedBegin[m_dd.rank], m_ddOwnedCount[m_dd.rank]);
+    exact_math::launch_gather_by_id(L, m_ddOther, m_ddSendIds, m_ddSendOff[m_dd.world], m_ddSendBuf);
     VT_CUDA(cudaGetLastError());
 }
 

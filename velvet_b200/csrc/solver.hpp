@@ -103,7 +103,7 @@ public:
     const ExchangePlan& ddPlan() const { return m_dd; }
     DDBuffers ddBuffers() const;
     void ddFrameBegin(float frameTime);
-    void ddSubstepBegin(int substep);
+    void ddSubstepBegin(int substep);  // hash (keys/sort replicated, lists of owned particles) + collide of owned particles + pack
     void ddIterateOwned();
     void ddIterateFinish();
     void ddGatherPack();
@@ -174,6 +174,7 @@ private:
     std::vector<unsigned> m_ddSendOff, m_ddRecvOff, m_ddOwnedBegin, m_ddOwnedCount;  // per peer / per rank
     unsigned m_ddMaxOwned = 0;
     DeviceBuffer<uint> m_ddSendIds, m_ddRecvIds;
+    DeviceBuffer<unsigned char> m_ddOwnedMask;
     DeviceBuffer<float4> m_ddSendBuf, m_ddRecvBuf, m_ddGatherSend, m_ddGatherRecv;
     float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
     bool m_instanced = false;

@@ -101,12 +101,14 @@ class DecomposedCloth:
         with self.torch.cuda.stream(self.stream):
             self._step(DD_FRAME_BEGIN, 0, dt)
             for s in range(P.numSubsteps):
-                self._step(DD_SUBSTEP_BEGIN, s)
+                self._step(DD_SUBSTEP_BEGIN, s)  # hash + collide of the owned particles, boundary packed
+                self._exchange_halo()
+                self._step(DD_ITERATE_FINISH)
                 for _ in range(P.numIterations):
                     self._step(DD_ITERATE_OWNED)
                     self._exchange_halo()
                     self._step(DD_ITERATE_FINISH)
-                if P.numIterations > 0 and self.world > 1:
+                if self.world > 1:
                     self._step(DD_GATHER_PACK)
                     self.dist.all_gather_into_tensor(self.gather_recv, self.gather_send)
                     self._step(DD_GATHER_UNPACK)
