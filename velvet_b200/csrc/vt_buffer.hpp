@@ -76,22 +76,13 @@ public:
     void reserve(size_t minCapacity)
     {
         if (minCapacity <= m_capacity) return;
-        const size_t newCapacity = minCapacity * 3 / 2;  // growth factor of the reference
-        T* fresh = nullptr;
-        VT_CUDA(cudaMallocManaged((void**)&fresh, newCapacity * sizeof(T)));
-        if (m_data) {
-            // the GPU may still be reading the old block (async frames): drain before the host touches it
-            VT_CUDA(cudaDeviceSynchronize());
-            std::memcpy(fresh, m_data, m_count * sizeof(T));
-            VT_CUDA(cudaFree(m_data));
-        }
-        m_data = fresh;
-        m_capacity = newCapacity;
-        m_generation++;
+        grow(minCapacity * 3 / 2);  // growth factor of the reference (push_back / append path)
     }
+    // resize() sizes exactly: the big fixed-size arrays (64 neighbour slots per particle, hash tables) are resized once
+    // and never pushed to, and 1.5x of 4.3 GB matters when 8 ranks register a 16.7M-particle cloth at the same time.
     void resize(size_t newCount)
     {
-        reserve(newCount);
+        if (newCount > m_capacity) grow(newCount);
         m_count = newCount;
     }
     void resize(size_t newCount, const T& val)
@@ -100,6 +91,15 @@ public:
         resize(newCount);
         for (size_t i = first; i < newCount; i++) m_data[i] = val;
     }
+    // Device-only placement (plain cudaMalloc) for arrays that only kernels touch (hash tables, neighbour lists).  Must be
+    // chosen while the buffer is empty; host indexing, push_back and append are then invalid.
+    void setDeviceOnly()
+    {
+        if (m_data) throw Error(-4, "VtBuffer::setDeviceOnly on an allocated buffer");
+        m_deviceOnly = true;
+    }
+    bool deviceOnly() const { return m_deviceOnly; }
+
     void destroy()
     {
         if (m_data) {
@@ -112,10 +112,33 @@ public:
     }
 
 private:
+    void grow(size_t newCapacity)
+    {
+        T* fresh = nullptr;
+        const cudaError_t e = m_deviceOnly ? cudaMalloc((void**)&fresh, newCapacity * sizeof(T))
+                                           : cudaMallocManaged((void**)&fresh, newCapacity * sizeof(T));
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            throw Error(-2, std::string(m_deviceOnly ? "cudaMalloc" : "cudaMallocManaged") + " of " + std::to_string(newCapacity * sizeof(T)) +
+                                " bytes failed: " + cudaGetErrorString(e) + " (VtBuffer::grow)");
+        }
+        if (m_data) {
+            // the GPU may still be reading the old block (async frames): drain before the host touches it
+            VT_CUDA(cudaDeviceSynchronize());
+            if (m_deviceOnly) VT_CUDA(cudaMemcpy(fresh, m_data, m_count * sizeof(T), cudaMemcpyDeviceToDevice));
+            else std::memcpy(fresh, m_data, m_count * sizeof(T));
+            VT_CUDA(cudaFree(m_data));
+        }
+        m_data = fresh;
+        m_capacity = newCapacity;
+        m_generation++;
+    }
+
     size_t m_count = 0;
     size_t m_capacity = 0;
     T* m_data = nullptr;
     unsigned m_generation = 0;
+    bool m_deviceOnly = false;
 };
 
 // Headless VtMergedBuffer: one managed array holding every cloth's range.  The reference mirrors each range
@@ -134,6 +157,7 @@ public:
         const size_t offset = m_vbuffer.size();
         m_offsets.push_back(offset);
         m_counts.push_back(count);
+        m_vbuffer.reserve(offset + count);  // amortised growth when cloths are registered one by one
         m_vbuffer.resize(offset + count);
         if (src) std::memcpy(m_vbuffer.data() + offset, src, count * sizeof(T));
         else std::memset((void*)(m_vbuffer.data() + offset), 0, count * sizeof(T));
