@@ -296,6 +296,19 @@ VELVET_API int velvet_solver_dd_info(VelvetSolver* s, VelvetDDInfo* out);
 /* per-peer element offsets into sendBuf / recvBuf: arrays of world + 1 entries */
 VELVET_API int velvet_solver_dd_offsets(VelvetSolver* s, unsigned* sendOffsets, unsigned* recvOffsets);
 VELVET_API int velvet_solver_dd_step(VelvetSolver* s, int op, int arg, float farg);
+/* NVLink peer-memory transport (the fast path; velvet_b200/csrc/dd_peer.cuh).  After dd_setup every rank exports a blob of
+ * CUDA IPC handles (its two predicted-position arrays + a flag array), the caller all-gathers the blobs (any transport:
+ * they are `velvet_dd_peer_blob_bytes()` plain bytes) and hands all `world` of them, rank-major, to dd_peer_import.  From
+ * then on velvet_solver_dd_simulate runs a whole frame as ONE CUDA graph per rank: boundary particles are stored straight
+ * into the peers' arrays by this library's kernels and ordered by release/acquire epoch flags over NVLink -- no host, no
+ * NCCL in the loop.  Every rank must call dd_simulate the same number of times.  A peer that never arrives makes the wait
+ * kernels time out (20 s): the next synchronising call returns VELVET_ERR_STATE.  dd_peer_close unmaps the peers; all ranks
+ * must have closed before any of them destroys its solver.  Results are bit-identical to velvet_solver_simulate. */
+VELVET_API size_t velvet_dd_peer_blob_bytes(void);
+VELVET_API int velvet_solver_dd_peer_export(VelvetSolver* s, void* blob);
+VELVET_API int velvet_solver_dd_peer_import(VelvetSolver* s, const void* blobs, size_t blobBytes);
+VELVET_API int velvet_solver_dd_peer_close(VelvetSolver* s);
+VELVET_API int velvet_solver_dd_simulate(VelvetSolver* s, float deltaTime, int sync);
 /* Host-only: the exchange lists of `rank` for a grid cloth of `resolution` cut into `world` ranks with tiles of
  * `tileSize` particles (what dd_setup computes), for tests without a GPU.  ids arrays may be NULL to query counts only:
  * counts[q] / counts[world + q] = number of particle ids sent to / received from rank q. */

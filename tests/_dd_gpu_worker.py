@@ -1,5 +1,5 @@
 """torchrun worker (one process per GPU): the domain-decomposed cloth must reproduce the single-GPU solver bit for bit.
-Usage: torchrun --nproc-per-node G tests/_dd_gpu_worker.py <outdir> [resolution] [frames] [bench_frames]"""
+Usage: torchrun --nproc-per-node G tests/_dd_gpu_worker.py <outdir> [resolution] [frames] [bench_frames] [peer|nccl]"""
 import json
 import os
 import sys
@@ -21,6 +21,7 @@ out_dir = sys.argv[1]
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 127
 frames = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 bench_frames = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+transport = sys.argv[5] if len(sys.argv) > 5 else "peer"
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -37,7 +38,7 @@ if have_ref:
     ref.UpdateColliders(cols)
 dd_solver = vb.build_scene(R, p, device=local)
 dd_solver.UpdateColliders(cols)
-dd = DecomposedCloth(dd_solver, local)
+dd = DecomposedCloth(dd_solver, local, transport=transport)
 ok = True
 worst = 0.0
 checksum = 0.0
@@ -55,7 +56,8 @@ for f in range(frames):
 sums = [None] * world
 dist.all_gather_object(sums, checksum)
 ok = ok and all(s == sums[0] for s in sums)
-res = {"rank": rank, "world": world, "particles": int(dd_solver.simParams.numParticles), "bit_identical": bool(ok), "max_abs_diff": worst,
+res = {"rank": rank, "world": world, "transport": dd.transport, "transport_requested": transport, "peer_error": dd.peer_error,
+       "launches_per_frame": int(dd_solver._L.velvet_solver_last_launch_count(dd_solver._h)), "particles": int(dd_solver.simParams.numParticles), "bit_identical": bool(ok), "max_abs_diff": worst,
        "compared_with_single_gpu": bool(have_ref),
        "tiles": [int(dd.info.tileBegin), int(dd.info.tileEnd), int(dd.info.numTiles)], "owned": int(dd.info.ownedCount),
        "halo_send": int(dd.info.sendTotal), "halo_recv": int(dd.info.recvTotal)}
@@ -73,6 +75,7 @@ if bench_frames:
             s.Simulate(sync=False)
         torch.cuda.synchronize(); dist.barrier()
         res[name] = (time.perf_counter() - t0) * 1e3 / bench_frames
+dd.close()
 json.dump(res, open(os.path.join(out_dir, f"dd_gpu{rank}.json"), "w"))
 print(json.dumps(res), flush=True)
 dist.destroy_process_group()

@@ -412,6 +412,42 @@ int velvet_solver_dd_step(VelvetSolver* s, int op, int arg, float farg)
     VT_API_END
 }
 
+size_t velvet_dd_peer_blob_bytes(void) { return VtClothSolverGPU::ddPeerBlobBytes(); }
+
+int velvet_solver_dd_peer_export(VelvetSolver* s, void* blob)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && blob, "dd_peer_export: NULL argument");
+    s->impl.ddPeerExport(blob);
+    VT_API_END
+}
+
+int velvet_solver_dd_peer_import(VelvetSolver* s, const void* blobs, size_t blobBytes)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && blobs, "dd_peer_import: NULL argument");
+    s->impl.ddPeerImport(blobs, blobBytes);
+    VT_API_END
+}
+
+int velvet_solver_dd_peer_close(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.ddPeerClose();
+    VT_API_END
+}
+
+int velvet_solver_dd_simulate(VelvetSolver* s, float deltaTime, int sync)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.ddSimulate(deltaTime > 0 ? deltaTime : kFixedDeltaTime);
+    if (sync && s->impl.ddPeerError())
+        return set_error(VELVET_ERR_STATE, "dd_simulate: a peer did not arrive within the time-out (exchange flags never advanced)");
+    VT_API_END
+}
+
 int velvet_dd_plan_grid(int resolution, int tileSize, int rank, int world, unsigned* counts, unsigned* sendIds, unsigned* recvIds,
                         unsigned* ownedRange2)
 {

@@ -153,6 +153,7 @@ VtClothSolverGPU::~VtClothSolverGPU()
 {
     cudaSetDevice(m_device);
     if (m_stream) cudaStreamSynchronize(m_stream);
+    try { ddPeerClose(); } catch (...) {}
     if (m_graphExec) cudaGraphExecDestroy(m_graphExec);
     if (m_graph) cudaGraphDestroy(m_graph);
     if (m_stream) cudaStreamDestroy(m_stream);
@@ -535,8 +536,9 @@ void VtClothSolverGPU::ensureFusedResources()
 
     m_pos4.allocate(N);
     m_vel4.allocate(N);
-    m_predA.allocate(N);
-    m_predB.allocate(N);
+    // at least 2 MB each: the decomposed mode exports them over CUDA IPC and must not share a driver slab with other arrays
+    m_predA.allocate(std::max<size_t>(N, 131072));
+    m_predB.allocate(std::max<size_t>(N, 131072));
     m_init4.allocate(N);
     m_sorted.allocate(2 * (size_t)N);
     m_keysAlt.allocate(N);
@@ -720,6 +722,13 @@ void VtClothSolverGPU::ddSetup(int rank, int world)
         for (unsigned i = 0; i < m_ddOwnedCount[rank]; i++) mask[m_plan.ownedIds[m_ddOwnedBegin[rank] + i]] = 1;
         m_ddOwnedMask.upload(mask, m_stream);
     }
+    {
+        std::vector<unsigned char> peerOf(sendIds.size());
+        for (int q = 0; q < world; q++)
+            for (unsigned i = m_ddSendOff[q]; i < m_ddSendOff[q + 1]; i++) peerOf[i] = (unsigned char)q;
+        m_ddSendPeer.upload(peerOf.empty() ? std::vector<unsigned char>(1, 0) : peerOf, m_stream);
+    }
+    ddPeerClose();  // mappings of an earlier setup refer to buffers that may have moved
     m_ddGatherSend.allocate(m_ddMaxOwned);
     m_ddGatherRecv.allocate((size_t)m_ddMaxOwned * world);
     Synchronize();
@@ -840,6 +849,237 @@ void VtClothSolverGPU::ddFrameEnd()
     FusedLaunch L{m_stream, simParams.numParticles};
     ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()), m_instancing);
     VT_CUDA(cudaGetLastError());
+}
+
+
+// ---- NVLink peer-memory transport ------------------------------------------------------------------------------------
+
+namespace {
+struct DDPeerBlob {
+    cudaIpcMemHandle_t pred[2];
+    cudaIpcMemHandle_t flags;
+    unsigned long long particles;
+    int rank, world, device, pad;
+};
+constexpr size_t kFlagWords = 524288;  // 2 MB: an allocation of its own
+}  // namespace
+
+size_t VtClothSolverGPU::ddPeerBlobBytes() { return sizeof(DDPeerBlob); }
+
+void VtClothSolverGPU::ddPeerExport(void* out)
+{
+    if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
+    if (m_dd.world > ddpeer::kMaxWorld) throw Error(VELVET_ERR_UNSUPPORTED, "peer transport: at most 16 ranks");
+    VT_CUDA(cudaSetDevice(m_device));
+    ddPeerClose();
+    m_ddFlags.allocate(kFlagWords);
+    m_ddCtl.allocate(1);
+    VT_CUDA(cudaMemsetAsync(m_ddFlags.data(), 0, m_ddFlags.bytes(), m_stream));
+    VT_CUDA(cudaMemsetAsync(m_ddCtl.data(), 0, m_ddCtl.bytes(), m_stream));
+    VT_CUDA(cudaStreamSynchronize(m_stream));  // zeroed before any peer can map and signal
+    DDPeerBlob b{};
+    VT_CUDA(cudaIpcGetMemHandle(&b.pred[0], m_predA.data()));
+    VT_CUDA(cudaIpcGetMemHandle(&b.pred[1], m_predB.data()));
+    VT_CUDA(cudaIpcGetMemHandle(&b.flags, m_ddFlags.data()));
+    b.particles = simParams.numParticles;
+    b.rank = m_dd.rank;
+    b.world = m_dd.world;
+    b.device = m_device;
+    std::memcpy(out, &b, sizeof(b));
+}
+
+void VtClothSolverGPU::ddPeerImport(const void* blobs, size_t blobBytes)
+{
+    if (!m_ddReady || !m_ddFlags.data()) throw Error(VELVET_ERR_STATE, "ddPeerImport: call ddSetup and ddPeerExport first");
+    if (blobBytes != sizeof(DDPeerBlob)) throw Error(VELVET_ERR_INVALID_ARGUMENT, "ddPeerImport: blob size mismatch");
+    VT_CUDA(cudaSetDevice(m_device));
+    ddpeer::PeerTable T{};
+    T.rank = m_dd.rank;
+    T.world = m_dd.world;
+    std::vector<void*> opened;
+    auto open = [&](const cudaIpcMemHandle_t& h) {
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            for (void* o : opened) cudaIpcCloseMemHandle(o);
+            throw Error(VELVET_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+        }
+        opened.push_back(p);
+        return p;
+    };
+    for (int q = 0; q < m_dd.world; q++) {
+        if (q == m_dd.rank) {
+            T.pred[0][q] = m_predA.data();
+            T.pred[1][q] = m_predB.data();
+            T.flags[q] = m_ddFlags.data();
+            continue;
+        }
+        DDPeerBlob b;
+        std::memcpy(&b, (const char*)blobs + (size_t)q * blobBytes, sizeof(b));
+        if (b.rank != q || b.world != m_dd.world || b.particles != simParams.numParticles) {
+            for (void* o : opened) cudaIpcCloseMemHandle(o);
+            throw Error(VELVET_ERR_INVALID_ARGUMENT, "ddPeerImport: blob " + std::to_string(q) + " does not describe rank " + std::to_string(q) +
+                                                         " of the same cloth");
+        }
+        T.pred[0][q] = (float4*)open(b.pred[0]);
+        T.pred[1][q] = (float4*)open(b.pred[1]);
+        T.flags[q] = (unsigned*)open(b.flags);
+    }
+    m_ddPeers = T;
+    m_ddOpened = std::move(opened);
+    m_ddPeersReady = true;
+    m_ddGraphKey = 0;  // pointers are baked into the graph
+}
+
+void VtClothSolverGPU::ddPeerClose()
+{
+    if (m_stream) cudaStreamSynchronize(m_stream);
+    if (m_ddGraphExec) cudaGraphExecDestroy(m_ddGraphExec);
+    if (m_ddGraph) cudaGraphDestroy(m_ddGraph);
+    m_ddGraphExec = nullptr;
+    m_ddGraph = nullptr;
+    m_ddGraphKey = 0;
+    for (void* p : m_ddOpened) cudaIpcCloseMemHandle(p);
+    m_ddOpened.clear();
+    m_ddPeersReady = false;
+}
+
+bool VtClothSolverGPU::ddPeerError()
+{
+    if (!m_ddCtl.data()) return false;
+    ddpeer::Control c{};
+    VT_CUDA(cudaMemcpyAsync(&c, m_ddCtl.data(), sizeof(c), cudaMemcpyDeviceToHost, m_stream));
+    VT_CUDA(cudaStreamSynchronize(m_stream));
+    return c.error != 0;
+}
+
+// One decomposed frame on m_stream.  Buffer roles: index 0 = predA, 1 = predB on every rank (all ranks swap in lock step).
+void VtClothSolverGPU::recordDDFrame()
+{
+    const VtSimParams& P = simParams;
+    const uint N = P.numParticles;
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, N};
+    SpatialHashGPU& H = *m_spatialHash;
+    const FrameParams* fp = m_frameParams;
+    const ddpeer::PeerTable* T = &m_ddPeers;
+    ddpeer::Control* ctl = m_ddCtl.data();
+    const unsigned long long timeoutNs = 20ull * 1000000000ull;
+    float4* buf[2] = {m_predA.data(), m_predB.data()};
+    int cur = 0, other = 1;
+    int launches = 0;
+    const int rank = m_dd.rank, world = m_dd.world;
+    const uint* ownedIds = m_dOwned.data() + m_ddOwnedBegin[rank];
+    const uint ownedCount = m_ddOwnedCount[rank];
+    const uint sendTotal = m_ddSendOff[world];
+    auto wait = [&] {
+        ddpeer::launch_wait(m_stream, T, ctl, m_ddFlags.data(), timeoutNs);
+        launches++;
+    };
+    auto push_halo = [&](int which) {  // boundary particles this rank owns and a peer reads next
+        ddpeer::launch_push_halo(m_stream, T, ctl, which, buf[which], m_ddSendIds, m_ddSendPeer, sendTotal);
+        launches++;
+    };
+
+    ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()), m_slotsDev,
+                       (uint)(3 * attachSlotPositions.size()), fp);
+    ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
+                    m_pos4, m_vel4, buf[cur], m_prepared, fp);
+    launches += 2;
+    TilePlanDev sub = m_planDev;  // this rank's tile range of the shared plan
+    sub.tiles = m_planDev.tiles + m_dd.tileBegin;
+    sub.numTiles = m_dd.tileEnd - m_dd.tileBegin;
+    const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
+    const bool odd = RadixSorter::numPasses(maxBit) & 1;
+    for (int substep = 0; substep < P.numSubsteps; substep++) {
+        // "I no longer read the buffer the peers are about to push into" (previous end_substep / begin_frame are done)
+        ddpeer::launch_signal(m_stream, T, ctl);
+        launches++;
+        if (P.enableSelfCollision && substep % P.interleavedHash == 0) {
+            uint* k0 = odd ? m_keysAlt.data() : H.particleHash.data();
+            uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
+            uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
+            uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
+            exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing);
+            m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            launches += 2 + m_sorter.lastLaunchCount();
+            VtHashParams hp = H.MakeParams(N, P.particleDiameter);
+            if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, m_sorted,
+                                                          hp, m_instancing, m_ddOwnedMask)) {
+                launches += 2;
+            } else {
+                exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
+                launches++;
+            }
+        }
+        ops.collide(L, buf[cur], buf[other], m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0, ownedIds, ownedCount);
+        launches++;
+        wait();  // every peer has signalled: their `other` is free to be written
+        push_halo(other);
+        wait();
+        std::swap(cur, other);
+        for (int iteration = 0; iteration < P.numIterations; iteration++) {
+            if (sub.numTiles) {
+                ops.iterate(L, buf[cur], buf[other], sub, m_slotsDev, fp, m_instancing);
+                launches++;
+            }
+            push_halo(other);
+            wait();
+            std::swap(cur, other);
+        }
+        // all-gather of the substep result: every owned particle into every peer's array at the same index
+        ddpeer::launch_push_owned(m_stream, T, ctl, cur, buf[cur], ownedIds, ownedCount);
+        launches++;
+        wait();
+        const bool last = substep == P.numSubsteps - 1;
+        ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
+                        reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
+        launches++;
+        if (!last) std::swap(cur, other);
+    }
+    ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()), m_instancing);
+    launches++;
+    VT_CUDA(cudaGetLastError());
+    m_ddGraphLaunches = launches;
+}
+
+void VtClothSolverGPU::ddSimulate(float frameTime)
+{
+    if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
+    if (!m_ddPeersReady) throw Error(VELVET_ERR_STATE, "ddSimulate: peers are not mapped (ddPeerExport / ddPeerImport)");
+    VT_CUDA(cudaSetDevice(m_device));
+    if (m_topologyDirty) throw Error(VELVET_ERR_STATE, "the cloth changed after ddSetup: call ddSetup again");
+    if (simParams.numSubsteps <= 0 || simParams.interleavedHash <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "bad substep parameters");
+    FrameParams hp;
+    hp.P = simParams;
+    hp.frameTime = frameTime;
+    hp.substepTime = frameTime / (float)simParams.numSubsteps;
+    hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
+    hp.numColliders = (uint)sdfColliders.size();
+    VT_CUDA(cudaMemcpyAsync(m_frameParams.data(), &hp, sizeof(hp), cudaMemcpyHostToDevice, m_stream));
+    const unsigned long long key = topologyKey() | 1ull;
+    if (!m_ddGraphExec || key != m_ddGraphKey) {
+        if (m_ddGraphExec) cudaGraphExecDestroy(m_ddGraphExec);
+        if (m_ddGraph) cudaGraphDestroy(m_ddGraph);
+        m_ddGraphExec = nullptr;
+        m_ddGraph = nullptr;
+        VT_CUDA(cudaStreamBeginCapture(m_stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            recordDDFrame();
+        } catch (...) {
+            cudaGraph_t broken = nullptr;
+            cudaStreamEndCapture(m_stream, &broken);
+            if (broken) cudaGraphDestroy(broken);
+            throw;
+        }
+        VT_CUDA(cudaStreamEndCapture(m_stream, &m_ddGraph));
+        VT_CUDA(cudaGraphInstantiate(&m_ddGraphExec, m_ddGraph, 0));
+        m_ddGraphKey = key;
+    }
+    VT_CUDA(cudaGraphLaunch(m_ddGraphExec, m_stream));
+    m_lastLaunches = m_ddGraphLaunches;
 }
 
 void VtClothSolverGPU::Simulate() { Simulate(kFixedDeltaTime); }

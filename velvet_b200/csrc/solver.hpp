@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "dd_peer.cuh"
 #include "fused_kernels.cuh"
 #include "radix_sort.cuh"
 #include "seam.hpp"
@@ -110,6 +111,14 @@ public:
     void ddGatherUnpack();
     void ddSubstepEnd(int substep);
     void ddFrameEnd();
+    // NVLink peer-memory transport (dd_peer.cuh): export this rank's IPC handles, map the peers', then run whole frames
+    // as one CUDA graph with no host or NCCL in the loop.
+    static size_t ddPeerBlobBytes();
+    void ddPeerExport(void* blob);
+    void ddPeerImport(const void* blobs, size_t blobBytes);  // `world` blobs, rank-major (own entry ignored)
+    void ddPeerClose();
+    void ddSimulate(float frameTime);
+    bool ddPeerError();  // true when a wait kernel timed out (peer missing); synchronises the stream
 
     // bulk variants (one memcpy instead of a managed-memory push_back per element)
     void AddStretchBulk(const int* idxPairs, const float* distances, size_t n);
@@ -177,6 +186,17 @@ private:
     DeviceBuffer<unsigned char> m_ddOwnedMask;
     DeviceBuffer<float4> m_ddSendBuf, m_ddRecvBuf, m_ddGatherSend, m_ddGatherRecv;
     float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
+    void recordDDFrame();
+    DeviceBuffer<unsigned> m_ddFlags;
+    DeviceBuffer<ddpeer::Control> m_ddCtl;
+    DeviceBuffer<unsigned char> m_ddSendPeer;
+    ddpeer::PeerTable m_ddPeers{};
+    std::vector<void*> m_ddOpened;
+    bool m_ddPeersReady = false;
+    unsigned long long m_ddGraphKey = 0;
+    cudaGraph_t m_ddGraph = nullptr;
+    cudaGraphExec_t m_ddGraphExec = nullptr;
+    int m_ddGraphLaunches = 0;
     bool m_instanced = false;
     int m_lastLaunches = 0;
     std::shared_ptr<SpatialHashGPU> m_spatialHash;

@@ -1,9 +1,14 @@
 """One large cloth decomposed over several GPUs (north_star mode 2): one process per GPU (torchrun), every rank registers
-the same cloth, rank r runs the Jacobi iterations of its own tile range, and the boundary particles move over
-NVLink with torch.distributed (NCCL) once per iteration; predicted positions are all-gathered once per substep.
+the same cloth, rank r runs the Jacobi iterations of its own tile range, the boundary particles move over NVLink once
+per iteration and the predicted positions are all-gathered once per substep.  Two transports:
 
-The solver's stepped C ABI (velvet_solver_dd_*) does the compute on the solver's stream; this module only moves bytes
-between tensors that alias the solver's device buffers.  Results are bit-identical to the single-GPU solver.
+* "peer" (default): the library's own kernels store boundary particles straight into the peers' arrays (CUDA IPC mappings)
+  and order them with epoch flags; a frame is one CUDA graph per rank (velvet_solver_dd_simulate).  torch.distributed is
+  used once, to all-gather the 216-byte IPC blobs.
+* "nccl": the stepped C ABI (velvet_solver_dd_step) with torch.distributed send/recv + all_gather between the steps, on
+  tensors that alias the solver's device buffers.  Fallback when IPC mappings are unavailable, and the cross-check.
+
+Both are bit-identical to the single-GPU solver.
 """
 from __future__ import annotations
 
@@ -48,7 +53,7 @@ class _DevicePtr:
 
 
 class DecomposedCloth:
-    def __init__(self, solver, device_index: int):
+    def __init__(self, solver, device_index: int, transport: str = "peer"):
         import torch
         import torch.distributed as dist
         if not dist.is_initialized():
@@ -76,6 +81,48 @@ class DecomposedCloth:
         self.gather_send = alias(self.info.gatherSend, self.info.maxOwnedCount)
         self.gather_recv = alias(self.info.gatherRecv, self.info.maxOwnedCount * self.world)
         self.halo_bytes_per_iteration = 16 * (self.info.sendTotal + self.info.recvTotal)
+        if transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
+        self.transport = "nccl"
+        self.peer_error = None
+        if transport == "peer" and self.world > 1:
+            self._map_peers(dev)
+
+    def _map_peers(self, dev):
+        """All-gather the IPC blobs and map the peers' arrays; every rank agrees on the outcome (peer, or nccl fallback)."""
+        torch, dist, L = self.torch, self.dist, self._L
+        L.velvet_dd_peer_blob_bytes.restype = C.c_size_t
+        L.velvet_solver_dd_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.velvet_solver_dd_peer_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.velvet_solver_dd_peer_close.argtypes = [C.c_void_p]
+        L.velvet_solver_dd_simulate.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        nbytes = int(L.velvet_dd_peer_blob_bytes())
+        blob = (C.c_ubyte * nbytes)()
+        check(L.velvet_solver_dd_peer_export(self.solver._h, blob))
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        everyone = torch.empty(nbytes * self.world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine)
+        raw = everyone.cpu().numpy().tobytes()
+        ok = 1
+        try:
+            check(L.velvet_solver_dd_peer_import(self.solver._h, raw, nbytes))
+        except _capi.VelvetError as e:
+            self.peer_error = str(e)
+            ok = 0
+        agreed = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()) == 1:
+            self.transport = "peer"
+        else:
+            check(L.velvet_solver_dd_peer_close(self.solver._h))
+
+    def close(self):
+        """Unmap the peers (collective: every rank must call it before any rank destroys its solver)."""
+        if self.transport == "peer":
+            self.solver.Synchronize()
+            check(self._L.velvet_solver_dd_peer_close(self.solver._h))
+            self.dist.barrier()
+            self.transport = "closed"
 
     def _step(self, op: int, arg: int = 0, farg: float = 0.0):
         check(self._L.velvet_solver_dd_step(self.solver._h, op, arg, farg))
@@ -97,6 +144,11 @@ class DecomposedCloth:
                 w.wait()  # orders the solver stream after the transfer; does not block the host
 
     def Simulate(self, dt: float = 1.0 / 60.0, sync: bool = True):
+        if self.transport == "peer":
+            check(self._L.velvet_solver_dd_simulate(self.solver._h, dt, 1 if sync else 0))
+            return
+        if self.transport == "closed":
+            raise RuntimeError("DecomposedCloth.close() was called")
         P = self.solver.simParams
         with self.torch.cuda.stream(self.stream):
             self._step(DD_FRAME_BEGIN, 0, dt)
