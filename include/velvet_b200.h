@@ -143,6 +143,11 @@ VELVET_API int velvet_SortPairs(unsigned* keys, unsigned* values, unsigned numIt
 
 /* Stream used by the seam functions (a cudaStream_t); NULL = legacy default stream. */
 VELVET_API int velvet_seam_set_stream(void* cudaStream);
+/* Self-test of the library's IEEE division (vt_div and vec3 / scalar, vt_math.cuh): for device arrays x, y of n floats writes
+ * the bits of vt_div(x[i], y[i]), of (x[i], x[i+1], x[i+2]) / y[i] (indices mod n, 3 words per i) and of the compiler's own
+ * x[i] / y[i].  All three must agree bit for bit with IEEE-754 division (tests/test_seam_gpu.py). */
+VELVET_API int velvet_selftest_division(const float* x, const float* y, unsigned n, unsigned* outDiv, unsigned* outVec3,
+                                        unsigned* outPlain);
 VELVET_API int velvet_device_synchronize(void);
 
 /* VtAllocBuffer / VtFreeBuffer (Common.cuh L66-78): managed memory, plus explicit copies. */

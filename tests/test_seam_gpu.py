@@ -222,3 +222,51 @@ def test_zero_sized_calls_are_noops(state):
     seam.HashObjects(0, 0, 0, 0, 0, 0, 0, vb.VtHashParams(0, 64, 0.1, 0.01, 0, 0.01))
     seam.SortPairs(0, 0, 0, 11)
     seam.synchronize()
+
+
+def test_library_division_is_ieee_for_every_operand_class():
+    """vt_div / vec3-by-scalar (vt_math.cuh) replace the compiler's division in every exact kernel: they must return the IEEE-754
+    round-to-nearest quotient for all operands -- random bit patterns, zeros of both signs, denormals, huge / tiny exponents,
+    inf and NaN -- bit for bit (NaNs compared as a class), against the compiler's x / y and against numpy on the CPU."""
+    from velvet_b200 import _capi
+    L = _capi.load()
+    L.velvet_selftest_division.argtypes = [C.c_void_p] * 2 + [C.c_uint] + [C.c_void_p] * 3
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-39, 3e38, -3e38, 2.0 ** -60, 2.0 ** 60,
+                        np.nextafter(np.float32(2.0 ** -60), np.float32(0)), np.nextafter(np.float32(2.0 ** 60), np.float32(np.inf)),
+                        1e-20, 1e20, 0.1, 3.0], np.float32)
+
+    def operands():
+        kind = rng.integers(0, 4, n)
+        bits = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)       # any bit pattern
+        moderate = (rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))).astype(np.float32)     # cloth-like magnitudes
+        wide = (rng.choice([-1.0, 1.0], n) * np.exp2(rng.uniform(-140, 127, n))).astype(np.float32)  # whole exponent range
+        spec = special[rng.integers(0, len(special), n)]
+        return np.where(kind == 0, bits, np.where(kind == 1, moderate, np.where(kind == 2, wide, spec))).astype(np.float32)
+
+    x, y = operands(), operands()
+    # every pair of specials at least once
+    sx, sy = np.meshgrid(special, special)
+    x[: sx.size], y[: sy.size] = sx.ravel(), sy.ravel()
+    dx, dy = dev(x), dev(y)
+    od = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ov = torch.zeros(3 * n, dtype=torch.int32, device="cuda")
+    op = torch.zeros(n, dtype=torch.int32, device="cuda")
+    _capi.check(L.velvet_selftest_division(dx.data_ptr(), dy.data_ptr(), n, od.data_ptr(), ov.data_ptr(), op.data_ptr()))
+    got = host(od).view(np.uint32)
+    vec = host(ov).view(np.uint32).reshape(n, 3)
+    plain = host(op).view(np.uint32)
+    with np.errstate(all="ignore"):
+        want = [(np.roll(x, -k) / y) for k in range(3)]
+
+    def same(a_bits, ref):
+        a = a_bits.view(np.float32)
+        return (a_bits == ref.view(np.uint32)) | (np.isnan(a) & np.isnan(ref))
+
+    assert same(plain, want[0]).all(), "the compiler's own division disagrees with the CPU: not an IEEE environment"
+    bad = ~same(got, want[0])
+    assert not bad.any(), (x[bad][:5], y[bad][:5], got[bad][:5], want[0].view(np.uint32)[bad][:5])
+    for k in range(3):
+        bad = ~same(np.ascontiguousarray(vec[:, k]), want[k])
+        assert not bad.any(), (k, np.roll(x, -k)[bad][:5], y[bad][:5])

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ 
                 const float distance = length(diff);
                 if (distance >= D) continue;
                 const vec3 gradient = diff / (distance + VT_EPSILON);
-                const float lambda = (distance - D) / denom;
+                const float lambda = vt_div(distance - D, denom);
                 const vec3 common = lambda * gradient;
                 deltaCount++;
                 positionDelta -= w_i * common;

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(BLOCK) collide_particles_kernel(float* deltas,
         const float distance = length(diff);
         if (distance >= P.particleDiameter) continue;
         const vec3 gradient = diff / (distance + VT_EPSILON);
-        const float lambda = (distance - P.particleDiameter) / denom;
+        const float lambda = vt_div(distance - P.particleDiameter, denom);
         const vec3 common = lambda * gradient;
         deltaCount++;
         positionDelta -= w_i * common;
@@ -390,6 +390,24 @@ using namespace velvet;
 #define VT_REQUIRE(cond, msg) \
     if (!(cond)) return set_error(VELVET_ERR_INVALID_ARGUMENT, msg)
 
+
+// ---- self-test of vt_div / vec3 operator/ (vt_math.cuh): quotients as raw bits, next to the compiler's own division
+namespace velvet { namespace {
+__global__ void selftest_division_kernel(const float* __restrict__ x, const float* __restrict__ y, unsigned n, unsigned* __restrict__ outDiv,
+                                         unsigned* __restrict__ outVec, unsigned* __restrict__ outPlain)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = x[i], b = x[(i + 1) % n], c = x[(i + 2) % n], d = y[i];
+    outDiv[i] = __float_as_uint(vt_div(a, d));
+    const vec3 v = V3(a, b, c) / d;
+    outVec[3 * (size_t)i + 0] = __float_as_uint(v.x);
+    outVec[3 * (size_t)i + 1] = __float_as_uint(v.y);
+    outVec[3 * (size_t)i + 2] = __float_as_uint(v.z);
+    outPlain[i] = __float_as_uint(__fdiv_rn(a, d));
+}
+} }  // namespace
+
 extern "C" {
 
 int velvet_SetSimulationParams(const VtSimParams* hostParams)
@@ -539,6 +557,16 @@ int velvet_SortPairs(unsigned* keys, unsigned* values, unsigned numItems, int en
         VT_CUDA(cudaMemcpyAsync(keys, g_keysAlt.data(), sizeof(unsigned) * numItems, cudaMemcpyDeviceToDevice, g_stream));
         VT_CUDA(cudaMemcpyAsync(values, g_valsAlt.data(), sizeof(unsigned) * numItems, cudaMemcpyDeviceToDevice, g_stream));
     }
+    VT_API_END
+}
+
+int velvet_selftest_division(const float* x, const float* y, unsigned n, unsigned* outDiv, unsigned* outVec3, unsigned* outPlain)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(x && y && outDiv && outVec3 && outPlain && n > 0, "selftest_division: bad argument");
+    velvet::selftest_division_kernel<<<(n + 255) / 256, 256>>>(x, y, n, outDiv, outVec3, outPlain);
+    VT_CUDA(cudaGetLastError());
+    VT_CUDA(cudaDeviceSynchronize());
     VT_API_END
 }
 
