@@ -314,6 +314,11 @@ VELVET_API int velvet_solver_dd_peer_export(VelvetSolver* s, void* blob);
 VELVET_API int velvet_solver_dd_peer_import(VelvetSolver* s, const void* blobs, size_t blobBytes);
 VELVET_API int velvet_solver_dd_peer_close(VelvetSolver* s);
 VELVET_API int velvet_solver_dd_simulate(VelvetSolver* s, float deltaTime, int sync);
+/* Host-only: shape of the Jacobi tile plan of a grid cloth (what the fused pipeline builds at registration), for tests and
+ * tuning without a GPU.  perTile4 (may be NULL) receives {nOwned, nHalo, nStretch, nBend} for the first capacityTiles tiles;
+ * globals4 (may be NULL) = {maxLocals, maxKS, maxKB, maxBendPerTile}. */
+VELVET_API int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, unsigned* perTile4, unsigned capacityTiles,
+                                      unsigned* globals4);
 /* Host-only: the exchange lists of `rank` for a grid cloth of `resolution` cut into `world` ranks with tiles of
  * `tileSize` particles (what dd_setup computes), for tests without a GPU.  ids arrays may be NULL to query counts only:
  * counts[q] / counts[world + q] = number of particle ids sent to / received from rank q. */

@@ -482,6 +482,38 @@ int velvet_dd_plan_grid(int resolution, int tileSize, int rank, int world, unsig
     VT_API_END
 }
 
+int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, unsigned* perTile4, unsigned capacityTiles, unsigned* globals4)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(resolution > 0 && numTiles, "plan_grid_tiles: bad argument");
+    const int R = resolution;
+    const size_t n = (size_t)(R + 1) * (R + 1);
+    std::vector<float> v(3 * n);
+    std::vector<unsigned> idx((size_t)6 * R * R);
+    GenerateClothMesh(R, v.data(), idx.data());
+    const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const GridConstraints g = GenerateGridConstraints(R, v.data(), idx.data(), identity, {}, 1.5f, 0);
+    const TilePlan plan = build_tile_plan((unsigned)n, v.data(), g.stretchIdx.data(), g.stretchLen.data(), g.stretchLen.size(),
+                                          g.bendIdx.data(), g.bendAngle.data(), g.bendAngle.size(), nullptr, nullptr, nullptr, 0,
+                                          tileSize ? tileSize : 256);
+    if (!plan.valid) return set_error(VELVET_ERR_UNSUPPORTED, plan.whyInvalid);
+    *numTiles = (unsigned)plan.tiles.size();
+    if (perTile4)
+        for (size_t t = 0; t < plan.tiles.size() && t < capacityTiles; t++) {
+            perTile4[4 * t + 0] = plan.tiles[t].nOwned;
+            perTile4[4 * t + 1] = plan.tiles[t].nHalo;
+            perTile4[4 * t + 2] = plan.tiles[t].nStretch;
+            perTile4[4 * t + 3] = plan.tiles[t].nBend;
+        }
+    if (globals4) {
+        globals4[0] = plan.maxLocals;
+        globals4[1] = plan.maxKS;
+        globals4[2] = plan.maxKB;
+        globals4[3] = plan.maxBendPerTile;
+    }
+    VT_API_END
+}
+
 int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects, float hashCellSizeScalar,
                        int maxNumNeighbors)
 {

@@ -165,13 +165,14 @@ __global__ void __launch_bounds__(PB) collide_kernel(const float4* __restrict__ 
 
 // ---------------------------------------------------------------- tile-fused Jacobi iteration
 //
-// Shared memory: sp[maxLocals] float4     tile + halo predicted positions, w = invMass
-//                slots[maxK][tileSize] float4   xyz = correction, w = 1 if the constraint was active
+// Shared memory: sp[maxLocals] float4            tile + halo predicted positions, w = invMass
+//                slots[maxK][tileSize] float4    xyz = correction, w = 1 if the constraint was active
+//                s_brec[maxBendPerTile] uint4, s_srec[maxStretchPerTile] uint2   the tile's constraint records
 // Slot (ordinal k, particle l) lives at slots[k * tileSize + l]: the per-particle sums read consecutive 16-byte words
 // (no bank conflicts); constraint threads scatter, but consecutive constraints touch neighbouring particles.
-// All global loads of a tile (positions, halo, constraint records) are issued before the first barrier so that their
-// latencies overlap; on a grid cloth one chunk covers the whole tile.
-constexpr int IT_SR = 5;  // stretch records per thread per chunk
+// Every global load of a tile is issued before the first barrier so that the latencies overlap; the constraint records go
+// global -> shared with cp.async and never occupy registers (prefetching them into registers spilled under the 64-register
+// cap, and a spill store has to wait for its load: ncu showed the long-scoreboard stalls on exactly those STL).
 
 // slot index of an encoded endpoint: row = ordinal (low 5 bits), column = local particle index
 template <int LOG2T>
@@ -252,48 +253,43 @@ iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ pred
     extern __shared__ float4 s_mem[];
     float4* sp = s_mem;
     float4* slots = s_mem + plan.maxLocals;
-    const unsigned slotRows = (plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB) + 1;  // + the dump row
+    const unsigned slotRows = plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB;
     uint4* s_brec = reinterpret_cast<uint4*>(slots + (slotRows << LOG2T));
+    uint2* s_srec = reinterpret_cast<uint2*>(s_brec + plan.maxBendPerTile);
 
     const TileDesc td = plan.tiles[blockIdx.x];
     const unsigned tid = threadIdx.x;
     const bool owner = tid < td.nOwned;
 
-    // ---- issue every global load of the tile up front; bend records go straight to shared memory (cp.async, no
-    //      registers held across the stretch phase)
+    // ---- issue every global load of the tile up front: first the particle ids (the position gathers depend on them), then
+    //      the constraint records (independent, they cover the id latency), then the position gathers
+    unsigned gid = 0, hid = 0, cntS = 0, cntB = 0;
+    if (owner) gid = __ldg(plan.ownedIds + td.ownedOff + tid);
+    if (tid < td.nHalo) hid = __ldg(plan.haloIds + td.haloOff + tid);
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(plan.stretchRec + td.stretchOff);  // even offset: 16-byte aligned
+        const unsigned pairs = (td.nStretch + 1) >> 1;
+        for (unsigned c = tid; c < pairs; c += T) cp_async_16(reinterpret_cast<uint4*>(s_srec) + c, g + c);
+    }
     for (unsigned c = tid; c < td.nBend; c += T) cp_async_16(s_brec + c, plan.bendRec + td.bendOff + c);
-    unsigned gid = 0, cntS = 0, cntB = 0;
-    float4 mine = make_float4(0, 0, 0, 0);
     if (owner) {
-        gid = __ldg(plan.ownedIds + td.ownedOff + tid);
+        cp_async_16(sp + tid, predIn + gid);  // positions travel global -> shared without passing through registers
         cntS = __ldg(plan.sCnt + td.ownedOff + tid);
         cntB = __ldg(plan.bCnt + td.ownedOff + tid);
     }
-    uint2 srec[IT_SR];
-#pragma unroll
-    for (int j = 0; j < IT_SR; j++) {
-        const unsigned c = tid + j * T;
-        srec[j] = c < td.nStretch ? __ldg(plan.stretchRec + td.stretchOff + c) : make_uint2(0, 0);
-    }
-    if (owner) {
-        mine = predIn[gid];
-        sp[tid] = mine;
-    }
-    for (unsigned i = tid; i < td.nHalo; i += T) sp[td.nOwned + i] = predIn[__ldg(plan.haloIds + td.haloOff + i)];
+    if (tid < td.nHalo) cp_async_16(sp + td.nOwned + tid, predIn + hid);
+    for (unsigned i = tid + T; i < td.nHalo; i += T) cp_async_16(sp + td.nOwned + i, predIn + __ldg(plan.haloIds + td.haloOff + i));
     cp_async_wait_all();
     __syncthreads();
 
     // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
-#pragma unroll
-    for (int j = 0; j < IT_SR; j++)
-        if (tid + j * T < td.nStretch) stretch_to_slots<LOG2T>(srec[j], sp, slots, plan.maxKS);
-    for (unsigned c = tid + IT_SR * T; c < td.nStretch; c += T)  // irregular meshes: remaining chunks
-        stretch_to_slots<LOG2T>(__ldg(plan.stretchRec + td.stretchOff + c), sp, slots, plan.maxKS);
+    for (unsigned c = tid; c < td.nStretch; c += T) stretch_to_slots<LOG2T>(s_srec[c], sp, slots, plan.maxKS);
     __syncthreads();
 
     vec3 delta = V3(0, 0, 0);
     float count = 0;
     if (owner) {
+        const float4 mine = sp[tid];
         sum_slots<LOG2T>(slots, tid, cntS, delta, count);
         // SolveAttachment_Kernel, L218-234: per-particle, no slot needed
         if (plan.hasAttach) {
@@ -319,6 +315,7 @@ iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ pred
     if (owner) {
         sum_slots<LOG2T>(slots, tid, cntB, delta, count);
         // ApplyDeltas_Kernel, L257-263
+        const float4 mine = sp[tid];
         vec3 p = V3(mine);
         if (count > 0) p += delta / count * fp->P.relaxationFactor;
         predOut[gid] = F4(p, mine.w);
@@ -425,10 +422,9 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
 {
-    // sp[maxLocals] + slot rows + a dump row; halo endpoints store to (dumpRow * T + local) with local < maxLocals,
-    // so the dump row is maxLocals wide
-    const size_t rows = (size_t)(plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB) + 1;
-    return sizeof(float4) * ((size_t)plan.maxLocals + rows * plan.threads + plan.maxBendPerTile);
+    // sp[maxLocals] + slot rows (halo endpoints have no slot: they are not stored) + bend records + stretch records
+    const size_t rows = (size_t)(plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB);
+    return sizeof(float4) * ((size_t)plan.maxLocals + rows * plan.threads + plan.maxBendPerTile + ((size_t)plan.maxStretchPerTile + 1) / 2);
 }
 
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,

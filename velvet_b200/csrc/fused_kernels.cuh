@@ -27,7 +27,7 @@ struct TilePlanDev {
     const uint2* stretchRec;
     const uint4* bendRec;
     const uint2* attachRec;
-    unsigned numTiles, maxLocals, maxKS, maxKB, tileSize, maxBendPerTile;
+    unsigned numTiles, maxLocals, maxKS, maxKB, tileSize, maxBendPerTile, maxStretchPerTile;
     unsigned threads;  // CTA size: the power of two >= tileSize (slot rows are `threads` wide)
     unsigned hasAttach;
 };

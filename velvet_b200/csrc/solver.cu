@@ -509,6 +509,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.maxKS = m_plan.maxKS;
     m_planDev.maxKB = m_plan.maxKB;
     m_planDev.maxBendPerTile = m_plan.maxBendPerTile;
+    m_planDev.maxStretchPerTile = m_plan.maxStretchPerTile;
     m_planDev.tileSize = (uint)m_plan.tileSize;
     m_planDev.threads = m_plan.tileSize <= 128 ? 128u : (m_plan.tileSize <= 256 ? 256u : 512u);
     m_planDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;

@@ -142,7 +142,10 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
 
     // ---- 3. per tile: halo discovery, slot ordinals, records
     plan.tiles.resize(numTiles);
-    plan.stretchRec.resize(sList.size());
+    // stretch records of a tile start on a 16-byte boundary (pairs of 8-byte records are staged with 16-byte cp.async)
+    std::vector<size_t> sRecOff(numTiles + 1, 0);
+    for (unsigned t = 0; t < numTiles; t++) sRecOff[t + 1] = (sRecOff[t] + (sOff[t + 1] - sOff[t]) + 1) & ~(size_t)1;
+    plan.stretchRec.assign(sRecOff[numTiles], Rec2{0, 0});
     plan.bendRec.resize(bList.size());
     plan.attachRec.resize(aList.size());
     plan.sCnt.resize(N);
@@ -158,7 +161,7 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
         td.nOwned = std::min(N, td.ownedOff + T) - td.ownedOff;
         td.haloOff = (unsigned)plan.haloIds.size();
         td.nHalo = 0;
-        td.stretchOff = (unsigned)sOff[t];
+        td.stretchOff = (unsigned)sRecOff[t];
         td.nStretch = (unsigned)(sOff[t + 1] - sOff[t]);
         td.bendOff = (unsigned)bOff[t];
         td.nBend = (unsigned)(bOff[t + 1] - bOff[t]);
@@ -187,7 +190,7 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
         };
 
         for (unsigned i = 0; i < td.nStretch; i++) {
-            const unsigned c = sList[td.stretchOff + i];
+            const unsigned c = sList[sOff[t] + i];
             const unsigned ea = endpoint((unsigned)stretchIndices[2 * (size_t)c], cntS);
             const unsigned eb = endpoint((unsigned)stretchIndices[2 * (size_t)c + 1], cntS);
             plan.stretchRec[td.stretchOff + i] = Rec2{ea | (eb << 16), float_bits(stretchLengths[c])};
@@ -210,6 +213,7 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
         }
         plan.maxLocals = std::max(plan.maxLocals, td.nOwned + td.nHalo);
         plan.maxBendPerTile = std::max(plan.maxBendPerTile, td.nBend);
+        plan.maxStretchPerTile = std::max(plan.maxStretchPerTile, td.nStretch);
 
         // attach: CSR by owned particle, ascending constraint id inside each particle
         for (unsigned i = 0; i < td.nAttach; i++) cntA[localOf[(unsigned)attachParticleIDs[aList[td.attachOff + i]]]]++;
