@@ -237,89 +237,161 @@ __device__ __forceinline__ void sum_slots(const float4* __restrict__ slots, unsi
     }
 }
 
-template <int LOG2T>
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent, software-pipelined form: CTA b walks the work items b, b + gridDim.x, ... (work item = tile x instance).
+// While tile k is being solved, the inputs of tile k+1 are already on their way into shared memory:
+//   top of k      : positions of k+1 (gathered by id with cp.async into the other half of the double-buffered sp)
+//   after stretch : stretch records of k+1 (s_srec is free again)
+//   after bending : bending records of k+1 (s_brec is free again)
+// and the data those copies depend on is fetched one step earlier still (particle ids of k+2 during k, tile descriptor
+// of k+2 at the top of k), so that no global-memory latency sits on the critical path of a tile.  Without this the chain
+// descriptor -> ids -> positions (three dependent misses, ~2000 cycles) opened every tile: 30 % of all warp stalls (ncu).
 #ifndef VT_IT_REGCAP_BLOCKS
 #define VT_IT_REGCAP_BLOCKS 4  // resident 256-thread CTAs per SM the register budget is sized for
 #endif
+template <int LOG2T>
 __global__ void __launch_bounds__(1 << LOG2T, (VT_IT_REGCAP_BLOCKS * 256) >> LOG2T)
-iterate_tile_kernel(const float4* __restrict__ predIn, float4* __restrict__ predOut, const TilePlanDev plan,
-                    const float* __restrict__ attachSlotPositions, const FrameParams* __restrict__ fp, const Instancing inst)
+iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const TilePlanDev plan,
+                    const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
+                    const unsigned totalWork)
 {
     constexpr unsigned T = 1u << LOG2T;
-    // batched independent cloths: blockIdx.y selects the instance; the plan (tiles, records) is shared by all of them
-    predIn += (size_t)blockIdx.y * inst.particles;
-    predOut += (size_t)blockIdx.y * inst.particles;
-    attachSlotPositions += (size_t)blockIdx.y * inst.slots * 3;
+    constexpr unsigned TD_WORDS = sizeof(TileDesc) / 4;
     extern __shared__ float4 s_mem[];
-    float4* sp = s_mem;
-    float4* slots = s_mem + plan.maxLocals;
+    float4* const spBase = s_mem;  // two buffers of maxLocals
+    float4* const slots = s_mem + 2 * plan.maxLocals;
     const unsigned slotRows = plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB;
-    uint4* s_brec = reinterpret_cast<uint4*>(slots + (slotRows << LOG2T));
-    uint2* s_srec = reinterpret_cast<uint2*>(s_brec + plan.maxBendPerTile);
+    uint4* const s_brec = reinterpret_cast<uint4*>(slots + (slotRows << LOG2T));
+    uint2* const s_srec = reinterpret_cast<uint2*>(s_brec + plan.maxBendPerTile);
+    unsigned* const s_tdw = reinterpret_cast<unsigned*>(s_srec + ((plan.maxStretchPerTile + 1u) & ~1u));  // ring of 3 descriptors
+    const TileDesc* const s_td = reinterpret_cast<const TileDesc*>(s_tdw);
 
-    const TileDesc td = plan.tiles[blockIdx.x];
     const unsigned tid = threadIdx.x;
-    const bool owner = tid < td.nOwned;
+    const unsigned stride = gridDim.x;
+    unsigned w = blockIdx.x;
+    if (w >= totalWork) return;
+    const float xpbd_bend = fp->xpbdBend;
 
-    // ---- issue every global load of the tile up front: first the particle ids (the position gathers depend on them), then
-    //      the constraint records (independent, they cover the id latency), then the position gathers
-    unsigned gid = 0, hid = 0, cntS = 0, cntB = 0;
-    if (owner) gid = __ldg(plan.ownedIds + td.ownedOff + tid);
-    if (tid < td.nHalo) hid = __ldg(plan.haloIds + td.haloOff + tid);
-    {
-        const uint4* g = reinterpret_cast<const uint4*>(plan.stretchRec + td.stretchOff);  // even offset: 16-byte aligned
-        const unsigned pairs = (td.nStretch + 1) >> 1;
+    // the batched-instances case: work item -> (instance, tile); the plan is shared by all instances
+    auto tile_of = [&](unsigned item) { return inst.count > 1 ? item % plan.numTiles : item; };
+    auto inst_of = [&](unsigned item) { return inst.count > 1 ? item / plan.numTiles : 0u; };
+    auto issue_positions = [&](float4* sp, const TileDesc& d, const float4* predIn, unsigned gid, unsigned hid) {
+        if (tid < d.nOwned) cp_async_16(sp + tid, predIn + gid);
+        // halo locals start at tileSize in every tile (tile_plan.cpp), so these never touch an entry another thread still reads
+        if (tid < d.nHalo) cp_async_16(sp + plan.tileSize + tid, predIn + hid);
+        for (unsigned i = tid + T; i < d.nHalo; i += T)
+            cp_async_16(sp + plan.tileSize + i, predIn + __ldg(plan.haloIds + d.haloOff + i));
+    };
+    auto issue_stretch = [&](const TileDesc& d) {
+        const uint4* g = reinterpret_cast<const uint4*>(plan.stretchRec + d.stretchOff);  // even offset: 16-byte aligned
+        const unsigned pairs = (d.nStretch + 1) >> 1;
         for (unsigned c = tid; c < pairs; c += T) cp_async_16(reinterpret_cast<uint4*>(s_srec) + c, g + c);
-    }
-    for (unsigned c = tid; c < td.nBend; c += T) cp_async_16(s_brec + c, plan.bendRec + td.bendOff + c);
-    if (owner) {
-        cp_async_16(sp + tid, predIn + gid);  // positions travel global -> shared without passing through registers
-        cntS = __ldg(plan.sCnt + td.ownedOff + tid);
-        cntB = __ldg(plan.bCnt + td.ownedOff + tid);
-    }
-    if (tid < td.nHalo) cp_async_16(sp + td.nOwned + tid, predIn + hid);
-    for (unsigned i = tid + T; i < td.nHalo; i += T) cp_async_16(sp + td.nOwned + i, predIn + __ldg(plan.haloIds + td.haloOff + i));
-    cp_async_wait_all();
-    __syncthreads();
+    };
+    auto issue_bend = [&](const TileDesc& d) {
+        for (unsigned c = tid; c < d.nBend; c += T) cp_async_16(s_brec + c, plan.bendRec + d.bendOff + c);
+    };
+    auto load_ids = [&](const TileDesc& d, unsigned& gid, unsigned& hid) {
+        gid = tid < d.nOwned ? __ldg(plan.ownedIds + d.ownedOff + tid) : 0u;
+        hid = tid < d.nHalo ? __ldg(plan.haloIds + d.haloOff + tid) : 0u;
+    };
 
-    // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
-    for (unsigned c = tid; c < td.nStretch; c += T) stretch_to_slots<LOG2T>(s_srec[c], sp, slots, plan.maxKS);
+    // ---- pipeline prologue: descriptors of the first two items, everything of the first, ids of the second
+    if (tid < TD_WORDS) s_tdw[tid] = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w)) + tid);
+    if (tid >= 32 && tid < 32 + TD_WORDS && w + stride < totalWork)
+        s_tdw[TD_WORDS + tid - 32] = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w + stride)) + tid - 32);
     __syncthreads();
+    unsigned gidCur, gidNext = 0, hidNext = 0;
+    {
+        unsigned hid;
+        load_ids(s_td[0], gidCur, hid);
+        issue_positions(spBase, s_td[0], predInAll + (size_t)inst_of(w) * inst.particles, gidCur, hid);
+        cp_async_commit();  // P(0)
+        issue_stretch(s_td[0]);
+        cp_async_commit();  // S(0)
+        issue_bend(s_td[0]);
+        cp_async_commit();  // B(0)
+        if (w + stride < totalWork) load_ids(s_td[1], gidNext, hidNext);
+    }
 
-    vec3 delta = V3(0, 0, 0);
-    float count = 0;
-    if (owner) {
-        const float4 mine = sp[tid];
-        sum_slots<LOG2T>(slots, tid, cntS, delta, count);
-        // SolveAttachment_Kernel, L218-234: per-particle, no slot needed
-        if (plan.hasAttach) {
-            const float lrs = fp->P.longRangeStretchiness;
-            const unsigned a1 = __ldg(plan.attOff + td.baseOff + tid + 1);
-            for (unsigned a = __ldg(plan.attOff + td.baseOff + tid); a < a1; a++) {
-                const uint2 r = __ldg(plan.attachRec + td.attachOff + a);
-                vec3 corr;
-                if (attach_eval(V3(mine), mine.w, load3(attachSlotPositions, r.x), __uint_as_float(r.y), lrs, corr)) {
-                    delta += corr;
-                    count += 1.0f;
+    for (unsigned k = 0; w < totalWork; k++, w += stride) {
+        const unsigned slotCur = k % 3, slotNext = (k + 1) % 3, slotNN = (k + 2) % 3;
+        const TileDesc& td = s_td[slotCur];
+        float4* const sp = spBase + (k & 1u) * plan.maxLocals;
+        const bool hasNext = w + stride < totalWork;
+        const bool hasNN = w + 2 * (size_t)stride < totalWork;
+        const size_t instOff = (size_t)inst_of(w) * inst.particles;
+        const bool owner = tid < td.nOwned;
+
+        // descriptor of k+2 (lands in the ring after the first barrier), positions of k+1
+        unsigned tdWord = 0;
+        if (hasNN && tid < TD_WORDS) tdWord = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w + 2 * stride)) + tid);
+        if (hasNext)
+            issue_positions(spBase + ((k + 1) & 1u) * plan.maxLocals, s_td[slotNext],
+                            predInAll + (size_t)inst_of(w + stride) * inst.particles, gidNext, hidNext);
+        cp_async_commit();      // P(k+1)
+        cp_async_wait_group<2>();  // P(k) and S(k) have landed; B(k), P(k+1) may still be in flight
+        __syncthreads();
+        if (hasNN && tid < TD_WORDS) s_tdw[slotNN * TD_WORDS + tid] = tdWord;
+        unsigned cntS = 0, cntB = 0;
+        if (owner) {
+            cntS = __ldg(plan.sCnt + td.ownedOff + tid);
+            cntB = __ldg(plan.bCnt + td.ownedOff + tid);
+        }
+
+        // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
+        for (unsigned c = tid; c < td.nStretch; c += T) stretch_to_slots<LOG2T>(s_srec[c], sp, slots, plan.maxKS);
+        __syncthreads();
+
+        if (hasNext) issue_stretch(s_td[slotNext]);
+        cp_async_commit();  // S(k+1)
+        unsigned gidNN = 0, hidNN = 0;
+        if (hasNN) load_ids(s_td[slotNN], gidNN, hidNN);  // consumed at the top of k+1
+
+        vec3 delta = V3(0, 0, 0);
+        float count = 0;
+        if (owner) {
+            sum_slots<LOG2T>(slots, tid, cntS, delta, count);
+            // SolveAttachment_Kernel, L218-234: per-particle, no slot needed
+            if (plan.hasAttach) {
+                const float4 mine = sp[tid];
+                const float* attachSlotPositions = attachSlotsAll + (size_t)inst_of(w) * inst.slots * 3;
+                const float lrs = fp->P.longRangeStretchiness;
+                const unsigned a1 = __ldg(plan.attOff + td.baseOff + tid + 1);
+                for (unsigned a = __ldg(plan.attOff + td.baseOff + tid); a < a1; a++) {
+                    const uint2 r = __ldg(plan.attachRec + td.attachOff + a);
+                    vec3 corr;
+                    if (attach_eval(V3(mine), mine.w, load3(attachSlotPositions, r.x), __uint_as_float(r.y), lrs, corr)) {
+                        delta += corr;
+                        count += 1.0f;
+                    }
                 }
             }
         }
-    }
-    __syncthreads();  // slots are reused by the bending phase
+        cp_async_wait_group<2>();  // B(k) has landed; P(k+1), S(k+1) may still be in flight
+        __syncthreads();           // slots are reused by the bending phase
 
-    // ---- SolveBending_Kernel, L128-188
-    const float xpbd_bend = fp->xpbdBend;
-    for (unsigned c = tid; c < td.nBend; c += T) bend_to_slots<LOG2T>(s_brec[c], sp, slots, xpbd_bend, plan.maxKB);
-    __syncthreads();
+        // ---- SolveBending_Kernel, L128-188
+        for (unsigned c = tid; c < td.nBend; c += T) bend_to_slots<LOG2T>(s_brec[c], sp, slots, xpbd_bend, plan.maxKB);
+        __syncthreads();
 
-    if (owner) {
-        sum_slots<LOG2T>(slots, tid, cntB, delta, count);
-        // ApplyDeltas_Kernel, L257-263
-        const float4 mine = sp[tid];
-        vec3 p = V3(mine);
-        if (count > 0) p += delta / count * fp->P.relaxationFactor;
-        predOut[gid] = F4(p, mine.w);
+        if (hasNext) issue_bend(s_td[slotNext]);
+        cp_async_commit();  // B(k+1)
+        if (owner) {
+            sum_slots<LOG2T>(slots, tid, cntB, delta, count);
+            // ApplyDeltas_Kernel, L257-263
+            const float4 mine = sp[tid];
+            vec3 p = V3(mine);
+            if (count > 0) p += delta / count * fp->P.relaxationFactor;
+            predOutAll[instOff + gidCur] = F4(p, mine.w);
+        }
+        gidCur = gidNext;
+        gidNext = gidNN;
+        hidNext = hidNN;
     }
+    cp_async_wait_all();
 }
 
 __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restrict__ predIn, float4* __restrict__ pos4,
@@ -422,29 +494,45 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
 {
-    // sp[maxLocals] + slot rows (halo endpoints have no slot: they are not stored) + bend records + stretch records
+    // 2 x sp[maxLocals] + slot rows (halo endpoints have no slot: they are not stored) + bend records + stretch records
+    // + a ring of three tile descriptors
     const size_t rows = (size_t)(plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB);
-    return sizeof(float4) * ((size_t)plan.maxLocals + rows * plan.threads + plan.maxBendPerTile + ((size_t)plan.maxStretchPerTile + 1) / 2);
+    return sizeof(float4) * (2 * (size_t)plan.maxLocals + rows * plan.threads + plan.maxBendPerTile + ((size_t)plan.maxStretchPerTile + 1) / 2) +
+           3 * sizeof(TileDesc);
 }
 
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst)
 {
-    const dim3 grid(plan.numTiles, inst.count);
+    const unsigned total = plan.numTiles * inst.count;
+    if (!total) return;
+    const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
     const size_t smem = iterate_smem_bytes(plan);
     switch (plan.threads) {
-    case 128: iterate_tile_kernel<7><<<grid, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst); break;
-    case 256: iterate_tile_kernel<8><<<grid, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst); break;
-    case 512: iterate_tile_kernel<9><<<grid, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst); break;
+    case 128: iterate_tile_kernel<7><<<grid, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); break;
+    case 256: iterate_tile_kernel<8><<<grid, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); break;
+    case 512: iterate_tile_kernel<9><<<grid, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); break;
     default: throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
     }
 }
 
-void configure_iterate_kernel(size_t smemBytes)
+// Opts in to > 48 KB dynamic shared memory and returns how many CTAs of `threads` threads the current device keeps resident.
+unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads)
 {
     VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    int dev = 0, sms = 0, perSm = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    VT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    switch (threads) {
+    case 128: VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<7>, 128, smemBytes)); break;
+    case 256: VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<8>, 256, smemBytes)); break;
+    case 512: VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<9>, 512, smemBytes)); break;
+    default: throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
+    }
+    if (perSm < 1) throw Error(VELVET_ERR_UNSUPPORTED, "the Jacobi tile kernel does not fit on an SM");
+    return (unsigned)(sms * perSm);
 }
 
 void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext, bool last,

@@ -518,8 +518,8 @@ void VtClothSolverGPU::ensureFusedResources()
         m_fallbackReason = "tile needs more than 200 KB of shared memory";
         return;
     }
-    exact_math::configure_iterate_kernel(smem);
-    fast_math::configure_iterate_kernel(smem);
+    m_planDev.residentCtas = std::min(exact_math::configure_iterate_kernel(smem, m_planDev.threads),
+                                      fast_math::configure_iterate_kernel(smem, m_planDev.threads));
 
     // vertex -> incident triangles, ascending triangle id
     {

@@ -183,7 +183,7 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
             }
             if (haloStamp[p] != t) {
                 haloStamp[p] = t;
-                haloLocal[p] = td.nOwned + td.nHalo++;
+                haloLocal[p] = T + td.nHalo++;  // halo locals start at the tile size, also in a partially filled tile
                 plan.haloIds.push_back(p);
             }
             return (haloLocal[p] << TP_ORD_BITS) | TP_NO_SLOT;
@@ -202,7 +202,7 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
             plan.bendRec[td.bendOff + i] = Rec4{e[0] | (e[1] << 16), e[2] | (e[3] << 16), float_bits(bendAngles[c]), c};
         }
         if (overflow) return fail("a particle has more than 30 stretch or bend constraints");
-        if (td.nOwned + td.nHalo > TP_MAX_LOCALS) return fail("tile halo too large (more than 2047 local particles)");
+        if (T + td.nHalo > TP_MAX_LOCALS) return fail("tile halo too large (more than 2047 local particles)");
 
         // per-particle constraint counts (the slot of ordinal k of particle l is slots[k * T + l])
         for (unsigned l = 0; l < td.nOwned; l++) {
@@ -211,7 +211,7 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
             plan.maxKS = std::max(plan.maxKS, cntS[l]);
             plan.maxKB = std::max(plan.maxKB, cntB[l]);
         }
-        plan.maxLocals = std::max(plan.maxLocals, td.nOwned + td.nHalo);
+        plan.maxLocals = std::max(plan.maxLocals, T + td.nHalo);
         plan.maxBendPerTile = std::max(plan.maxBendPerTile, td.nBend);
         plan.maxStretchPerTile = std::max(plan.maxStretchPerTile, td.nStretch);
 

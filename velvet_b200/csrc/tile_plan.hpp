@@ -54,7 +54,7 @@ struct TilePlan {
     std::vector<Rec2> stretchRec;        // {ea | eb << 16, restLength bits}; every tile's range starts at an even index
     std::vector<Rec4> bendRec;           // {e0 | e1 << 16, e2 | e3 << 16, restAngle bits, constraint id}
     std::vector<Rec2> attachRec;         // {slot id, distance bits}
-    unsigned maxLocals = 0;              // max over tiles of nOwned + nHalo
+    unsigned maxLocals = 0;              // tileSize + max over tiles of nHalo (halo locals start at tileSize)
     unsigned maxBendPerTile = 0;         // max over tiles of nBend (bend records are staged in shared memory)
     unsigned maxStretchPerTile = 0;      // max over tiles of nStretch (staged in shared memory as well)
     unsigned maxKS = 0, maxKB = 0;       // max stretch / bend constraints on one particle; slot rows are [k][local], plus a dump row
