@@ -148,6 +148,12 @@ VELVET_API int velvet_seam_set_stream(void* cudaStream);
  * x[i] / y[i].  All three must agree bit for bit with IEEE-754 division (tests/test_seam_gpu.py). */
 VELVET_API int velvet_selftest_division(const float* x, const float* y, unsigned n, unsigned* outDiv, unsigned* outVec3,
                                         unsigned* outPlain);
+/* Self-test of the checked-fast constraint evaluators (stretch_eval_u / bend_eval_u / vt_sqrt_u, vt_math.cuh) against the
+ * branchy evaluators: `operands` holds n records of 18 floats (p0..p3 xyz, w0..w3, rest, xpbd compliance term; the stretch
+ * test uses p0, p1, w0, w1, rest).  mismatches3 / fast3 are device arrays of 3 counters {stretch, bend, sqrt}: results that
+ * differ while the validity predicate held (must be 0) and how often it held; the sqrt test sweeps all 2^32 operands. */
+VELVET_API int velvet_selftest_constraints(const float* operands, unsigned n, unsigned long long* mismatches3,
+                                           unsigned long long* fast3);
 VELVET_API int velvet_device_synchronize(void);
 
 /* VtAllocBuffer / VtFreeBuffer (Common.cuh L66-78): managed memory, plus explicit copies. */

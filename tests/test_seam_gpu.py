@@ -270,3 +270,53 @@ def test_library_division_is_ieee_for_every_operand_class():
     for k in range(3):
         bad = ~same(np.ascontiguousarray(vec[:, k]), want[k])
         assert not bad.any(), (k, np.roll(x, -k)[bad][:5], y[bad][:5])
+
+
+def test_checked_fast_constraint_evaluators_match_the_branchy_ones():
+    """The Jacobi kernel evaluates constraints with branch-light IEEE sequences guarded by ONE validity predicate
+    (stretch_eval_u / bend_eval_u / vt_sqrt_u) and falls back to the plain evaluators when it fails.  Wherever the predicate
+    holds the results must be bit-identical -- cloth-like geometry (where it must hold almost always, or the fast path
+    would be pointless), degenerate geometry (repeated points, zero weights, rest length hit exactly) and arbitrary bit
+    patterns -- and the square root is swept over all 2^32 operands."""
+    from velvet_b200 import _capi
+    L = _capi.load()
+    L.velvet_selftest_constraints.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    h = 2.0 / 1023
+
+    def cloth_like(m):
+        base = rng.uniform(-1, 1, (m, 1, 3))
+        quad = np.array([[0, 0, 0], [h, h, 0], [h, 0, 0], [0, h, 0]])  # wing0, wing1, edge2, edge3
+        fold = rng.uniform(-0.6, 0.6, (m, 1)) * h
+        pts = base + quad[None] + rng.normal(0, 0.03 * h, (m, 4, 3))
+        pts[:, 1, 2] += fold[:, 0]
+        w = rng.choice([0.0, 1.0, 1.0, 1.0, 2.5], (m, 4))
+        rest = np.linalg.norm(pts[:, 0] - pts[:, 1], axis=1) * rng.uniform(0.9, 1.1, m)
+        return np.concatenate([pts.reshape(m, 12), w, rest[:, None], rng.choice([0.0, 1e-3], (m, 1))], axis=1)
+
+    a = cloth_like(n).astype(np.float32)
+    b = cloth_like(n).astype(np.float32)
+    # degenerate: exactly flat quads on a lattice (zero cross-product components, acos(1)), repeated points, all pinned
+    k = np.arange(n)
+    b[:, 2::3][:, :4] = 0.0
+    b[k % 7 == 0, 3:6] = b[k % 7 == 0, 0:3]
+    b[k % 11 == 0, 12:16] = 0.0
+    b[k % 13 == 0, 9:12] = b[k % 13 == 0, 6:9]
+    exact = (np.linalg.norm(b[:, 0:3].astype(np.float32) - b[:, 3:6].astype(np.float32), axis=1)).astype(np.float32)
+    b[k % 5 == 0, 16] = exact[k % 5 == 0]
+    c = rng.integers(0, 2 ** 32, (n, 18), dtype=np.uint64).astype(np.uint32).view(np.float32)        # any bit pattern
+    d = (rng.choice([-1.0, 1.0], (n, 18)) * np.exp2(rng.uniform(-140, 127, (n, 18)))).astype(np.float32)  # whole exponent range
+    counts = {}
+    for name, ops in (("cloth", a), ("degenerate", b), ("bits", c), ("wide", d)):
+        x = dev(np.ascontiguousarray(ops, np.float32))
+        mism = torch.zeros(3, dtype=torch.int64, device="cuda")
+        fast = torch.zeros(3, dtype=torch.int64, device="cuda")
+        _capi.check(L.velvet_selftest_constraints(x.data_ptr(), n, mism.data_ptr(), fast.data_ptr()))
+        m, fs = host(mism), host(fast)
+        counts[name] = (m.tolist(), fs.tolist())
+        assert m[0] == 0 and m[1] == 0 and m[2] == 0, (name, m, fs)
+    print("selftest_constraints (mismatches, fast-path valid):", counts)
+    # cloth-like operands: pinned-pinned pairs (1/25 of the stretch operands, 1/625 of the bends) are the only expected fallbacks
+    assert counts["cloth"][1][0] >= 0.94 * n and counts["cloth"][1][1] >= 0.98 * n
+    assert counts["cloth"][1][2] > 2 ** 30  # sqrt fast path covers [2^-101, 2^128)

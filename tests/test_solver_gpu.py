@@ -421,3 +421,41 @@ def test_empty_solver_and_error_convention():
         g.AddAttach(3, 0, 0.0)  # out of range -> error status, never exit()
     with pytest.raises(vb.VelvetError):
         g.SetTileSize(100)
+
+
+# ---------------------------------------------------------------- committed golden vectors (reference CUDA kernels on B200)
+@pytest.mark.parametrize("math_mode", [vb.MATH_EXACT, vb.MATH_FAST])
+def test_product_against_reference_kernel_golden_vectors(math_mode):
+    """tests/golden/refcuda_*.npz hold outputs of the reference's own VtClothSolverGPU.cu / SpatialHashGPU.cu (see
+    tests/golden/make_golden.py): positions within north_star's tolerance, spatial hash bit-exact on identical inputs."""
+    gold = np.load(os.path.join(GOLDEN, "refcuda_cfg1.npz"))
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, _ = make_pair(31, p, position=(0, 2.5, 0), rotation=(0, 0, 0), attached=[0, 31], oracle=False, math_mode=math_mode)
+    sphere = ColliderTrack(vb.COLLIDER_SPHERE, (0, 0.6, -1.0), (0.6, 0.6, 0.6))
+    plane = vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1))
+    for fr in range(15):
+        sphere.move((0, 0.6, -math.cos(2 * fr / 60.0)))
+        g.UpdateColliders([plane, sphere.collider()])
+        g.Simulate()
+        if fr + 1 in (1, 5, 10, 15):
+            assert max_abs_diff(g.download("positions"), gold[f"positions_{fr + 1}"]) <= TOL_1, fr + 1
+    gold = np.load(os.path.join(GOLDEN, "refcuda_drape64.npz"))
+    g, _ = make_pair(63, p, oracle=False, math_mode=math_mode)
+    g.UpdateColliders(vb.sphere_plane_colliders())
+    for fr in range(20):
+        g.Simulate()
+        if fr + 1 in (1, 10, 20):
+            assert max_abs_diff(g.download("positions"), gold[f"positions_{fr + 1}"]) <= (TOL_1 if fr == 0 else TOL_60), fr + 1
+    for R in (31, 63):
+        gold = np.load(os.path.join(GOLDEN, f"refcuda_hash_R{R}.npz"))
+        n = (R + 1) ** 2
+        g, _ = make_pair(R, gpu_params(), oracle=False, math_mode=math_mode)
+        g.upload("initialPositions", gold["initialPositions"])
+        g.upload("predicted", gold["predicted"])
+        g.Hash()
+        assert np.array_equal(g.download("particleHash"), gold["particleHash"])
+        assert np.array_equal(g.download("particleIndex"), gold["particleIndex"])
+        assert np.array_equal(g.download("cellStart"), gold["cellStart"])
+        valid = gold["cellStart"] != 0xFFFFFFFF
+        assert np.array_equal(g.download("cellEnd")[valid], gold["cellEnd"][valid])
+        assert np.array_equal(valid_prefix_table(g.download("neighbors"), n, 64), gold["neighbors"])

@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = [
     "velvet_SetSimulationParams", "velvet_InitializePositions", "velvet_PredictPositions", "velvet_SolveStretch",
     "velvet_SolveBending", "velvet_SolveAttachment", "velvet_ApplyDeltas", "velvet_CollideSDF",
     "velvet_CollideParticles", "velvet_Finalize", "velvet_ComputeNormal", "velvet_HashObjects", "velvet_SortPairs",
-    "velvet_seam_set_stream", "velvet_selftest_division", "velvet_device_synchronize", "velvet_alloc", "velvet_free", "velvet_copy",
+    "velvet_seam_set_stream", "velvet_selftest_division", "velvet_selftest_constraints", "velvet_device_synchronize", "velvet_alloc", "velvet_free", "velvet_copy",
     "velvet_solver_create", "velvet_solver_destroy", "velvet_solver_params", "velvet_solver_set_pipeline",
     "velvet_solver_set_math_mode", "velvet_solver_set_tile_size", "velvet_solver_add_cloth", "velvet_solver_add_stretch",
     "velvet_solver_add_attach_slot", "velvet_solver_add_attach", "velvet_solver_add_bend",

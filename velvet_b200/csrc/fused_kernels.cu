@@ -188,24 +188,77 @@ __device__ __forceinline__ void cp_async_16(void* smemDst, const void* gmemSrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int LOG2T>
-__device__ __forceinline__ void stretch_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots,
-                                                 unsigned dumpRow)
+// One constraint: positions from the staged tile, corrections into the endpoints' private slots.  An inactive constraint
+// stores +0 vectors with flag 0, so the per-particle sums need no select.
+// EXACT build: the checked-fast evaluators of vt_math.cuh; when their validity predicate fails (rare: pinned pair,
+// degenerate or non-finite geometry) the constraint is redone by an out-of-line copy of the branchy evaluator, so the hot
+// loop stays small and straight.  FAST build: the predicate is constant true.
+struct StretchOut {
+    vec3 c1, c2;
+    float flag;
+};
+__device__ __forceinline__ StretchOut stretch_solve(const uint2 r, const float4* __restrict__ sp, bool& ok)
 {
     const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
     const float4 pa = sp[ea >> TP_ORD_BITS], pb = sp[eb >> TP_ORD_BITS];
+    StretchOut o;
 #if VT_FAST_MATH
-    vec3 c1, c2;
-    const float flag = stretch_eval_flagged(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2) ? 1.0f : 0.0f;
+    const bool active = stretch_eval_flagged(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), o.c1, o.c2);
 #else
-    vec3 c1 = V3(0, 0, 0), c2 = c1;
-    const float flag = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), c1, c2) ? 1.0f : 0.0f;
+    const bool active = stretch_eval_u(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), o.c1, o.c2, ok);
 #endif
+    if (!active) o.c1 = o.c2 = V3(0, 0, 0);
+    o.flag = active ? 1.0f : 0.0f;
+    return o;
+}
+template <int LOG2T>
+__device__ __forceinline__ void stretch_store(const uint2 r, const StretchOut& o, float4* __restrict__ slots, unsigned dumpRow)
+{
+    const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
     // halo endpoints carry the dump-row ordinal and are simply not stored (a store into a shared dump row would be a
     // benign write-write race, but it would drown compute-sanitizer racecheck in false positives)
-    if ((ea & 31u) != dumpRow) slots[slot_of<LOG2T>(ea)] = F4(c1, flag);
-    if ((eb & 31u) != dumpRow) slots[slot_of<LOG2T>(eb)] = F4(c2, flag);
+    if ((ea & 31u) != dumpRow) slots[slot_of<LOG2T>(ea)] = F4(o.c1, o.flag);
+    if ((eb & 31u) != dumpRow) slots[slot_of<LOG2T>(eb)] = F4(o.c2, o.flag);
 }
+
+struct BendOut {
+    vec3 c0, c1, c2, c3;
+    float flag;
+};
+template <int LOG2T>
+__device__ __forceinline__ void bend_store(const uint4 r, const BendOut& o, float4* __restrict__ slots, unsigned dumpRow)
+{
+    const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
+    if ((e0 & 31u) != dumpRow) slots[slot_of<LOG2T>(e0)] = F4(o.c0, o.flag);
+    if ((e1 & 31u) != dumpRow) slots[slot_of<LOG2T>(e1)] = F4(o.c1, o.flag);
+    if ((e2 & 31u) != dumpRow) slots[slot_of<LOG2T>(e2)] = F4(o.c2, o.flag);
+    if ((e3 & 31u) != dumpRow) slots[slot_of<LOG2T>(e3)] = F4(o.c3, o.flag);
+}
+
+#if !VT_FAST_MATH
+template <int LOG2T>
+__device__ __noinline__ void stretch_slow_to_slots(const uint2 r, const float4* __restrict__ sp, float4* __restrict__ slots, unsigned dumpRow)
+{
+    const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
+    const float4 pa = sp[ea >> TP_ORD_BITS], pb = sp[eb >> TP_ORD_BITS];
+    StretchOut o;
+    o.c1 = o.c2 = V3(0, 0, 0);
+    o.flag = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), o.c1, o.c2) ? 1.0f : 0.0f;
+    stretch_store<LOG2T>(r, o, slots, dumpRow);
+}
+template <int LOG2T>
+__device__ __noinline__ void bend_slow_to_slots(const uint4 r, const float4* __restrict__ sp, float4* __restrict__ slots,
+                                                float xpbd_bend, unsigned dumpRow)
+{
+    const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
+    const float4 p0 = sp[e0 >> TP_ORD_BITS], p1 = sp[e1 >> TP_ORD_BITS], p2 = sp[e2 >> TP_ORD_BITS], p3 = sp[e3 >> TP_ORD_BITS];
+    BendOut o;
+    o.c0 = o.c1 = o.c2 = o.c3 = V3(0, 0, 0);
+    o.flag = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend, o.c0, o.c1,
+                       o.c2, o.c3) ? 1.0f : 0.0f;
+    bend_store<LOG2T>(r, o, slots, dumpRow);
+}
+#endif
 
 template <int LOG2T>
 __device__ __forceinline__ void bend_to_slots(const uint4 r, const float4* __restrict__ sp, float4* __restrict__ slots,
@@ -213,26 +266,35 @@ __device__ __forceinline__ void bend_to_slots(const uint4 r, const float4* __res
 {
     const unsigned e0 = r.x & 0xffffu, e1 = r.x >> 16, e2 = r.y & 0xffffu, e3 = r.y >> 16;
     const float4 p0 = sp[e0 >> TP_ORD_BITS], p1 = sp[e1 >> TP_ORD_BITS], p2 = sp[e2 >> TP_ORD_BITS], p3 = sp[e3 >> TP_ORD_BITS];
-    vec3 c0 = V3(0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
-    const float flag = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
-                                 c0, c1, c2, c3) ? 1.0f : 0.0f;
-    if ((e0 & 31u) != dumpRow) slots[slot_of<LOG2T>(e0)] = F4(c0, flag);
-    if ((e1 & 31u) != dumpRow) slots[slot_of<LOG2T>(e1)] = F4(c1, flag);
-    if ((e2 & 31u) != dumpRow) slots[slot_of<LOG2T>(e2)] = F4(c2, flag);
-    if ((e3 & 31u) != dumpRow) slots[slot_of<LOG2T>(e3)] = F4(c3, flag);
+    BendOut o;
+#if VT_FAST_MATH
+    o.c0 = o.c1 = o.c2 = o.c3 = V3(0, 0, 0);
+    const bool active = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
+                                  o.c0, o.c1, o.c2, o.c3);
+#else
+    bool ok = true;
+    const bool active = bend_eval_u(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, __uint_as_float(r.z), xpbd_bend,
+                                    o.c0, o.c1, o.c2, o.c3, ok);
+    if (!ok) {
+        bend_slow_to_slots<LOG2T>(r, sp, slots, xpbd_bend, dumpRow);
+        return;
+    }
+    if (!active) o.c0 = o.c1 = o.c2 = o.c3 = V3(0, 0, 0);
+#endif
+    o.flag = active ? 1.0f : 0.0f;
+    bend_store<LOG2T>(r, o, slots, dumpRow);
 }
 
-// Sum of a particle's slots in ordinal (= constraint id) order.  Inactive slots add +0, which is bit-neutral because the
-// accumulator starts at +0 and can never become -0.
+// Sum of a particle's slots in ordinal (= constraint id) order.  Inactive slots hold +0 vectors with flag 0: adding +0 is
+// bit-neutral because the accumulator starts at +0 and can never become -0.
 template <int LOG2T>
 __device__ __forceinline__ void sum_slots(const float4* __restrict__ slots, unsigned tid, unsigned n, vec3& delta, float& count)
 {
     for (unsigned k = 0; k < n; k++) {
         const float4 v = slots[(k << LOG2T) + tid];
-        const bool on = v.w != 0;
-        delta.x += on ? v.x : 0.0f;
-        delta.y += on ? v.y : 0.0f;
-        delta.z += on ? v.z : 0.0f;
+        delta.x += v.x;
+        delta.y += v.y;
+        delta.z += v.z;
         count += v.w;
     }
 }
@@ -297,6 +359,16 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         gid = tid < d.nOwned ? __ldg(plan.ownedIds + d.ownedOff + tid) : 0u;
         hid = tid < d.nHalo ? __ldg(plan.haloIds + d.haloOff + tid) : 0u;
     };
+    // stretch | bend << 8 constraint counts of this thread's particle; fetched one tile ahead (the compiler sinks a plain
+    // load to its first use after the stretch phase, where ncu showed it as the kernel's largest long-scoreboard stall)
+    auto load_counts = [&](const TileDesc& d) -> unsigned {
+        unsigned cs = 0, cb = 0;
+        if (tid < d.nOwned) {
+            asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cs) : "l"(plan.sCnt + d.ownedOff + tid));
+            asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cb) : "l"(plan.bCnt + d.ownedOff + tid));
+        }
+        return cs | (cb << 8);
+    };
 
     // ---- pipeline prologue: descriptors of the first two items, everything of the first, ids of the second
     if (tid < TD_WORDS) s_tdw[tid] = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w)) + tid);
@@ -304,6 +376,7 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         s_tdw[TD_WORDS + tid - 32] = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w + stride)) + tid - 32);
     __syncthreads();
     unsigned gidCur, gidNext = 0, hidNext = 0;
+    unsigned cntCur = load_counts(s_td[0]);
     {
         unsigned hid;
         load_ids(s_td[0], gidCur, hid);
@@ -332,17 +405,26 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             issue_positions(spBase + ((k + 1) & 1u) * plan.maxLocals, s_td[slotNext],
                             predInAll + (size_t)inst_of(w + stride) * inst.particles, gidNext, hidNext);
         cp_async_commit();      // P(k+1)
+        const unsigned cntNext = hasNext ? load_counts(s_td[slotNext]) : 0u;
         cp_async_wait_group<2>();  // P(k) and S(k) have landed; B(k), P(k+1) may still be in flight
         __syncthreads();
         if (hasNN && tid < TD_WORDS) s_tdw[slotNN * TD_WORDS + tid] = tdWord;
-        unsigned cntS = 0, cntB = 0;
-        if (owner) {
-            cntS = __ldg(plan.sCnt + td.ownedOff + tid);
-            cntB = __ldg(plan.bCnt + td.ownedOff + tid);
-        }
+        const unsigned cntS = cntCur & 0xffu, cntB = cntCur >> 8;
 
         // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
-        for (unsigned c = tid; c < td.nStretch; c += T) stretch_to_slots<LOG2T>(s_srec[c], sp, slots, plan.maxKS);
+        // two constraints per trip: their dependent chains (sqrt, reciprocals) interleave
+        for (unsigned c = tid; c < td.nStretch; c += 2 * T) {
+            const bool two = c + T < td.nStretch;
+            const uint2 r0 = s_srec[c], r1 = s_srec[two ? c + T : c];
+            bool ok0 = true, ok1 = true;
+            const StretchOut o0 = stretch_solve(r0, sp, ok0), o1 = stretch_solve(r1, sp, ok1);
+            if (ok0) stretch_store<LOG2T>(r0, o0, slots, plan.maxKS);
+            if (two && ok1) stretch_store<LOG2T>(r1, o1, slots, plan.maxKS);
+#if !VT_FAST_MATH
+            if (!ok0) stretch_slow_to_slots<LOG2T>(r0, sp, slots, plan.maxKS);
+            if (two && !ok1) stretch_slow_to_slots<LOG2T>(r1, sp, slots, plan.maxKS);
+#endif
+        }
         __syncthreads();
 
         if (hasNext) issue_stretch(s_td[slotNext]);
@@ -390,6 +472,7 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         gidCur = gidNext;
         gidNext = gidNN;
         hidNext = hidNN;
+        cntCur = cntNext;
     }
     cp_async_wait_all();
 }

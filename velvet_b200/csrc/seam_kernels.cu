@@ -406,6 +406,61 @@ __global__ void selftest_division_kernel(const float* __restrict__ x, const floa
     outVec[3 * (size_t)i + 2] = __float_as_uint(v.z);
     outPlain[i] = __float_as_uint(__fdiv_rn(a, d));
 }
+
+// ---- self-test of the checked-fast constraint evaluators (vt_math.cuh): whenever their validity predicate holds they must
+// return exactly what the branchy evaluators return; whenever it does not, the caller falls back to those, so a mismatch is
+// only counted while `ok` is true.  mismatches[0] stretch, [1] bend, [2] sqrt; fast[0..2] = how often the fast path was valid.
+__device__ __forceinline__ bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
+__device__ __forceinline__ bool same_vec(vec3 a, vec3 b) { return same_bits(a.x, b.x) && same_bits(a.y, b.y) && same_bits(a.z, b.z); }
+
+__global__ void selftest_constraints_kernel(const float* __restrict__ in, unsigned n, unsigned long long* __restrict__ mismatches,
+                                            unsigned long long* __restrict__ fast)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* f = in + 18 * (size_t)i;
+    const vec3 p0 = V3(f[0], f[1], f[2]), p1 = V3(f[3], f[4], f[5]), p2 = V3(f[6], f[7], f[8]), p3 = V3(f[9], f[10], f[11]);
+    const float w0 = f[12], w1 = f[13], w2 = f[14], w3 = f[15], rest = f[16], xpbd = f[17];
+    {
+        vec3 a1 = V3(0, 0, 0), a2 = a1, b1, b2;
+        const bool actA = stretch_eval(p0, p1, w0, w1, rest, a1, a2);
+        bool ok = true;
+        const bool actB = stretch_eval_u(p0, p1, w0, w1, rest, b1, b2, ok);
+        if (ok) {
+            atomicAdd(fast + 0, 1ull);
+            if (actA != actB || (actA && !(same_vec(a1, b1) && same_vec(a2, b2)))) atomicAdd(mismatches + 0, 1ull);
+        }
+    }
+    {
+        vec3 a0 = V3(0, 0, 0), a1 = a0, a2 = a0, a3 = a0, b0, b1, b2, b3;
+        const bool actA = bend_eval(p0, p1, p2, p3, w0, w1, w2, w3, rest, xpbd, a0, a1, a2, a3);
+        bool ok = true;
+        const bool actB = bend_eval_u(p0, p1, p2, p3, w0, w1, w2, w3, rest, xpbd, b0, b1, b2, b3, ok);
+        if (ok) {
+            atomicAdd(fast + 1, 1ull);
+            if (actA != actB || (actA && !(same_vec(a0, b0) && same_vec(a1, b1) && same_vec(a2, b2) && same_vec(a3, b3))))
+                atomicAdd(mismatches + 1, 1ull);
+        }
+    }
+}
+
+// every one of the 2^32 operands of sqrt
+__global__ void selftest_sqrt_kernel(unsigned long long* __restrict__ mismatches, unsigned long long* __restrict__ fast)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0, valid = 0;
+    for (unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u < (1ull << 32); u += stride) {
+        const float x = __uint_as_float((unsigned)u);
+        bool ok = true;
+        const float s = vt_sqrt_u(x, ok);
+        if (ok) {
+            valid++;
+            if (!same_bits(s, sqrtf(x))) bad++;
+        }
+    }
+    if (bad) atomicAdd(mismatches + 2, bad);
+    atomicAdd(fast + 2, valid);
+}
 } }  // namespace
 
 extern "C" {
@@ -565,6 +620,19 @@ int velvet_selftest_division(const float* x, const float* y, unsigned n, unsigne
     VT_API_BEGIN
     VT_REQUIRE(x && y && outDiv && outVec3 && outPlain && n > 0, "selftest_division: bad argument");
     velvet::selftest_division_kernel<<<(n + 255) / 256, 256>>>(x, y, n, outDiv, outVec3, outPlain);
+    VT_CUDA(cudaGetLastError());
+    VT_CUDA(cudaDeviceSynchronize());
+    VT_API_END
+}
+
+int velvet_selftest_constraints(const float* operands, unsigned n, unsigned long long* mismatches3, unsigned long long* fast3)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(operands && mismatches3 && fast3 && n > 0, "selftest_constraints: bad argument");
+    VT_CUDA(cudaMemset(mismatches3, 0, 3 * sizeof(unsigned long long)));
+    VT_CUDA(cudaMemset(fast3, 0, 3 * sizeof(unsigned long long)));
+    velvet::selftest_constraints_kernel<<<(n + 255) / 256, 256>>>(operands, n, mismatches3, fast3);
+    velvet::selftest_sqrt_kernel<<<148 * 8, 256>>>(mismatches3, fast3);
     VT_CUDA(cudaGetLastError());
     VT_CUDA(cudaDeviceSynchronize());
     VT_API_END
