@@ -325,6 +325,10 @@ VELVET_API int velvet_solver_dd_simulate(VelvetSolver* s, float deltaTime, int s
  * globals4 (may be NULL) = {maxLocals, maxKS, maxKB, maxBendPerTile}. */
 VELVET_API int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, unsigned* perTile4, unsigned capacityTiles,
                                       unsigned* globals4);
+/* Host-only: shared-memory wavefronts per Jacobi iteration of the constraint threads' 16-byte accesses (position loads and
+ * slot stores) for the tile plan of a grid cloth: out3 = {minimum, with records in constraint-id order, with the emitted
+ * bank-conflict-avoiding order}. */
+VELVET_API int velvet_plan_grid_smem_wavefronts(int resolution, int tileSize, unsigned long long* out3);
 /* Host-only: the exchange lists of `rank` for a grid cloth of `resolution` cut into `world` ranks with tiles of
  * `tileSize` particles (what dd_setup computes), for tests without a GPU.  ids arrays may be NULL to query counts only:
  * counts[q] / counts[world + q] = number of particle ids sent to / received from rank q. */

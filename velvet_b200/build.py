@@ -35,6 +35,7 @@ FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     *(["-fmad=true", "-prec-div=false", "-prec-sqrt=false"] if VARIANT.startswith("fast") else ["-fmad=false"]),
     *([f"-DVT_IT_REGCAP_BLOCKS={VARIANT[-1]}"] if VARIANT[-2:-1] == "b" else []),
+    *os.environ.get("VELVET_VARIANT_DEFS", "").split(),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-Wall,-Wno-unused-function",
     "-I", INCLUDE,

@@ -514,6 +514,27 @@ int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, uns
     VT_API_END
 }
 
+int velvet_plan_grid_smem_wavefronts(int resolution, int tileSize, unsigned long long* out3)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(resolution > 0 && out3, "plan_grid_smem_wavefronts: bad argument");
+    const int R = resolution;
+    const size_t n = (size_t)(R + 1) * (R + 1);
+    std::vector<float> v(3 * n);
+    std::vector<unsigned> idx((size_t)6 * R * R);
+    GenerateClothMesh(R, v.data(), idx.data());
+    const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const GridConstraints g = GenerateGridConstraints(R, v.data(), idx.data(), identity, {}, 1.5f, 0);
+    const TilePlan plan = build_tile_plan((unsigned)n, v.data(), g.stretchIdx.data(), g.stretchLen.data(), g.stretchLen.size(),
+                                          g.bendIdx.data(), g.bendAngle.data(), g.bendAngle.size(), nullptr, nullptr, nullptr, 0,
+                                          tileSize ? tileSize : 256);
+    if (!plan.valid) return set_error(VELVET_ERR_UNSUPPORTED, plan.whyInvalid);
+    out3[0] = plan.smemWavefrontsIdeal;
+    out3[1] = plan.smemWavefrontsIdOrder;
+    out3[2] = plan.smemWavefronts;
+    VT_API_END
+}
+
 int velvet_hash_create(VelvetSpatialHash** out, float particleDiameter, int maxNumObjects, float hashCellSizeScalar,
                        int maxNumNeighbors)
 {

@@ -197,18 +197,46 @@ struct StretchOut {
     vec3 c1, c2;
     float flag;
 };
-__device__ __forceinline__ StretchOut stretch_solve(const uint2 r, const float4* __restrict__ sp, bool& ok)
+// first half: positions, distance, active flag; second half (only for active constraints): the divisions
+struct StretchWork {
+    float4 pa, pb;
+#if !VT_FAST_MATH
+    StretchHalf h;
+#endif
+    bool active;
+};
+__device__ __forceinline__ StretchWork stretch_begin(const uint2 r, const float4* __restrict__ sp, bool& ok)
 {
     const unsigned ea = r.x & 0xffffu, eb = r.x >> 16;
-    const float4 pa = sp[ea >> TP_ORD_BITS], pb = sp[eb >> TP_ORD_BITS];
+    StretchWork w;
+    w.pa = sp[ea >> TP_ORD_BITS];
+    w.pb = sp[eb >> TP_ORD_BITS];
+#if VT_FAST_MATH
+    w.active = true;
+#else
+    w.h = stretch_begin_u(V3(w.pa), V3(w.pb), w.pa.w, w.pb.w, __uint_as_float(r.y), ok);
+    w.active = w.h.active;
+#endif
+    return w;
+}
+__device__ __forceinline__ StretchOut stretch_finish(const uint2 r, const StretchWork& w, bool& ok)
+{
     StretchOut o;
 #if VT_FAST_MATH
-    const bool active = stretch_eval_flagged(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), o.c1, o.c2);
-#else
-    const bool active = stretch_eval_u(V3(pa), V3(pb), pa.w, pb.w, __uint_as_float(r.y), o.c1, o.c2, ok);
-#endif
+    const bool active = stretch_eval_flagged(V3(w.pa), V3(w.pb), w.pa.w, w.pb.w, __uint_as_float(r.y), o.c1, o.c2);
     if (!active) o.c1 = o.c2 = V3(0, 0, 0);
     o.flag = active ? 1.0f : 0.0f;
+#else
+    stretch_finish_u(w.h, w.pa.w, w.pb.w, __uint_as_float(r.y), o.c1, o.c2, ok);
+    o.flag = 1.0f;
+#endif
+    return o;
+}
+__device__ __forceinline__ StretchOut stretch_inactive()
+{
+    StretchOut o;
+    o.c1 = o.c2 = V3(0, 0, 0);
+    o.flag = 0.0f;
     return o;
 }
 template <int LOG2T>
@@ -362,12 +390,9 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     // stretch | bend << 8 constraint counts of this thread's particle; fetched one tile ahead (the compiler sinks a plain
     // load to its first use after the stretch phase, where ncu showed it as the kernel's largest long-scoreboard stall)
     auto load_counts = [&](const TileDesc& d) -> unsigned {
-        unsigned cs = 0, cb = 0;
-        if (tid < d.nOwned) {
-            asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cs) : "l"(plan.sCnt + d.ownedOff + tid));
-            asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cb) : "l"(plan.bCnt + d.ownedOff + tid));
-        }
-        return cs | (cb << 8);
+        unsigned c = 0;
+        if (tid < d.nOwned) asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(c) : "l"(plan.cnt16 + d.ownedOff + tid));
+        return c;
     };
 
     // ---- pipeline prologue: descriptors of the first two items, everything of the first, ids of the second
@@ -412,18 +437,38 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         const unsigned cntS = cntCur & 0xffu, cntB = cntCur >> 8;
 
         // ---- SolveStretch_Kernel, VtClothSolverGPU.cu L76-101: one evaluation per constraint
-        // two constraints per trip: their dependent chains (sqrt, reciprocals) interleave
-        for (unsigned c = tid; c < td.nStretch; c += 2 * T) {
-            const bool two = c + T < td.nStretch;
-            const uint2 r0 = s_srec[c], r1 = s_srec[two ? c + T : c];
-            bool ok0 = true, ok1 = true;
-            const StretchOut o0 = stretch_solve(r0, sp, ok0), o1 = stretch_solve(r1, sp, ok1);
-            if (ok0) stretch_store<LOG2T>(r0, o0, slots, plan.maxKS);
-            if (two && ok1) stretch_store<LOG2T>(r1, o1, slots, plan.maxKS);
+        // two constraints per trip (their dependent chains -- sqrt, reciprocals -- interleave), then at most one single
+        {
+            unsigned c = tid;
+            for (; c + T < td.nStretch; c += 2 * T) {
+                const uint2 r0 = s_srec[c], r1 = s_srec[c + T];
+                bool ok0 = true, ok1 = true;
+                const StretchWork w0 = stretch_begin(r0, sp, ok0), w1 = stretch_begin(r1, sp, ok1);
+                StretchOut o0 = stretch_inactive(), o1 = o0;
+                if (w0.active || w1.active) {
+                    o0 = stretch_finish(r0, w0, ok0);
+                    o1 = stretch_finish(r1, w1, ok1);
+                    if (!w0.active) o0 = stretch_inactive();
+                    if (!w1.active) o1 = stretch_inactive();
+                }
+                if (ok0) stretch_store<LOG2T>(r0, o0, slots, plan.maxKS);
+                if (ok1) stretch_store<LOG2T>(r1, o1, slots, plan.maxKS);
 #if !VT_FAST_MATH
-            if (!ok0) stretch_slow_to_slots<LOG2T>(r0, sp, slots, plan.maxKS);
-            if (two && !ok1) stretch_slow_to_slots<LOG2T>(r1, sp, slots, plan.maxKS);
+                if (!ok0) stretch_slow_to_slots<LOG2T>(r0, sp, slots, plan.maxKS);
+                if (!ok1) stretch_slow_to_slots<LOG2T>(r1, sp, slots, plan.maxKS);
 #endif
+            }
+            if (c < td.nStretch) {
+                const uint2 r0 = s_srec[c];
+                bool ok0 = true;
+                const StretchWork w0 = stretch_begin(r0, sp, ok0);
+                StretchOut o0 = stretch_inactive();
+                if (w0.active) o0 = stretch_finish(r0, w0, ok0);
+                if (ok0) stretch_store<LOG2T>(r0, o0, slots, plan.maxKS);
+#if !VT_FAST_MATH
+                else stretch_slow_to_slots<LOG2T>(r0, sp, slots, plan.maxKS);
+#endif
+            }
         }
         __syncthreads();
 
@@ -664,7 +709,7 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
     if (hp.tableSize <= 0) return false;
     const unsigned n = L.numParticles;
     SortedParticle* sorted = reinterpret_cast<SortedParticle*>(sortedScratch);
-    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n);
+    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n, hp.cellSpacing);
     cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
         neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, ownedMask);
     return true;

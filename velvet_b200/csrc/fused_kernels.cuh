@@ -21,8 +21,7 @@ struct TilePlanDev {
     const TileDesc* tiles;
     const unsigned* ownedIds;
     const unsigned* haloIds;
-    const uint8_t* sCnt;
-    const uint8_t* bCnt;
+    const uint16_t* cnt16;  // stretch | bend << 8 constraint counts per owned particle
     const unsigned* attOff;
     const uint2* stretchRec;
     const uint4* bendRec;

@@ -134,25 +134,56 @@ __device__ __forceinline__ unsigned hash_key_fast(int hx, int hy, int hz, const 
     return fastmod_u32(mag, f);
 }
 
-// One 32-byte record per sorted slot: {predicted xyz, particle id} {registration-time xyz, unused}.  Both distance tests
-// of a candidate read the same 32-byte sector.
+// One 32-byte record per sorted slot: {predicted xyz, cell tag} {registration-time xyz, particle id}.  Both distance tests
+// of a candidate read the same 32-byte sector; the second half is only fetched for candidates that pass the first test.
+//
+// Cell tag: the candidate's integer cell coordinates, each biased by 256 and clamped to [0, 507], in three 10-bit fields.
+// A bucket of the reference's table mixes particles of unrelated cells (tableSize is a power of two: 207 936 occupied cells
+// fold into 138 605 buckets on a flat 1024^2 sheet), so ~60 % of the candidates a particle meets cannot be neighbours at
+// all.  tag + (514 - own coordinate) per field lands in [512, 519] exactly when the candidate's cell is within -2 .. +5
+// cells of the particle's on that axis: ONE add and ONE masked compare reject every candidate whose cell is three or more
+// cells away on some axis, i.e. at least 2 cell widths apart, which the reference's `distance^2 < cellSpacing^2` test rejects
+// as well.  The filter is a superset test (clamping only shrinks differences), the float tests still decide, so the lists
+// stay bit-identical; it only removes the float work and the second half of the predicate for the foreign candidates.
 struct __align__(32) SortedParticle {
-    float4 pos;   // w = particle id bits
-    float4 init;
+    float4 pos;   // w = cell tag bits
+    float4 init;  // w = particle id bits
 };
+constexpr unsigned CN_TAG_FIELD = 10, CN_TAG_BIAS = 256, CN_TAG_MAX = 507, CN_TAG_K = 514;
+constexpr unsigned CN_TAG_MASK = 0x3F8u | (0x3F8u << 10) | (0x3F8u << 20);
+constexpr unsigned CN_TAG_WANT = 0x200u | (0x200u << 10) | (0x200u << 20);
+
+__device__ __forceinline__ unsigned cn_tag_coord(int i)
+{
+    const int b = i + (int)CN_TAG_BIAS;
+    return (unsigned)(b < 0 ? 0 : (b > (int)CN_TAG_MAX ? (int)CN_TAG_MAX : b));
+}
+__device__ __forceinline__ unsigned cn_cell_tag(int ix, int iy, int iz)
+{
+    return cn_tag_coord(ix) | (cn_tag_coord(iy) << CN_TAG_FIELD) | (cn_tag_coord(iz) << (2 * CN_TAG_FIELD));
+}
+// what a particle adds to a candidate's tag
+__device__ __forceinline__ unsigned cn_cell_probe(int ix, int iy, int iz)
+{
+    return (CN_TAG_K - cn_tag_coord(ix)) | ((CN_TAG_K - cn_tag_coord(iy)) << CN_TAG_FIELD) |
+           ((CN_TAG_K - cn_tag_coord(iz)) << (2 * CN_TAG_FIELD));
+}
 
 static __global__ void __launch_bounds__(256) reorder_sorted_kernel(SortedParticle* __restrict__ sorted,
                                                                     const unsigned* __restrict__ particleIndex,
                                                                     const float4* __restrict__ pred,
-                                                                    const float4* __restrict__ init4, unsigned n)
+                                                                    const float4* __restrict__ init4, unsigned n,
+                                                                    float cellSpacing)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned id = particleIndex[i];
     float4 p = __ldg(pred + id);
-    p.w = __uint_as_float(id);
+    float4 o = __ldg(init4 + id);
+    p.w = __uint_as_float(cn_cell_tag(int_coord(p.x, cellSpacing), int_coord(p.y, cellSpacing), int_coord(p.z, cellSpacing)));
+    o.w = __uint_as_float(id);
     sorted[i].pos = p;
-    sorted[i].init = __ldg(init4 + id);
+    sorted[i].init = o;
 }
 
 constexpr int CN_THREADS = 256;
@@ -164,6 +195,8 @@ constexpr int CN_THREADS = 256;
 // Thread t handles the particle in sorted slot t (the reference's mapping, SpatialHashGPU.cu L87-88): the lanes of a
 // warp sit in the same few buckets and walk the same candidate runs (mostly convergent loops, broadcast loads); the
 // scattered 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
+// The walk is software-pipelined over buckets (the range of the next non-empty bucket is fetched while the candidates of
+// the current one are tested) and four candidates are in flight per trip.
 static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
     unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
     const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles,
@@ -171,18 +204,26 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
 {
     const unsigned t = blockIdx.x * CN_THREADS + threadIdx.x;
     if (t >= hp.numObjects) return;
-    const float4 me = __ldg(&sorted[t].pos);
-    const unsigned id = __float_as_uint(me.w);
+    const float4 me = __ldg(&sorted[t].pos), me0 = __ldg(&sorted[t].init);
+    const unsigned id = __float_as_uint(me0.w);
     if (ownedMask && !__ldg(ownedMask + id)) return;  // domain-decomposed mode: another rank builds this particle's list
     const unsigned tableBase = (id / instanceParticles) * (unsigned)hp.tableSize;  // this instance's rows of the table
     const vec3 position = V3(me);
-    const vec3 originalPos = V3(__ldg(&sorted[t].init));
+    const vec3 originalPos = V3(me0);
     const int ix = int_coord(position.x, hp.cellSpacing);
     const int iy = int_coord(position.y, hp.cellSpacing);
     const int iz = int_coord(position.z, hp.cellSpacing);
+    const unsigned probe = cn_cell_probe(ix, iy, iz);
     const int hx0 = (int)((unsigned)(ix - 1) * 92837111u), hx1 = (int)((unsigned)ix * 92837111u), hx2 = (int)((unsigned)(ix + 1) * 92837111u);
     const int hy0 = (int)((unsigned)(iy - 1) * 689287499u), hy1 = (int)((unsigned)iy * 689287499u), hy2 = (int)((unsigned)(iy + 1) * 689287499u);
     const int hz0 = (int)((unsigned)(iz - 1) * 283923481u), hz1 = (int)((unsigned)iz * 283923481u), hz2 = (int)((unsigned)(iz + 1) * 283923481u);
+    auto key_of = [&](int b) {
+        const int a = b / 9, m = (b / 3) % 3, c = b % 3;
+        const int hx = a == 0 ? hx0 : a == 1 ? hx1 : hx2;
+        const int hy = m == 0 ? hy0 : m == 1 ? hy1 : hy2;
+        const int hz = c == 0 ? hz0 : c == 1 ? hz1 : hz2;
+        return tableBase + hash_key_fast(hx, hy, hz, fm);
+    };
 
     // phase 1: which of the 27 buckets (x, y, z traversal order = bit order) are non-empty; 27 independent loads in flight
     unsigned mask = 0;
@@ -199,36 +240,41 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     const float cs2 = hp.cellSpacing2, pd2 = hp.particleDiameter2;
     unsigned* out = neighbors + id;
     unsigned k = 0;
-    while (mask) {
-        const int b = __ffs(mask) - 1;
+    unsigned cur = 0, end = 0;
+    if (mask) {
+        const unsigned key = key_of(__ffs(mask) - 1);
         mask &= mask - 1;
-        const int a = b / 9, m = (b / 3) % 3, c = b % 3;
-        const int hx = a == 0 ? hx0 : a == 1 ? hx1 : hx2;
-        const int hy = m == 0 ? hy0 : m == 1 ? hy1 : hy2;
-        const int hz = c == 0 ? hz0 : c == 1 ? hz1 : hz2;
-        const unsigned key = tableBase + hash_key_fast(hx, hy, hz, fm);
-        unsigned cur = __ldg(cellStart + key);
-        unsigned end = __ldg(cellEnd + key);
+        cur = __ldg(cellStart + key);
+        end = __ldg(cellEnd + key);
+    }
+    while (cur < end) {  // a listed bucket is never empty
         if (cur + K < end) end = cur + K;
-        // two candidates (4 x 16 bytes) in flight per trip; both distance tests are evaluated unconditionally: the
-        // second vector sits in the same 32-byte sector and a branch-free body keeps the warp converged
-        for (; cur < end; cur += 2) {
-            const bool two = cur + 1 < end;
-            const SortedParticle* c0 = sorted + cur;
-            const SortedParticle* c1 = sorted + (two ? cur + 1 : cur);
-            const float4 q0 = __ldg(&c0->pos), o0 = __ldg(&c0->init), q1 = __ldg(&c1->pos), o1 = __ldg(&c1->init);
-            const unsigned nb0 = __float_as_uint(q0.w), nb1 = __float_as_uint(q1.w);
-            const bool hit0 = nb0 != id && length2(position - V3(q0)) < cs2 && length2(originalPos - V3(o0)) > pd2;
-            const bool hit1 = two && nb1 != id && length2(position - V3(q1)) < cs2 && length2(originalPos - V3(o1)) > pd2;
-            if (hit0) {
-                out[(size_t)k * N] = nb0;
-                if (++k >= K) return;
-            }
-            if (hit1) {
-                out[(size_t)k * N] = nb1;
-                if (++k >= K) return;
+        unsigned nextCur = 0, nextEnd = 0;
+        if (mask) {  // range of the next bucket: in flight while this one is tested
+            const unsigned key = key_of(__ffs(mask) - 1);
+            mask &= mask - 1;
+            nextCur = __ldg(cellStart + key);
+            nextEnd = __ldg(cellEnd + key);
+        }
+        for (; cur < end; cur += 4) {
+            float4 q[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) q[j] = __ldg(&sorted[cur + j < end ? cur + j : cur].pos);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (cur + j >= end) break;
+                if (((__float_as_uint(q[j].w) + probe) & CN_TAG_MASK) != CN_TAG_WANT) continue;  // cell >= 3 cells away
+                if (!(length2(position - V3(q[j])) < cs2)) continue;
+                const float4 o = __ldg(&sorted[cur + j].init);  // same 32-byte sector as q[j]: an L1 hit
+                const unsigned nb = __float_as_uint(o.w);
+                if (nb != id && length2(originalPos - V3(o)) > pd2) {
+                    out[(size_t)k * N] = nb;
+                    if (++k >= K) return;
+                }
             }
         }
+        cur = nextCur;
+        end = nextEnd;
     }
     if (k < K) out[(size_t)k * N] = 0xffffffffu;
 }

@@ -489,8 +489,11 @@ void VtClothSolverGPU::ensureFusedResources()
     m_dTiles.upload(m_plan.tiles, st);
     m_dOwned.upload(m_plan.ownedIds, st);
     m_dHalo.upload(m_plan.haloIds, st);
-    m_dSCnt.upload(m_plan.sCnt, st);
-    m_dBCnt.upload(m_plan.bCnt, st);
+    {
+        std::vector<uint16_t> cnt16(m_plan.sCnt.size());  // stretch | bend << 8 per owned particle: one load in the kernel
+        for (size_t i = 0; i < cnt16.size(); i++) cnt16[i] = (uint16_t)(m_plan.sCnt[i] | (m_plan.bCnt[i] << 8));
+        m_dCnt16.upload(cnt16, st);
+    }
     m_dAttOff.upload(m_plan.attOff, st);
     m_dStretchRec.upload(reinterpret_cast<const uint2*>(m_plan.stretchRec.data()), m_plan.stretchRec.size(), st);
     m_dBendRec.upload(reinterpret_cast<const uint4*>(m_plan.bendRec.data()), m_plan.bendRec.size(), st);
@@ -498,8 +501,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.tiles = m_dTiles;
     m_planDev.ownedIds = m_dOwned;
     m_planDev.haloIds = m_dHalo;
-    m_planDev.sCnt = m_dSCnt;
-    m_planDev.bCnt = m_dBCnt;
+    m_planDev.cnt16 = m_dCnt16;
     m_planDev.attOff = m_dAttOff;
     m_planDev.stretchRec = m_dStretchRec;
     m_planDev.bendRec = m_dBendRec;

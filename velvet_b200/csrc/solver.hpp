@@ -222,7 +222,7 @@ private:
     TilePlanDev m_planDev{};
     DeviceBuffer<TileDesc> m_dTiles;
     DeviceBuffer<uint> m_dOwned, m_dHalo, m_dAttOff;
-    DeviceBuffer<uint8_t> m_dSCnt, m_dBCnt;
+    DeviceBuffer<uint16_t> m_dCnt16;
     DeviceBuffer<uint2> m_dStretchRec, m_dAttachRec;
     DeviceBuffer<uint4> m_dBendRec;
 };

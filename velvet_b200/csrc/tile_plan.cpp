@@ -27,6 +27,99 @@ inline unsigned float_bits(float f)
     return u;
 }
 
+// ---- bank-conflict-avoiding record order (see tile_plan.hpp).  A record has K 16-bit endpoints (local << 5 | ordinal,
+// ordinal == TP_NO_SLOT for halo endpoints).  Lane l of a warp handles record (base + l): records [8g, 8g+8) of a tile form
+// a quarter-warp.  Endpoint k of those 8 records is one 16-byte shared-memory access (position load sp[local]; slot store
+// slots[ordinal][local] for owned endpoints): its bank group is local mod 8.
+template <int K>
+struct EndpointsOf;
+template <>
+struct EndpointsOf<2> {
+    static void get(const Rec2& r, unsigned* e) { e[0] = r.x & 0xffffu; e[1] = r.x >> 16; }
+};
+template <>
+struct EndpointsOf<4> {
+    static void get(const Rec4& r, unsigned* e) { e[0] = r.x & 0xffffu; e[1] = r.x >> 16; e[2] = r.y & 0xffffu; e[3] = r.y >> 16; }
+};
+
+// wavefronts of the loads + stores of one quarter-warp (8 records or fewer)
+template <int K, class Rec>
+unsigned quarter_wavefronts(const Rec* recs, unsigned n)
+{
+    unsigned total = 0;
+    for (int k = 0; k < K; k++) {
+        unsigned loadLocals[8][8], loadCnt[8] = {0}, storeCnt[8] = {0};
+        for (unsigned i = 0; i < n; i++) {
+            unsigned e[K];
+            EndpointsOf<K>::get(recs[i], e);
+            const unsigned local = e[k] >> TP_ORD_BITS, cls = local & 7u;
+            bool seen = false;  // lanes reading the same address are served together
+            for (unsigned j = 0; j < loadCnt[cls]; j++) seen |= loadLocals[cls][j] == local;
+            if (!seen) loadLocals[cls][loadCnt[cls]++] = local;
+            if ((e[k] & 31u) != TP_NO_SLOT) storeCnt[cls]++;
+        }
+        unsigned l = 0, st = 0;
+        for (int c = 0; c < 8; c++) {
+            l = std::max(l, loadCnt[c]);
+            st = std::max(st, storeCnt[c]);
+        }
+        total += l + st;
+    }
+    return total;
+}
+
+template <int K, class Rec>
+size_t tile_wavefronts(const Rec* recs, unsigned n)
+{
+    size_t total = 0;
+    for (unsigned b = 0; b < n; b += 8) total += quarter_wavefronts<K>(recs + b, std::min(8u, n - b));
+    return total;
+}
+
+template <int K, class Rec>
+void reorder_for_banks(Rec* recs, unsigned n, std::vector<Rec>& scratch, std::vector<unsigned char>& taken)
+{
+    constexpr unsigned WINDOW = 128;
+    scratch.assign(recs, recs + n);
+    taken.assign(n, 0);
+    unsigned head = 0, out = 0;
+    while (out < n) {
+        // owner[k][cls]: 0 = free, else local + 1 of the endpoint holding the bank group; halo endpoints of the same local
+        // may share (one address, no store)
+        unsigned owner[K][8] = {};
+        bool ownedSlot[K][8] = {};
+        unsigned cnt = 0;
+        auto fits = [&](const Rec& r) {
+            unsigned e[K];
+            EndpointsOf<K>::get(r, e);
+            for (int k = 0; k < K; k++) {
+                const unsigned local = e[k] >> TP_ORD_BITS, cls = local & 7u;
+                const bool halo = (e[k] & 31u) == TP_NO_SLOT;
+                if (owner[k][cls] && !(halo && !ownedSlot[k][cls] && owner[k][cls] == local + 1)) return false;
+            }
+            return true;
+        };
+        auto take = [&](unsigned i) {
+            unsigned e[K];
+            EndpointsOf<K>::get(scratch[i], e);
+            for (int k = 0; k < K; k++) {
+                const unsigned local = e[k] >> TP_ORD_BITS, cls = local & 7u;
+                owner[k][cls] = local + 1;
+                ownedSlot[k][cls] = ownedSlot[k][cls] || (e[k] & 31u) != TP_NO_SLOT;
+            }
+            taken[i] = 1;
+            recs[out++] = scratch[i];
+            cnt++;
+        };
+        const unsigned want = std::min(8u, n - out);
+        for (unsigned i = head; i < n && i < head + WINDOW && cnt < want; i++)
+            if (!taken[i] && fits(scratch[i])) take(i);
+        for (unsigned i = head; i < n && cnt < want; i++)  // nothing conflict-free left in the window: fill in id order
+            if (!taken[i]) take(i);
+        while (head < n && taken[head]) head++;
+    }
+}
+
 }  // namespace
 
 TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchIndices, const float* stretchLengths,
@@ -154,6 +247,9 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
     plan.haloIds.clear();
     std::vector<unsigned> haloStamp(N, 0xffffffffu), haloLocal(N);
     std::vector<unsigned> cntS(T), cntB(T), cntA(T);
+    std::vector<Rec2> scratch2;
+    std::vector<Rec4> scratch4;
+    std::vector<unsigned char> takenScratch;
 
     for (unsigned t = 0; t < numTiles; t++) {
         TileDesc& td = plan.tiles[t];
@@ -203,6 +299,17 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
         }
         if (overflow) return fail("a particle has more than 30 stretch or bend constraints");
         if (T + td.nHalo > TP_MAX_LOCALS) return fail("tile halo too large (more than 2047 local particles)");
+
+        // record order inside the tile: free of shared-memory bank conflicts where possible (ordinals are already fixed)
+        {
+            Rec2* sr = plan.stretchRec.data() + td.stretchOff;
+            Rec4* br = plan.bendRec.data() + td.bendOff;
+            plan.smemWavefrontsIdeal += (size_t)((td.nStretch + 7) / 8) * 4 + (size_t)((td.nBend + 7) / 8) * 8;
+            plan.smemWavefrontsIdOrder += tile_wavefronts<2>(sr, td.nStretch) + tile_wavefronts<4>(br, td.nBend);
+            reorder_for_banks<2>(sr, td.nStretch, scratch2, takenScratch);
+            reorder_for_banks<4>(br, td.nBend, scratch4, takenScratch);
+            plan.smemWavefronts += tile_wavefronts<2>(sr, td.nStretch) + tile_wavefronts<4>(br, td.nBend);
+        }
 
         // per-particle constraint counts (the slot of ordinal k of particle l is slots[k * T + l])
         for (unsigned l = 0; l < td.nOwned; l++) {

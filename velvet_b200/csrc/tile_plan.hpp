@@ -12,6 +12,12 @@
 // only owned endpoints receive a slot.  Particles referenced but not owned form the tile's halo.
 // Slot of (particle local index l, ordinal k) is slots[k * tileSize + l]: consecutive particles read consecutive
 // 16-byte words, so the per-particle sums are free of shared-memory bank conflicts.
+//
+// The ORDER of a tile's records is free (a slot is addressed by ordinal, not by record position), and it decides the bank
+// conflicts of the constraint threads: a warp-wide 16-byte access is served in quarter-warps of 8 lanes, conflict-free when
+// the 8 local indices differ mod 8.  In constraint-id order the 4 stretch constraints generated per grid vertex sit in
+// adjacent lanes and share an endpoint: their slot stores collide 4-way (ncu, round 1: 2.7x the ideal store wavefronts, the
+// LSU pipe 57 % busy).  build_tile_plan therefore emits the records of a tile in a greedily conflict-avoiding order.
 #pragma once
 
 #include <cstdint>
@@ -60,6 +66,9 @@ struct TilePlan {
     unsigned maxKS = 0, maxKB = 0;       // max stretch / bend constraints on one particle; slot rows are [k][local], plus a dump row
     // statistics
     size_t numStretchEvaluated = 0, numBendEvaluated = 0, numHalo = 0;
+    // shared-memory wavefronts of the constraint threads' 16-byte accesses (position loads + slot stores) per Jacobi
+    // iteration: the minimum (4 per warp-wide access), with records in constraint-id order, and in the emitted order
+    size_t smemWavefrontsIdeal = 0, smemWavefrontsIdOrder = 0, smemWavefronts = 0;
 };
 
 // positions: packed float3 (host) used only to order particles spatially.
