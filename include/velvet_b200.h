@@ -250,6 +250,13 @@ VELVET_API int velvet_solver_upload(VelvetSolver* s, int bufferId, const void* h
 /* Asynchronous read-back of positions+normals on the solver stream into pinned host memory (headless
  * replacement of positions.sync()/normals.sync(), hpp L109-110). */
 VELVET_API int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals);
+/* Double-buffered variant: the results are snapshot on the solver stream into one of two device staging buffers and copied
+ * to pinned host memory on a separate copy stream, so the transfer of frame k overlaps the simulation of frame k+1 (the
+ * next velvet_solver_simulate may be issued at once).  *ticket (0 or 1) identifies the transfer for
+ * velvet_solver_readback_wait, which blocks the host until that transfer has landed.  At most two may be outstanding:
+ * wait for ticket t before the host buffers passed with it are reused. */
+VELVET_API int velvet_solver_readback_pipelined(VelvetSolver* s, float* hostPositions, float* hostNormals, int* ticket);
+VELVET_API int velvet_solver_readback_wait(VelvetSolver* s, int ticket);
 /* The cudaStream_t the solver launches on. */
 VELVET_API void* velvet_solver_stream(VelvetSolver* s);
 /* Number of kernel launches (graph kernel nodes included) issued by the last Simulate call. */

@@ -461,3 +461,32 @@ def test_product_against_reference_kernel_golden_vectors(math_mode):
         valid = gold["cellStart"] != 0xFFFFFFFF
         assert np.array_equal(g.download("cellEnd")[valid], gold["cellEnd"][valid])
         assert np.array_equal(valid_prefix_table(g.download("neighbors"), n, 64), gold["neighbors"])
+
+
+def test_pipelined_readback_delivers_every_frame():
+    """velvet_solver_readback_pipelined: frame k's positions/normals land in the host buffers given for frame k while
+    frame k+1 is already being simulated; each must equal what a blocking download of that frame returns."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    p = gpu_params(numSubsteps=3, numIterations=4)
+    g, _ = make_pair(63, p, oracle=False)
+    ref, _ = make_pair(63, p, oracle=False)
+    for s in (g, ref):
+        s.UpdateColliders(vb.sphere_plane_colliders())
+    n = 64 * 64 * 3
+    hp = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    hn = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    want = []
+    for _ in range(5):
+        ref.Simulate()
+        want.append((ref.download("positions").reshape(-1).copy(), ref.download("normals").reshape(-1).copy()))
+    prev = None
+    for k in range(5):
+        g.Simulate(sync=False)
+        t = g.ReadbackPipelined(C.c_void_p(hp[k & 1].data_ptr()), C.c_void_p(hn[k & 1].data_ptr()))
+        if prev is not None:
+            g.ReadbackWait(prev[0])
+            assert np.array_equal(hp[prev[1]].numpy(), want[k - 1][0]) and np.array_equal(hn[prev[1]].numpy(), want[k - 1][1]), k - 1
+        prev = (t, k & 1)
+    g.ReadbackWait(prev[0])
+    assert np.array_equal(hp[prev[1]].numpy(), want[4][0]) and np.array_equal(hn[prev[1]].numpy(), want[4][1])

@@ -284,6 +284,22 @@ int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* h
     VT_API_END
 }
 
+int velvet_solver_readback_pipelined(VelvetSolver* s, float* hostPositions, float* hostNormals, int* ticket)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && ticket, "readback_pipelined: bad argument");
+    *ticket = s->impl.ReadbackPipelined(hostPositions, hostNormals);
+    VT_API_END
+}
+
+int velvet_solver_readback_wait(VelvetSolver* s, int ticket)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.ReadbackWait(ticket);
+    VT_API_END
+}
+
 void* velvet_solver_stream(VelvetSolver* s) { return s ? (void*)s->impl.stream() : nullptr; }
 int velvet_solver_last_launch_count(VelvetSolver* s) { return s ? s->impl.lastLaunchCount() : 0; }
 

@@ -342,13 +342,17 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 #ifndef VT_IT_REGCAP_BLOCKS
 #define VT_IT_REGCAP_BLOCKS 4  // resident 256-thread CTAs per SM the register budget is sized for
 #endif
-template <int LOG2T>
-__global__ void __launch_bounds__(1 << LOG2T, (VT_IT_REGCAP_BLOCKS * 256) >> LOG2T)
+// LOG2T: width of a slot row (= tile capacity in particles); NT: threads per CTA.  NT > 2^LOG2T gives the tile extra
+// constraint threads: a 16x16-particle tile of a grid cloth is touched by 17x17 = 289 bending constraints, so with 256
+// threads 33 of them (two warps) did a second, latency-long bend while six warps idled at the barrier (ncu: 12 % of all
+// stall samples); with 320 threads every bend phase is a single trip.
+template <int LOG2T, int NT>
+__global__ void __launch_bounds__(NT, (VT_IT_REGCAP_BLOCKS * 256) / NT)
 iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const TilePlanDev plan,
                     const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
                     const unsigned totalWork)
 {
-    constexpr unsigned T = 1u << LOG2T;
+    constexpr unsigned T = NT;  // stride of every cooperative loop
     constexpr unsigned TD_WORDS = sizeof(TileDesc) / 4;
     extern __shared__ float4 s_mem[];
     float4* const spBase = s_mem;  // two buffers of maxLocals
@@ -629,6 +633,9 @@ size_t iterate_smem_bytes(const TilePlanDev& plan)
            3 * sizeof(TileDesc);
 }
 
+// kernel variants: (slot-row width, threads)
+#define VT_ITERATE_VARIANTS(X) X(7, 128) X(7, 160) X(8, 256) X(8, 320) X(9, 512) X(9, 640)
+
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst)
 {
@@ -636,29 +643,29 @@ void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut,
     if (!total) return;
     const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
     const size_t smem = iterate_smem_bytes(plan);
-    switch (plan.threads) {
-    case 128: iterate_tile_kernel<7><<<grid, 128, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); break;
-    case 256: iterate_tile_kernel<8><<<grid, 256, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); break;
-    case 512: iterate_tile_kernel<9><<<grid, 512, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); break;
-    default: throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
+#define VT_LAUNCH(LOG2T, NT)                                                                                               \
+    if (plan.threads == (1u << LOG2T) && plan.ctaThreads == NT) {                                                          \
+        iterate_tile_kernel<LOG2T, NT><<<grid, NT, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); \
+        return;                                                                                                            \
     }
+    VT_ITERATE_VARIANTS(VT_LAUNCH)
+#undef VT_LAUNCH
+    throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
 }
 
-// Opts in to > 48 KB dynamic shared memory and returns how many CTAs of `threads` threads the current device keeps resident.
-unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads)
+// Opts in to > 48 KB dynamic shared memory and returns how many CTAs of this plan the current device keeps resident.
+unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads)
 {
-    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     int dev = 0, sms = 0, perSm = 0;
     VT_CUDA(cudaGetDevice(&dev));
     VT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    switch (threads) {
-    case 128: VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<7>, 128, smemBytes)); break;
-    case 256: VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<8>, 256, smemBytes)); break;
-    case 512: VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<9>, 512, smemBytes)); break;
-    default: throw Error(VELVET_ERR_INVALID_ARGUMENT, "unsupported Jacobi tile size");
+#define VT_CONFIG(LOG2T, NT)                                                                                               \
+    if (threads == (1u << LOG2T) && ctaThreads == NT) {                                                                    \
+        VT_CUDA(cudaFuncSetAttribute(iterate_tile_kernel<LOG2T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes)); \
+        VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_tile_kernel<LOG2T, NT>, NT, smemBytes));     \
     }
+    VT_ITERATE_VARIANTS(VT_CONFIG)
+#undef VT_CONFIG
     if (perSm < 1) throw Error(VELVET_ERR_UNSUPPORTED, "the Jacobi tile kernel does not fit on an SM");
     return (unsigned)(sms * perSm);
 }

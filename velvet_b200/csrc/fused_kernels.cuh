@@ -28,7 +28,8 @@ struct TilePlanDev {
     const uint2* attachRec;
     unsigned numTiles, maxLocals, maxKS, maxKB, tileSize, maxBendPerTile, maxStretchPerTile;
     unsigned residentCtas;  // grid of the persistent iterate kernel: CTAs the device keeps resident at once
-    unsigned threads;  // CTA size: the power of two >= tileSize (slot rows are `threads` wide)
+    unsigned threads;     // slot-row width: the power of two >= tileSize
+    unsigned ctaThreads;  // CTA size: `threads`, or 1.25x that when a tile has more bending constraints than particles
     unsigned hasAttach;
 };
 
@@ -78,7 +79,7 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
-unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads);  // opt in to > 48 KB smem; returns resident CTAs on the device
+unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
 // Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
 // of positions / velocities / predicted to the public packed-float3 buffers).
@@ -134,7 +135,7 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
-unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads);  // opt in to > 48 KB smem; returns resident CTAs on the device
+unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
 // Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
 // of positions / velocities / predicted to the public packed-float3 buffers).

@@ -156,7 +156,53 @@ VtClothSolverGPU::~VtClothSolverGPU()
     try { ddPeerClose(); } catch (...) {}
     if (m_graphExec) cudaGraphExecDestroy(m_graphExec);
     if (m_graph) cudaGraphDestroy(m_graph);
+    if (m_copyStream) {
+        cudaStreamSynchronize(m_copyStream);
+        cudaStreamDestroy(m_copyStream);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (m_staged[i]) cudaEventDestroy(m_staged[i]);
+        if (m_copyDone[i]) cudaEventDestroy(m_copyDone[i]);
+    }
     if (m_stream) cudaStreamDestroy(m_stream);
+}
+
+int VtClothSolverGPU::ReadbackPipelined(float* hostPositions, float* hostNormals)
+{
+    if (!m_copyStream) {
+        VT_CUDA(cudaStreamCreateWithFlags(&m_copyStream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            VT_CUDA(cudaEventCreateWithFlags(&m_staged[i], cudaEventDisableTiming));
+            VT_CUDA(cudaEventCreateWithFlags(&m_copyDone[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = (int)(m_readbackSeq++ & 1u);
+    const size_t floats = positions.size() * 3;
+    // the staging buffer of this slot may still be feeding the copy issued two calls ago
+    if (m_copyPending[slot]) VT_CUDA(cudaStreamWaitEvent(m_stream, m_copyDone[slot], 0));
+    if (hostPositions && floats) {
+        m_stagePos[slot].allocate(floats);
+        VT_CUDA(cudaMemcpyAsync(m_stagePos[slot].data(), positions.data(), floats * 4, cudaMemcpyDeviceToDevice, m_stream));
+    }
+    if (hostNormals && floats) {
+        m_stageNrm[slot].allocate(floats);
+        VT_CUDA(cudaMemcpyAsync(m_stageNrm[slot].data(), normals.data(), floats * 4, cudaMemcpyDeviceToDevice, m_stream));
+    }
+    VT_CUDA(cudaEventRecord(m_staged[slot], m_stream));
+    VT_CUDA(cudaStreamWaitEvent(m_copyStream, m_staged[slot], 0));
+    if (hostPositions && floats)
+        VT_CUDA(cudaMemcpyAsync(hostPositions, m_stagePos[slot].data(), floats * 4, cudaMemcpyDeviceToHost, m_copyStream));
+    if (hostNormals && floats)
+        VT_CUDA(cudaMemcpyAsync(hostNormals, m_stageNrm[slot].data(), floats * 4, cudaMemcpyDeviceToHost, m_copyStream));
+    VT_CUDA(cudaEventRecord(m_copyDone[slot], m_copyStream));
+    m_copyPending[slot] = true;
+    return slot;
+}
+
+void VtClothSolverGPU::ReadbackWait(int ticket)
+{
+    if (ticket < 0 || ticket > 1) throw Error(VELVET_ERR_INVALID_ARGUMENT, "ReadbackWait: unknown ticket");
+    if (m_copyPending[ticket]) VT_CUDA(cudaEventSynchronize(m_copyDone[ticket]));
 }
 
 void VtClothSolverGPU::Synchronize() { VT_CUDA(cudaStreamSynchronize(m_stream)); }
@@ -515,13 +561,20 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.tileSize = (uint)m_plan.tileSize;
     m_planDev.threads = m_plan.tileSize <= 128 ? 128u : (m_plan.tileSize <= 256 ? 256u : 512u);
     m_planDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
+    // Experiment knob (VELVET_ITERATE_WIDE=1): a quarter more threads per CTA, so that a tile touched by more bending
+    // constraints than it has particles (289 vs 256 on a grid) needs one bend trip per warp.  Measured on B200 at 1M
+    // particles: 75.9 us per iteration against 70.0 us with T threads -- three resident CTAs per SM instead of four cost
+    // more than the shorter bend phase saves -- so it stays off.
+    m_planDev.ctaThreads = m_planDev.threads;
+    if (const char* e = getenv("VELVET_ITERATE_WIDE"))
+        if (atoi(e) != 0) m_planDev.ctaThreads += m_planDev.threads / 4;
     const size_t smem = exact_math::iterate_smem_bytes(m_planDev);
     if (smem > 200 * 1024) {
         m_fallbackReason = "tile needs more than 200 KB of shared memory";
         return;
     }
-    m_planDev.residentCtas = std::min(exact_math::configure_iterate_kernel(smem, m_planDev.threads),
-                                      fast_math::configure_iterate_kernel(smem, m_planDev.threads));
+    m_planDev.residentCtas = std::min(exact_math::configure_iterate_kernel(smem, m_planDev.threads, m_planDev.ctaThreads),
+                                      fast_math::configure_iterate_kernel(smem, m_planDev.threads, m_planDev.ctaThreads));
 
     // vertex -> incident triangles, ascending triangle id
     {

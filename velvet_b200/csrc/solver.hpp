@@ -82,6 +82,13 @@ public:
     void Synchronize();
     void OnDestroy();  // L50-54
 
+    // Double-buffered read-back of positions + normals (headless replacement of VtMergedBuffer::sync, VtBuffer.hpp
+    // L180-236): the frame's results are snapshot into one of two device staging buffers on the solver stream (a few
+    // microseconds) and travel to pinned host memory on a separate copy stream, so the PCIe transfer of frame k overlaps
+    // the simulation of frame k+1.  Returns a ticket for ReadbackWait; at most two read-backs may be outstanding.
+    int ReadbackPipelined(float* hostPositions, float* hostNormals);
+    void ReadbackWait(int ticket);
+
     // Batched independent cloths (north_star mode 1 / BASELINE config 4): `numInstances` copies of one grid cloth of
     // `resolution`, instance i placed by modelMatrices16[i].  Instances never interact: each has its own rows of the
     // hash table, its own neighbour lists and attach-slot positions; they share ONE constraint set / tile plan, built
@@ -173,6 +180,11 @@ private:
 
     int m_device = 0;
     cudaStream_t m_stream = nullptr;
+    cudaStream_t m_copyStream = nullptr;
+    cudaEvent_t m_staged[2] = {nullptr, nullptr}, m_copyDone[2] = {nullptr, nullptr};
+    bool m_copyPending[2] = {false, false};
+    unsigned m_readbackSeq = 0;
+    DeviceBuffer<float> m_stagePos[2], m_stageNrm[2];
     int m_pipeline = 0;
     int m_tileSize = 0;
     int m_mathMode = VELVET_MATH_EXACT;

@@ -174,6 +174,15 @@ class VtClothSolverGPU:
     def ReadbackAsync(self, host_positions_ptr, host_normals_ptr):
         check(self._L.velvet_solver_readback_async(self._h, host_positions_ptr, host_normals_ptr))
 
+    def ReadbackPipelined(self, host_positions_ptr, host_normals_ptr) -> int:
+        """Double-buffered read-back on a separate copy stream (overlaps the next Simulate); returns a ticket."""
+        t = C.c_int(-1)
+        check(self._L.velvet_solver_readback_pipelined(self._h, host_positions_ptr, host_normals_ptr, C.byref(t)))
+        return t.value
+
+    def ReadbackWait(self, ticket: int):
+        check(self._L.velvet_solver_readback_wait(self._h, ticket))
+
     @property
     def stream(self) -> int:
         return self._L.velvet_solver_stream(self._h) or 0
