@@ -19,6 +19,8 @@
 //   * colliders are prepared once per frame (lastTransform * invCurTransform hoisted) and staged per CTA.
 #include "fused_kernels.cuh"
 
+#include <algorithm>
+
 #include "hash_kernels.cuh"
 #include "vt_buffer.hpp"
 
@@ -720,6 +722,20 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
     cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
         neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, ownedMask);
     return true;
+}
+
+// plain device-side copy (read-back staging): a kernel rather than cudaMemcpyAsync because the source is managed memory,
+// for which the driver's copy path is not stream-fast
+static __global__ void __launch_bounds__(256) copy_words_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t words)
+{
+    if (!words) return;
+    const unsigned grid = (unsigned)std::min<size_t>((words + 255) / 256, 148 * 16);
+    copy_words_kernel<<<grid, 256, 0, stream>>>(static_cast<const unsigned*>(src), static_cast<unsigned*>(dst), words);
 }
 
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n)

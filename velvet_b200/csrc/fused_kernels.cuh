@@ -106,6 +106,7 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
                                    const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp,
                                    Instancing inst,  // hp.tableSize = rows per instance
                                    const unsigned char* ownedMask = nullptr);  // decomposed mode: lists of owned particles only
+void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t words);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
 // halo exchange plumbing of the domain-decomposed mode: out[i] = src[ids[i]]  /  dst[ids[i]] = in[i]
 void launch_gather_by_id(const FusedLaunch& L, const float4* src, const unsigned* ids, unsigned n, float4* out);

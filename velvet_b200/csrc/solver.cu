@@ -182,11 +182,11 @@ int VtClothSolverGPU::ReadbackPipelined(float* hostPositions, float* hostNormals
     if (m_copyPending[slot]) VT_CUDA(cudaStreamWaitEvent(m_stream, m_copyDone[slot], 0));
     if (hostPositions && floats) {
         m_stagePos[slot].allocate(floats);
-        VT_CUDA(cudaMemcpyAsync(m_stagePos[slot].data(), positions.data(), floats * 4, cudaMemcpyDeviceToDevice, m_stream));
+        exact_math::launch_copy_words(m_stream, positions.data(), m_stagePos[slot].data(), floats);
     }
     if (hostNormals && floats) {
         m_stageNrm[slot].allocate(floats);
-        VT_CUDA(cudaMemcpyAsync(m_stageNrm[slot].data(), normals.data(), floats * 4, cudaMemcpyDeviceToDevice, m_stream));
+        exact_math::launch_copy_words(m_stream, normals.data(), m_stageNrm[slot].data(), floats);
     }
     VT_CUDA(cudaEventRecord(m_staged[slot], m_stream));
     VT_CUDA(cudaStreamWaitEvent(m_copyStream, m_staged[slot], 0));
