@@ -16,4 +16,6 @@ ncu --set full --import-source on --clock-control none -k regex:iterate_tile -s 
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_iter.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:cache_neighbors_sorted -s 4 -c 1 -f -o gpurun_out/cache_r01d \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_cache.log 2>&1
+( compute-sanitizer --tool memcheck python tests/sanitize_gpu.py; compute-sanitizer --tool racecheck python tests/sanitize_gpu.py ) 2>&1 | grep -E "^ok|SUMMARY|ERROR|hazard" > gpurun_out/sanitizer_r01d.txt
+python bench.py --math fast --no-cpu-baseline > gpurun_out/bench_fast.json 2> gpurun_out/bench_fast.err
 ls -la gpurun_out
