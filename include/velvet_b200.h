@@ -242,6 +242,11 @@ VELVET_API int velvet_solver_synchronize(VelvetSolver* s);
 /* SpatialHashGPU::Hash(predicted) on the solver's own hash (hpp L83). */
 VELVET_API int velvet_solver_hash(VelvetSolver* s);
 
+/* The same rebuild through the fused pipeline's own hash kernels (float4 state, own radix sort, reordered tag-filtered
+ * neighbour cache) -- what velvet_solver_simulate runs internally -- on the public `predicted` buffer; results in the same
+ * public hash buffers, bit-identical to velvet_solver_hash.  Synchronous. */
+VELVET_API int velvet_solver_hash_fused(VelvetSolver* s);
+
 /* Device pointer + element count (elements of the type listed at VelvetBufferId) of a public buffer. */
 VELVET_API int velvet_solver_buffer(VelvetSolver* s, int bufferId, void** devPtr, size_t* count);
 /* Copy a public buffer to / from host memory (count elements of the buffer's type, synchronous). */

@@ -127,3 +127,74 @@ def test_spatial_hash_object_matches_oracle():
     assert np.array_equal(h.download("particleHash"), ph)
     assert np.array_equal(h.download("particleIndex"), pi)
     assert np.array_equal(valid_prefix_table(h.download("neighbors"), n, 64), valid_prefix_table(nb, n, 64))
+
+
+# ---------------------------------------------------------------- the fused pipeline's own hash kernels on arbitrary inputs
+def _hash_fused_vs_oracle(pos, init, R, k=64):
+    """Drives hash_particles / onesweep sort / find_cell_start / reorder + tag-filtered neighbour cache (the kernels
+    Simulate() runs) through velvet_solver_hash_fused on a solver of (R+1)^2 particles and compares every buffer with O1."""
+    n = (R + 1) ** 2
+    assert len(pos) == n
+    p = vb.default_params()
+    p.maxNumNeighbors = k
+    g = vb.build_scene(R, p)
+    D = np.float32(g.simParams.particleDiameter)
+    g.HashFused()  # builds the fused resources (tile plan from the regular grid) before the buffers are overwritten
+    g.upload("initialPositions", init.reshape(-1))
+    g.upload("predicted", pos.reshape(-1))
+    g.HashFused()
+    cell = np.float32(D * np.float32(p.hashCellSizeScalar))
+    args = (n, k, cell, np.float32(cell * cell), 2 * n, np.float32(D * D))
+    ph, pi, cs, ce, nb = (np.zeros(m, np.uint32) for m in (n, n, 2 * n, 2 * n, k * n))
+    o1.lib().o1_hash_objects(f(ph), f(pi), f(cs), f(ce), f(nb), f(pos), f(init), o1.HashParams(*args))
+    assert np.array_equal(g.download("particleHash"), ph), "sorted cell keys"
+    assert np.array_equal(g.download("particleIndex"), pi), "sorted particle order"
+    assert np.array_equal(g.download("cellStart"), cs), "cellStart"
+    valid = cs != 0xFFFFFFFF
+    assert np.array_equal(g.download("cellEnd")[valid], ce[valid]), "cellEnd"
+    tab = valid_prefix_table(nb, n, k)
+    assert np.array_equal(valid_prefix_table(g.download("neighbors"), n, k), tab), "neighbor lists"
+    return tab, float(D)
+
+
+def test_fused_hash_on_a_crumpled_cloud_and_far_from_the_origin():
+    """The neighbour cache of the fused pipeline rejects candidates by a clamped 10-bit cell tag before the float tests.
+    Inputs that stress it: negative coordinates, a cloud hundreds of cells wide (tag coordinates clamp at +-256 cells),
+    clusters thousands of cells from the origin (every tag clamped: the filter must degrade to 'pass', never to 'reject')."""
+    R = 99
+    n = (R + 1) ** 2
+    rng = np.random.default_rng(21)
+    h = 2.0 / R
+    D = 1.5 * h
+    cell = 1.5 * D
+    # (a) crumpled: particles scattered in a box ~14 cells wide around the origin, registration positions unrelated
+    init = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    pos = rng.uniform(-7 * cell, 7 * cell, (n, 3)).astype(np.float32)
+    tab, _ = _hash_fused_vs_oracle(pos, init, R)
+    assert (tab != 0xFFFFFFFF).sum() > n
+    # (b) a sheet of blobs spanning ~1400 cells in x: tags clamp on both sides
+    centers = np.stack([np.linspace(-700 * cell, 700 * cell, 50), np.zeros(50), np.zeros(50)], 1)
+    pos = (centers[rng.integers(0, 50, n)] + rng.normal(0, 1.2 * cell, (n, 3))).astype(np.float32)
+    tab, _ = _hash_fused_vs_oracle(pos, init, R)
+    assert (tab != 0xFFFFFFFF).sum() > n
+    # (c) everything far outside the tag range, in all octants
+    centers = rng.choice([-1.0, 1.0], (40, 3)) * rng.uniform(3000 * cell, 9000 * cell, (40, 3))
+    pos = (centers[rng.integers(0, 40, n)] + rng.normal(0, 1.5 * cell, (n, 3))).astype(np.float32)
+    tab, _ = _hash_fused_vs_oracle(pos, init, R)
+    assert (tab != 0xFFFFFFFF).sum() > n
+
+
+def test_fused_hash_dense_cluster_and_small_caps():
+    """> 64 particles per bucket and > 64 accepted neighbours (bucket scan and list caps, SpatialHashGPU.cu L108 / L120),
+    and a small maxNumNeighbors."""
+    R = 49
+    n = (R + 1) ** 2
+    rng = np.random.default_rng(22)
+    h = 2.0 / R
+    cell = 2.25 * h
+    init = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+    pos = rng.uniform(0, 1.5 * cell, (n, 3)).astype(np.float32)
+    tab, _ = _hash_fused_vs_oracle(pos, init, R)
+    assert ((tab != 0xFFFFFFFF).sum(0) == 64).any()
+    tab, _ = _hash_fused_vs_oracle(pos, init, R, k=7)
+    assert ((tab != 0xFFFFFFFF).sum(0) == 7).any()

@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "velvet_solver_set_math_mode", "velvet_solver_set_tile_size", "velvet_solver_add_cloth", "velvet_solver_add_stretch",
     "velvet_solver_add_attach_slot", "velvet_solver_add_attach", "velvet_solver_add_bend",
     "velvet_solver_update_colliders", "velvet_make_collider", "velvet_solver_simulate", "velvet_solver_simulate_dt",
-    "velvet_solver_synchronize", "velvet_solver_hash", "velvet_solver_buffer", "velvet_solver_download",
+    "velvet_solver_synchronize", "velvet_solver_hash", "velvet_solver_hash_fused", "velvet_solver_buffer", "velvet_solver_download",
     "velvet_solver_upload", "velvet_solver_readback_async", "velvet_solver_readback_pipelined", "velvet_solver_readback_wait", "velvet_solver_stream",
     "velvet_solver_last_launch_count", "velvet_solver_simulate_timed", "velvet_generate_cloth_mesh",
     "velvet_transform_matrix", "velvet_cloth_object_start", "velvet_solver_add_cloth_instances", "velvet_solver_dd_setup", "velvet_solver_dd_info",
@@ -133,6 +133,7 @@ def load():
         "velvet_solver_simulate_dt": [v, f, i],
         "velvet_solver_synchronize": [v],
         "velvet_solver_hash": [v],
+        "velvet_solver_hash_fused": [v],
         "velvet_solver_buffer": [v, i, C.POINTER(v), C.POINTER(C.c_size_t)],
         "velvet_solver_download": [v, i, v, C.c_size_t],
         "velvet_solver_upload": [v, i, v, C.c_size_t],

@@ -237,6 +237,15 @@ int velvet_solver_hash(VelvetSolver* s)
     VT_API_END
 }
 
+int velvet_solver_hash_fused(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    VT_REQUIRE(s->impl.spatialHash(), "no cloth registered");
+    s->impl.HashFused();
+    VT_API_END
+}
+
 int velvet_solver_buffer(VelvetSolver* s, int bufferId, void** devPtr, size_t* count)
 {
     VT_API_BEGIN

@@ -167,6 +167,35 @@ VtClothSolverGPU::~VtClothSolverGPU()
     if (m_stream) cudaStreamDestroy(m_stream);
 }
 
+void VtClothSolverGPU::HashFused()
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    const uint N = simParams.numParticles;
+    if (!N) return;
+    ensureFusedResources();
+    if (!m_fusedUsable) throw Error(VELVET_ERR_UNSUPPORTED, "HashFused: the fused pipeline is not usable (" + m_fallbackReason + ")");
+    SpatialHashGPU& H = *m_spatialHash;
+    FusedLaunch L{m_stream, N};
+    exact_math::launch_pack_float4(L, reinterpret_cast<const float*>(H.initialPositions.data()), m_init4, N);
+    exact_math::launch_pack_float4(L, reinterpret_cast<const float*>(predicted.data()), m_predA, N);
+    const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
+    const bool odd = RadixSorter::numPasses(maxBit) & 1;
+    uint* k0 = odd ? m_keysAlt.data() : H.particleHash.data();
+    uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
+    uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
+    uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
+    exact_math::launch_hash_particles(L, k0, v0, m_predA, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing);
+    m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
+    exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+    VtHashParams hp = H.MakeParams(N, simParams.particleDiameter);
+    hp.tableSize = H.tableSize() / (int)m_instancing.count;
+    if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_predA, m_init4, m_sorted, hp,
+                                                   m_instancing))
+        exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_predA, m_init4, hp);
+    VT_CUDA(cudaGetLastError());
+    Synchronize();
+}
+
 int VtClothSolverGPU::ReadbackPipelined(float* hostPositions, float* hostNormals)
 {
     if (!m_copyStream) {

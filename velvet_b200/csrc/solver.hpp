@@ -86,6 +86,11 @@ public:
     // L180-236): the frame's results are snapshot into one of two device staging buffers on the solver stream (a few
     // microseconds) and travel to pinned host memory on a separate copy stream, so the PCIe transfer of frame k overlaps
     // the simulation of frame k+1.  Returns a ticket for ReadbackWait; at most two read-backs may be outstanding.
+    // The fused pipeline's spatial-hash stage (hash -> sort -> cell table -> reordered, tag-filtered neighbour cache) run
+    // stand-alone on the public `predicted` buffer and the hash's current initialPositions; results land in the public hash
+    // buffers.  Simulate() runs exactly these kernels on its internal float4 state; this entry exists so that they can be
+    // checked on arbitrary inputs (tests/test_hash_gpu.py).  Synchronous.
+    void HashFused();
     int ReadbackPipelined(float* hostPositions, float* hostNormals);
     void ReadbackWait(int ticket);
 

@@ -171,6 +171,10 @@ class VtClothSolverGPU:
         check(self._L.velvet_solver_hash(self._h))
         self.Synchronize()
 
+    def HashFused(self):
+        """The fused pipeline's own hash kernels on the public `predicted` buffer (what Simulate runs internally)."""
+        check(self._L.velvet_solver_hash_fused(self._h))
+
     def ReadbackAsync(self, host_positions_ptr, host_normals_ptr):
         check(self._L.velvet_solver_readback_async(self._h, host_positions_ptr, host_normals_ptr))
 
