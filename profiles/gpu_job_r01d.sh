@@ -18,4 +18,5 @@ ncu --set full --import-source on --clock-control none -k regex:cache_neighbors_
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_cache.log 2>&1
 ( compute-sanitizer --tool memcheck python tests/sanitize_gpu.py; compute-sanitizer --tool racecheck python tests/sanitize_gpu.py ) 2>&1 | grep -E "^ok|SUMMARY|ERROR|hazard" > gpurun_out/sanitizer_r01d.txt
 python bench.py --math fast --no-cpu-baseline > gpurun_out/bench_fast.json 2> gpurun_out/bench_fast.err
+python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 ls -la gpurun_out

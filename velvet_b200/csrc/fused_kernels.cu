@@ -63,11 +63,13 @@ __global__ void prepare_inputs_kernel(const VtSDFCollider* __restrict__ collider
     for (unsigned k = i; k < numSlotFloats; k += blockDim.x) slotPositionsOut[k] = slotPositions[k];
 }
 
+#if !VT_FAST_MATH  // integer helpers exist in the exact build only
 __global__ void __launch_bounds__(PB) fill_kernel(unsigned* __restrict__ dst, unsigned value, unsigned n)
 {
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id < n) dst[id] = value;
 }
+#endif
 
 __global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict__ positions,
                                                          const float* __restrict__ velocities,
@@ -586,6 +588,7 @@ __global__ void __launch_bounds__(PB) normals_kernel(const float4* __restrict__ 
     store3(normalsOut, id, normalize(sum));
 }
 
+#if !VT_FAST_MATH  // plumbing kernels exist in the exact build only
 __global__ void __launch_bounds__(PB) gather_by_id_kernel(const float4* __restrict__ src, const unsigned* __restrict__ ids, unsigned n,
                                                           float4* __restrict__ out)
 {
@@ -606,6 +609,8 @@ __global__ void __launch_bounds__(PB) pack_float4_kernel(const float* __restrict
     if (id >= n) return;
     out[id] = F4(load3(packed3, id), 0.0f);
 }
+
+#endif
 
 }  // namespace
 
