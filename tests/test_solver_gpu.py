@@ -490,3 +490,30 @@ def test_pipelined_readback_delivers_every_frame():
         prev = (t, k & 1)
     g.ReadbackWait(prev[0])
     assert np.array_equal(hp[prev[1]].numpy(), want[4][0]) and np.array_equal(hn[prev[1]].numpy(), want[4][1])
+
+
+def test_uploading_constraint_or_initial_position_buffers_takes_effect_in_the_fused_pipeline():
+    """Public buffers are the reference's contract (VtBuffer: the host may rewrite them between frames).  Rewriting a
+    constraint buffer must rebuild the fused pipeline's tile plan, rewriting initialPositions must refresh the copy its
+    neighbour filter uses: the fused result has to follow the oracle given the same edits."""
+    p = gpu_params(numSubsteps=3, numIterations=5)
+    g, o = make_pair(31, p)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    for _ in range(2):
+        g.Simulate()
+        o.simulate()
+    assert_fused_parity(g, o, TOL_1)
+    # shrink every rest length by 5 %, stiffen nothing else
+    sl = (o.buffer("stretchLengths") * np.float32(0.95)).astype(np.float32)
+    o.buffer("stretchLengths")[:] = sl
+    g.upload("stretchLengths", sl)
+    # and pretend the cloth was registered slightly sheared: changes which close pairs count as self-collision neighbours
+    ip = o.buffer("initialPositions").reshape(-1, 3).copy()
+    ip[:, 0] += np.float32(0.3) * ip[:, 2]
+    o.buffer("initialPositions")[:] = ip.reshape(-1)
+    g.upload("initialPositions", ip.reshape(-1))
+    for _ in range(3):
+        g.Simulate()
+        o.simulate()
+    assert_fused_parity(g, o, TOL_1)
+    assert np.array_equal(valid_prefix_table(g.download("neighbors"), 1024, 64), valid_prefix_table(o.buffer("neighbors"), 1024, 64))

@@ -278,6 +278,7 @@ int velvet_solver_upload(VelvetSolver* s, int bufferId, const void* host, size_t
     VT_REQUIRE(bytes <= v.count * v.elemSize, "upload: more bytes than the buffer holds");
     s->impl.Synchronize();
     if (bytes) VT_CUDA(cudaMemcpy(v.ptr, host, bytes, cudaMemcpyDefault));
+    s->impl.NotifyBufferEdited(bufferId);
     VT_API_END
 }
 

@@ -167,6 +167,27 @@ VtClothSolverGPU::~VtClothSolverGPU()
     if (m_stream) cudaStreamDestroy(m_stream);
 }
 
+void VtClothSolverGPU::NotifyBufferEdited(int bufferId)
+{
+    switch (bufferId) {
+    case VELVET_BUF_INDICES:
+    case VELVET_BUF_STRETCHINDICES:
+    case VELVET_BUF_STRETCHLENGTHS:
+    case VELVET_BUF_BENDINDICES:
+    case VELVET_BUF_BENDANGLES:
+    case VELVET_BUF_ATTACHPARTICLEIDS:
+    case VELVET_BUF_ATTACHSLOTIDS:
+    case VELVET_BUF_ATTACHDISTANCES:
+        invalidate();
+        break;
+    case VELVET_BUF_INITIALPOSITIONS:
+        m_initDirty = true;
+        break;
+    default:
+        break;
+    }
+}
+
 void VtClothSolverGPU::HashFused()
 {
     VT_CUDA(cudaSetDevice(m_device));
@@ -519,7 +540,16 @@ void VtClothSolverGPU::simulateSeam(float frameTime, Stage* t)
 // ---- fused pipeline resources: SoA state, tile plan, vertex->triangle CSR (rebuilt when the topology changes)
 void VtClothSolverGPU::ensureFusedResources()
 {
-    if (!m_topologyDirty) return;
+    if (!m_topologyDirty) {
+        if (m_initDirty && m_fusedUsable) {  // initialPositions were edited in place: refresh the float4 copy the hash filters with
+            exact_math::launch_pack_float4(FusedLaunch{m_stream, simParams.numParticles},
+                                           reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4,
+                                           simParams.numParticles);
+            m_initDirty = false;
+        }
+        return;
+    }
+    m_initDirty = false;  // the rebuild below packs the current initialPositions
     Synchronize();
     const uint N = simParams.numParticles;
     if (!m_instanced) m_instancing = Instancing{1u, N, (uint)attachSlotPositions.size()};

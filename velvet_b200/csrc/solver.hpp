@@ -86,6 +86,10 @@ public:
     // L180-236): the frame's results are snapshot into one of two device staging buffers on the solver stream (a few
     // microseconds) and travel to pinned host memory on a separate copy stream, so the PCIe transfer of frame k overlaps
     // the simulation of frame k+1.  Returns a ticket for ReadbackWait; at most two read-backs may be outstanding.
+    // To be called after the host (or velvet_solver_upload) rewrote a public buffer in place: constraint / topology buffers
+    // make the fused pipeline rebuild its tile plan, initialPositions refreshes its float4 copy; state buffers (positions,
+    // velocities, predicted, invMasses, attachSlotPositions) are re-imported every frame anyway.
+    void NotifyBufferEdited(int bufferId);
     // The fused pipeline's spatial-hash stage (hash -> sort -> cell table -> reordered, tag-filtered neighbour cache) run
     // stand-alone on the public `predicted` buffer and the hash's current initialPositions; results land in the public hash
     // buffers.  Simulate() runs exactly these kernels on its internal float4 state; this entry exists so that they can be
@@ -220,6 +224,7 @@ private:
 
     // fused pipeline state
     bool m_topologyDirty = true;
+    bool m_initDirty = false;  // initialPositions edited: m_init4 must be re-packed
     bool m_fusedUsable = false;
     std::string m_fallbackReason;
     unsigned long long m_graphKey = 0;
