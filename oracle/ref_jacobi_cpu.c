@@ -1,7 +1,7 @@
 /*
  * oracle/ref_jacobi_cpu.c -- O1 parity oracle.  TEST INFRASTRUCTURE ONLY (see the header).
- * PARITY UNPINNED by the reference (no golden vectors exist upstream); pinned by property
- * tests and by the reference's CUDA kernels built on stand-in headers (oracle/ref_cuda).
+ * The reference ships no golden vectors; pinned against committed outputs of the reference's own CUDA
+ * kernels (tests/golden/refcuda_*.npz), by those kernels run live (oracle/ref_cuda) and by property tests.
  *
  * Sequential fp32 restatement of the kernels of VtClothSolverGPU.cu / SpatialHashGPU.cu and
  * of the host orchestration in VtClothSolverGPU.hpp / SpatialHashGPU.hpp /
