@@ -17,6 +17,9 @@ Fixtures (all small, np.savez_compressed):
                               iterations): positions after frames 1, 5, 10, 15 (contact-free, where the reference is
                               self-consistent), velocities + normals after frame 1
   refcuda_drape64.npz         64x64 self-colliding drape over sphere + plane: positions after frames 1, 10, 20
+  refcuda_cube25.npz          25x25 cloth with 4 corner attachments (long-range attachment active) falling on a rotated,
+                              slowly turning unit cube + plane, friction 0.6, 5 substeps x 5 iterations: positions after
+                              frames 1, 5, 10 (cube SDF with rounded edges, collider velocity in the friction term)
 """
 import math
 import os
@@ -105,6 +108,23 @@ def drape_fixture(out):
     np.savez_compressed(os.path.join(out, "refcuda_drape64.npz"), frames=np.array([1, 10, 20]), **keep)
 
 
+def cube_fixture(out):
+    R = 24
+    p = params(numSubsteps=5, numIterations=5, friction=0.6)
+    corners = [0, R, (R + 1) * (R + 1) - 1, (R + 1) * R]
+    o, r = pair(R, p, (0, 1.5, 1.0), (90, 0, 0), corners)
+    keep = {}
+    last = o1.transform_matrix((0, 0.95, 0), (0, 15, 0), (1, 1, 1))
+    for f in range(10):
+        cur = o1.transform_matrix((0, 0.95, 0), (0, 15 + 2 * (f + 1), 0), (1, 1, 1))
+        r.set_colliders([o1.make_collider(o1.PLANE, (0, 0, 0), (1, 1, 1)), o1.make_collider(o1.CUBE, (0, 0.95, 0), (1, 1, 1), cur, last)])
+        last = cur
+        r.simulate()
+        if f + 1 in (1, 5, 10):
+            keep[f"positions_{f + 1}"] = r.buffer("positions").copy()
+    np.savez_compressed(os.path.join(out, "refcuda_cube25.npz"), frames=np.array([1, 5, 10]), **keep)
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out, exist_ok=True)
@@ -114,4 +134,5 @@ if __name__ == "__main__":
         hash_fixture(R, out)
     cfg1_fixture(out)
     drape_fixture(out)
+    cube_fixture(out)
     print("golden fixtures written to", out, sorted(os.listdir(out)))

@@ -273,3 +273,27 @@ def test_oracle_positions_within_tolerance_of_reference_kernel_golden_drape64():
             worst[f] = float(np.max(np.abs(s.buffer("positions") - g[f"positions_{f}"])))
     print("O1 vs reference CUDA kernels, 64x64 drape, max |dx| per frame:", worst)
     assert worst[1] <= 1e-4 * 2.0 and worst[10] <= 1e-3 * 2.0 and worst[20] <= 1e-3 * 2.0, worst
+
+
+def test_oracle_positions_within_tolerance_of_reference_kernel_golden_cube25():
+    """Cube SDF (rounded edges, collider velocity in the friction term), friction 0.6, four corner attachments with
+    long-range attachment: the reference's own kernels after 1 / 5 / 10 frames."""
+    g = _golden("refcuda_cube25")
+    R = 24
+    p = o1.default_params()
+    p.numSubsteps, p.numIterations, p.friction = 5, 5, 0.6
+    s = o1.O1Solver(p)
+    v, idx = o1.generate_cloth_mesh(R)
+    corners = [0, R, (R + 1) * (R + 1) - 1, (R + 1) * R]
+    s.cloth_object_start(R, v, idx, o1.transform_matrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1)), corners)
+    last = o1.transform_matrix((0, 0.95, 0), (0, 15, 0), (1, 1, 1))
+    worst = {}
+    for f in range(10):
+        cur = o1.transform_matrix((0, 0.95, 0), (0, 15 + 2 * (f + 1), 0), (1, 1, 1))
+        s.set_colliders([o1.make_collider(o1.PLANE, (0, 0, 0), (1, 1, 1)), o1.make_collider(o1.CUBE, (0, 0.95, 0), (1, 1, 1), cur, last)])
+        last = cur
+        s.simulate()
+        if f + 1 in (1, 5, 10):
+            worst[f + 1] = float(np.max(np.abs(s.buffer("positions") - g[f"positions_{f + 1}"])))
+    print("O1 vs reference CUDA kernels, 25x25 cloth on a turning cube, max |dx| per frame:", worst)
+    assert worst[1] <= 1e-4 * 2.0 and worst[5] <= 1e-3 * 2.0 and worst[10] <= 1e-3 * 2.0, worst

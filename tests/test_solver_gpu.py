@@ -448,6 +448,18 @@ def test_product_against_reference_kernel_golden_vectors(math_mode):
         g.Simulate()
         if fr + 1 in (1, 10, 20):
             assert max_abs_diff(g.download("positions"), gold[f"positions_{fr + 1}"]) <= (TOL_1 if fr == 0 else TOL_60), fr + 1
+    # 25x25 cloth, four corner attachments, on a turning cube with friction 0.6 (cube SDF + collider velocity)
+    gold = np.load(os.path.join(GOLDEN, "refcuda_cube25.npz"))
+    R = 24
+    pc = gpu_params(numSubsteps=5, numIterations=5, friction=0.6)
+    g, _ = make_pair(R, pc, attached=[0, R, (R + 1) * (R + 1) - 1, (R + 1) * R], oracle=False, math_mode=math_mode)
+    cube = ColliderTrack(vb.COLLIDER_CUBE, (0, 0.95, 0), (1, 1, 1), (0, 15, 0))
+    for fr in range(10):
+        cube.move((0, 0.95, 0), (0, 15 + 2 * (fr + 1), 0))
+        g.UpdateColliders([vb.MakeCollider(vb.COLLIDER_PLANE, (0, 0, 0), (1, 1, 1)), cube.collider()])
+        g.Simulate()
+        if fr + 1 in (1, 5, 10):
+            assert max_abs_diff(g.download("positions"), gold[f"positions_{fr + 1}"]) <= (TOL_1 if fr == 0 else TOL_60), fr + 1
     for R in (31, 63):
         gold = np.load(os.path.join(GOLDEN, f"refcuda_hash_R{R}.npz"))
         n = (R + 1) ** 2
