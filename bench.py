@@ -39,6 +39,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 at
+# communicator creation), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -143,7 +154,7 @@ def reference_main(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -367,7 +378,7 @@ def velvet_main(args, rank, world, local_rank):
         "stages_ms": {k: round(v, 4) for k, v in stages.items()}, "setup_s": setup_s,
         "other_math_mode": other,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     group.barrier()
     group.close()
     return 0
