@@ -337,6 +337,10 @@ VELVET_API int velvet_solver_dd_simulate(VelvetSolver* s, float deltaTime, int s
  * globals4 (may be NULL) = {maxLocals, maxKS, maxKB, maxBendPerTile}. */
 VELVET_API int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, unsigned* perTile4, unsigned capacityTiles,
                                       unsigned* globals4);
+/* Host-only: FNV-1a digest of every array of the tile plan of a grid cloth (with two attach slots on vertices {0, R} when
+ * withAttach != 0).  The plan is built by worker threads (VELVET_PLAN_THREADS, default: the hardware concurrency); the digest
+ * must not depend on their number (tests/test_capi_cpu.py). */
+VELVET_API int velvet_plan_grid_digest(int resolution, int tileSize, int withAttach, unsigned long long* digest);
 /* Host-only: shared-memory wavefronts per Jacobi iteration of the constraint threads' 16-byte accesses (position loads and
  * slot stores) for the tile plan of a grid cloth: out3 = {minimum, with records in constraint-id order, with the emitted
  * bank-conflict-avoiding order}. */

@@ -64,3 +64,33 @@ def test_tile_plan_record_order_avoids_shared_memory_bank_conflicts():
         ideal, id_order, emitted = out[0], out[1], out[2]
         assert id_order >= 1.7 * ideal, (R, tile, list(out))
         assert emitted <= 1.25 * ideal, (R, tile, list(out))
+
+
+def test_tile_plan_does_not_depend_on_the_number_of_builder_threads():
+    """build_tile_plan distributes tiles over worker threads; every array of the plan must be identical to the
+    single-threaded build (the kernels' results depend on the plan only through these arrays)."""
+    import ctypes as C
+    import os
+    from velvet_b200 import _capi
+    L = _capi.load()
+    L.velvet_plan_grid_digest.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+
+    def digest(R, tile, attach, threads):
+        old = os.environ.get("VELVET_PLAN_THREADS")
+        if threads is None:
+            os.environ.pop("VELVET_PLAN_THREADS", None)
+        else:
+            os.environ["VELVET_PLAN_THREADS"] = str(threads)
+        try:
+            d = C.c_ulonglong()
+            assert L.velvet_plan_grid_digest(R, tile, attach, C.byref(d)) == 0
+            return d.value
+        finally:
+            if old is None:
+                os.environ.pop("VELVET_PLAN_THREADS", None)
+            else:
+                os.environ["VELVET_PLAN_THREADS"] = old
+
+    for R, tile, attach in ((255, 256, 0), (255, 128, 1), (300, 256, 1), (511, 256, 0)):
+        one = digest(R, tile, attach, 1)
+        assert digest(R, tile, attach, 3) == one and digest(R, tile, attach, 8) == one and digest(R, tile, attach, None) == one

@@ -540,6 +540,46 @@ int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, uns
     VT_API_END
 }
 
+int velvet_plan_grid_digest(int resolution, int tileSize, int withAttach, unsigned long long* digest)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(resolution > 0 && digest, "plan_grid_digest: bad argument");
+    const int R = resolution;
+    const size_t n = (size_t)(R + 1) * (R + 1);
+    std::vector<float> v(3 * n);
+    std::vector<unsigned> idx((size_t)6 * R * R);
+    GenerateClothMesh(R, v.data(), idx.data());
+    const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::vector<int> attached;
+    if (withAttach) attached = {0, R};
+    const GridConstraints g = GenerateGridConstraints(R, v.data(), idx.data(), identity, attached, 1.5f, 0);
+    const TilePlan plan = build_tile_plan((unsigned)n, v.data(), g.stretchIdx.data(), g.stretchLen.data(), g.stretchLen.size(),
+                                          g.bendIdx.data(), g.bendAngle.data(), g.bendAngle.size(), g.attachPid.data(),
+                                          g.attachSlot.data(), g.attachDist.data(), g.attachDist.size(), tileSize ? tileSize : 256);
+    if (!plan.valid) return set_error(VELVET_ERR_UNSUPPORTED, plan.whyInvalid);
+    unsigned long long h = 1469598103934665603ull;  // FNV-1a over every array of the plan
+    auto mix = [&](const void* p, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < bytes; i++) {
+            h ^= b[i];
+            h *= 1099511628211ull;
+        }
+    };
+    mix(plan.tiles.data(), plan.tiles.size() * sizeof(TileDesc));
+    mix(plan.ownedIds.data(), plan.ownedIds.size() * 4);
+    mix(plan.haloIds.data(), plan.numHalo * 4);
+    mix(plan.sCnt.data(), plan.sCnt.size());
+    mix(plan.bCnt.data(), plan.bCnt.size());
+    mix(plan.attOff.data(), plan.attOff.size() * 4);
+    mix(plan.stretchRec.data(), plan.stretchRec.size() * sizeof(Rec2));
+    mix(plan.bendRec.data(), plan.bendRec.size() * sizeof(Rec4));
+    mix(plan.attachRec.data(), plan.attachRec.size() * sizeof(Rec2));
+    const unsigned globals[5] = {plan.maxLocals, plan.maxBendPerTile, plan.maxStretchPerTile, plan.maxKS, plan.maxKB};
+    mix(globals, sizeof(globals));
+    *digest = h;
+    VT_API_END
+}
+
 int velvet_plan_grid_smem_wavefronts(int resolution, int tileSize, unsigned long long* out3)
 {
     VT_API_BEGIN

@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace velvet {
 
@@ -244,97 +246,169 @@ TilePlan build_tile_plan(unsigned N, const float* positions, const int* stretchI
     plan.sCnt.resize(N);
     plan.bCnt.resize(N);
     plan.attOff.resize((size_t)N + numTiles);
+    // Tiles are independent once the per-tile constraint lists exist: worker threads take contiguous tile ranges.  Every
+    // output range is disjoint per tile; the halo lists are collected per worker (discovery order inside a tile is the
+    // sequential order) and concatenated in tile order afterwards, so the plan does not depend on the thread count.
+    struct Worker {
+        std::vector<unsigned> halo;                 // halo ids of the worker's tiles, tile after tile
+        std::vector<unsigned> haloKey, haloVal;     // open-addressing map particle -> halo local of the current tile
+        std::vector<unsigned> cntS, cntB, cntA;
+        std::vector<Rec2> scratch2;
+        std::vector<Rec4> scratch4;
+        std::vector<unsigned char> taken;
+        unsigned maxKS = 0, maxKB = 0, maxLocals = 0, maxBend = 0, maxStretch = 0;
+        size_t wfIdeal = 0, wfIdOrder = 0, wfEmitted = 0;
+        std::string error;
+    };
+    unsigned numWorkers = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    if (const char* e = getenv("VELVET_PLAN_THREADS")) numWorkers = (unsigned)std::max(1, atoi(e));
+    numWorkers = std::min(numWorkers, std::max(1u, numTiles / 64u));  // small plans: one thread
+    std::vector<Worker> workers(numWorkers);
+    std::vector<unsigned> haloCount(numTiles, 0);
+
+    auto run = [&](unsigned wi) {
+        Worker& W = workers[wi];
+        const unsigned tBegin = (unsigned)((unsigned long long)numTiles * wi / numWorkers);
+        const unsigned tEnd = (unsigned)((unsigned long long)numTiles * (wi + 1) / numWorkers);
+        constexpr unsigned MAP = 4096, EMPTY = 0xffffffffu;  // > 2 x TP_MAX_LOCALS entries
+        W.haloKey.assign(MAP, EMPTY);
+        W.haloVal.resize(MAP);
+        W.cntS.resize(T);
+        W.cntB.resize(T);
+        W.cntA.resize(T);
+        std::vector<unsigned> usedSlots;
+        for (unsigned t = tBegin; t < tEnd; t++) {
+            TileDesc& td = plan.tiles[t];
+            td.ownedOff = t * T;
+            td.nOwned = std::min(N, td.ownedOff + T) - td.ownedOff;
+            td.haloOff = 0;  // filled in after the join
+            td.nHalo = 0;
+            td.stretchOff = (unsigned)sRecOff[t];
+            td.nStretch = (unsigned)(sOff[t + 1] - sOff[t]);
+            td.bendOff = (unsigned)bOff[t];
+            td.nBend = (unsigned)(bOff[t + 1] - bOff[t]);
+            td.attachOff = (unsigned)aOff[t];
+            td.nAttach = (unsigned)(aOff[t + 1] - aOff[t]);
+            td.baseOff = td.ownedOff + t;
+            td.pad = 0;
+            std::fill(W.cntS.begin(), W.cntS.end(), 0u);
+            std::fill(W.cntB.begin(), W.cntB.end(), 0u);
+            std::fill(W.cntA.begin(), W.cntA.end(), 0u);
+            for (unsigned slot : usedSlots) W.haloKey[slot] = EMPTY;
+            usedSlots.clear();
+
+            bool overflow = false, haloOverflow = false;
+            auto endpoint = [&](unsigned p, std::vector<unsigned>& cnt) -> unsigned {
+                if (tileOf[p] == t) {
+                    const unsigned l = localOf[p];
+                    const unsigned k = cnt[l]++;
+                    if (k >= TP_NO_SLOT) overflow = true;
+                    return (l << TP_ORD_BITS) | (k & 31u);
+                }
+                unsigned slot = (p * 2654435761u) >> 20;  // 12 bits
+                while (W.haloKey[slot] != EMPTY && W.haloKey[slot] != p) slot = (slot + 1) & (MAP - 1);
+                if (W.haloKey[slot] == EMPTY) {
+                    if (T + td.nHalo >= TP_MAX_LOCALS) {  // reported below; keep the map from filling up
+                        haloOverflow = true;
+                        return (TP_MAX_LOCALS << TP_ORD_BITS) | TP_NO_SLOT;
+                    }
+                    W.haloKey[slot] = p;
+                    W.haloVal[slot] = T + td.nHalo++;  // halo locals start at the tile size, also in a partially filled tile
+                    usedSlots.push_back(slot);
+                    W.halo.push_back(p);
+                }
+                return (W.haloVal[slot] << TP_ORD_BITS) | TP_NO_SLOT;
+            };
+
+            for (unsigned i = 0; i < td.nStretch; i++) {
+                const unsigned c = sList[sOff[t] + i];
+                const unsigned ea = endpoint((unsigned)stretchIndices[2 * (size_t)c], W.cntS);
+                const unsigned eb = endpoint((unsigned)stretchIndices[2 * (size_t)c + 1], W.cntS);
+                plan.stretchRec[td.stretchOff + i] = Rec2{ea | (eb << 16), float_bits(stretchLengths[c])};
+            }
+            for (unsigned i = 0; i < td.nBend; i++) {
+                const unsigned c = bList[td.bendOff + i];
+                unsigned e[4];
+                for (int k = 0; k < 4; k++) e[k] = endpoint(bendIndices[4 * (size_t)c + k], W.cntB);
+                plan.bendRec[td.bendOff + i] = Rec4{e[0] | (e[1] << 16), e[2] | (e[3] << 16), float_bits(bendAngles[c]), c};
+            }
+            haloCount[t] = td.nHalo;
+            if (overflow) {
+                W.error = "a particle has more than 30 stretch or bend constraints";
+                return;
+            }
+            if (haloOverflow || T + td.nHalo > TP_MAX_LOCALS) {
+                W.error = "tile halo too large (more than 2047 local particles)";
+                return;
+            }
+
+            // record order inside the tile: free of shared-memory bank conflicts where possible (ordinals are already fixed)
+            {
+                Rec2* sr = plan.stretchRec.data() + td.stretchOff;
+                Rec4* br = plan.bendRec.data() + td.bendOff;
+                W.wfIdeal += (size_t)((td.nStretch + 7) / 8) * 4 + (size_t)((td.nBend + 7) / 8) * 8;
+                W.wfIdOrder += tile_wavefronts<2>(sr, td.nStretch) + tile_wavefronts<4>(br, td.nBend);
+                reorder_for_banks<2>(sr, td.nStretch, W.scratch2, W.taken);
+                reorder_for_banks<4>(br, td.nBend, W.scratch4, W.taken);
+                W.wfEmitted += tile_wavefronts<2>(sr, td.nStretch) + tile_wavefronts<4>(br, td.nBend);
+            }
+
+            // per-particle constraint counts (the slot of ordinal k of particle l is slots[k * T + l])
+            for (unsigned l = 0; l < td.nOwned; l++) {
+                plan.sCnt[td.ownedOff + l] = (uint8_t)W.cntS[l];
+                plan.bCnt[td.ownedOff + l] = (uint8_t)W.cntB[l];
+                W.maxKS = std::max(W.maxKS, W.cntS[l]);
+                W.maxKB = std::max(W.maxKB, W.cntB[l]);
+            }
+            W.maxLocals = std::max(W.maxLocals, T + td.nHalo);
+            W.maxBend = std::max(W.maxBend, td.nBend);
+            W.maxStretch = std::max(W.maxStretch, td.nStretch);
+
+            // attach: CSR by owned particle, ascending constraint id inside each particle
+            for (unsigned i = 0; i < td.nAttach; i++) W.cntA[localOf[(unsigned)attachParticleIDs[aList[td.attachOff + i]]]]++;
+            unsigned accA = 0;
+            for (unsigned l = 0; l < td.nOwned; l++) {
+                plan.attOff[td.baseOff + l] = accA;
+                accA += W.cntA[l];
+                W.cntA[l] = plan.attOff[td.baseOff + l];
+            }
+            plan.attOff[td.baseOff + td.nOwned] = accA;
+            for (unsigned i = 0; i < td.nAttach; i++) {
+                const unsigned c = aList[td.attachOff + i];
+                const unsigned l = localOf[(unsigned)attachParticleIDs[c]];
+                plan.attachRec[td.attachOff + W.cntA[l]++] = Rec2{(unsigned)attachSlotIDs[c], float_bits(attachDistances[c])};
+            }
+        }
+    };
+    if (numWorkers == 1) {
+        run(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned wi = 0; wi < numWorkers; wi++) pool.emplace_back(run, wi);
+        for (std::thread& th : pool) th.join();
+    }
+    for (const Worker& W : workers)
+        if (!W.error.empty()) return fail(W.error);  // workers are scanned in tile order: the first failing range wins
     plan.haloIds.clear();
-    std::vector<unsigned> haloStamp(N, 0xffffffffu), haloLocal(N);
-    std::vector<unsigned> cntS(T), cntB(T), cntA(T);
-    std::vector<Rec2> scratch2;
-    std::vector<Rec4> scratch4;
-    std::vector<unsigned char> takenScratch;
-
-    for (unsigned t = 0; t < numTiles; t++) {
-        TileDesc& td = plan.tiles[t];
-        td.ownedOff = t * T;
-        td.nOwned = std::min(N, td.ownedOff + T) - td.ownedOff;
-        td.haloOff = (unsigned)plan.haloIds.size();
-        td.nHalo = 0;
-        td.stretchOff = (unsigned)sRecOff[t];
-        td.nStretch = (unsigned)(sOff[t + 1] - sOff[t]);
-        td.bendOff = (unsigned)bOff[t];
-        td.nBend = (unsigned)(bOff[t + 1] - bOff[t]);
-        td.attachOff = (unsigned)aOff[t];
-        td.nAttach = (unsigned)(aOff[t + 1] - aOff[t]);
-        td.baseOff = td.ownedOff + t;
-        td.pad = 0;
-        std::fill(cntS.begin(), cntS.end(), 0u);
-        std::fill(cntB.begin(), cntB.end(), 0u);
-        std::fill(cntA.begin(), cntA.end(), 0u);
-
-        bool overflow = false;
-        auto endpoint = [&](unsigned p, std::vector<unsigned>& cnt) -> unsigned {
-            if (tileOf[p] == t) {
-                const unsigned l = localOf[p];
-                const unsigned k = cnt[l]++;
-                if (k >= TP_NO_SLOT) overflow = true;
-                return (l << TP_ORD_BITS) | (k & 31u);
-            }
-            if (haloStamp[p] != t) {
-                haloStamp[p] = t;
-                haloLocal[p] = T + td.nHalo++;  // halo locals start at the tile size, also in a partially filled tile
-                plan.haloIds.push_back(p);
-            }
-            return (haloLocal[p] << TP_ORD_BITS) | TP_NO_SLOT;
-        };
-
-        for (unsigned i = 0; i < td.nStretch; i++) {
-            const unsigned c = sList[sOff[t] + i];
-            const unsigned ea = endpoint((unsigned)stretchIndices[2 * (size_t)c], cntS);
-            const unsigned eb = endpoint((unsigned)stretchIndices[2 * (size_t)c + 1], cntS);
-            plan.stretchRec[td.stretchOff + i] = Rec2{ea | (eb << 16), float_bits(stretchLengths[c])};
+    {
+        size_t total = 0;
+        for (const Worker& W : workers) total += W.halo.size();
+        plan.haloIds.reserve(total + 1);
+        unsigned off = 0;
+        for (unsigned t = 0; t < numTiles; t++) {
+            plan.tiles[t].haloOff = off;
+            off += haloCount[t];
         }
-        for (unsigned i = 0; i < td.nBend; i++) {
-            const unsigned c = bList[td.bendOff + i];
-            unsigned e[4];
-            for (int k = 0; k < 4; k++) e[k] = endpoint(bendIndices[4 * (size_t)c + k], cntB);
-            plan.bendRec[td.bendOff + i] = Rec4{e[0] | (e[1] << 16), e[2] | (e[3] << 16), float_bits(bendAngles[c]), c};
-        }
-        if (overflow) return fail("a particle has more than 30 stretch or bend constraints");
-        if (T + td.nHalo > TP_MAX_LOCALS) return fail("tile halo too large (more than 2047 local particles)");
-
-        // record order inside the tile: free of shared-memory bank conflicts where possible (ordinals are already fixed)
-        {
-            Rec2* sr = plan.stretchRec.data() + td.stretchOff;
-            Rec4* br = plan.bendRec.data() + td.bendOff;
-            plan.smemWavefrontsIdeal += (size_t)((td.nStretch + 7) / 8) * 4 + (size_t)((td.nBend + 7) / 8) * 8;
-            plan.smemWavefrontsIdOrder += tile_wavefronts<2>(sr, td.nStretch) + tile_wavefronts<4>(br, td.nBend);
-            reorder_for_banks<2>(sr, td.nStretch, scratch2, takenScratch);
-            reorder_for_banks<4>(br, td.nBend, scratch4, takenScratch);
-            plan.smemWavefronts += tile_wavefronts<2>(sr, td.nStretch) + tile_wavefronts<4>(br, td.nBend);
-        }
-
-        // per-particle constraint counts (the slot of ordinal k of particle l is slots[k * T + l])
-        for (unsigned l = 0; l < td.nOwned; l++) {
-            plan.sCnt[td.ownedOff + l] = (uint8_t)cntS[l];
-            plan.bCnt[td.ownedOff + l] = (uint8_t)cntB[l];
-            plan.maxKS = std::max(plan.maxKS, cntS[l]);
-            plan.maxKB = std::max(plan.maxKB, cntB[l]);
-        }
-        plan.maxLocals = std::max(plan.maxLocals, T + td.nHalo);
-        plan.maxBendPerTile = std::max(plan.maxBendPerTile, td.nBend);
-        plan.maxStretchPerTile = std::max(plan.maxStretchPerTile, td.nStretch);
-
-        // attach: CSR by owned particle, ascending constraint id inside each particle
-        for (unsigned i = 0; i < td.nAttach; i++) cntA[localOf[(unsigned)attachParticleIDs[aList[td.attachOff + i]]]]++;
-        unsigned accA = 0;
-        for (unsigned l = 0; l < td.nOwned; l++) {
-            plan.attOff[td.baseOff + l] = accA;
-            accA += cntA[l];
-            cntA[l] = plan.attOff[td.baseOff + l];
-        }
-        plan.attOff[td.baseOff + td.nOwned] = accA;
-        for (unsigned i = 0; i < td.nAttach; i++) {
-            const unsigned c = aList[td.attachOff + i];
-            const unsigned l = localOf[(unsigned)attachParticleIDs[c]];
-            plan.attachRec[td.attachOff + cntA[l]++] = Rec2{(unsigned)attachSlotIDs[c], float_bits(attachDistances[c])};
+        for (const Worker& W : workers) {
+            plan.haloIds.insert(plan.haloIds.end(), W.halo.begin(), W.halo.end());
+            plan.maxKS = std::max(plan.maxKS, W.maxKS);
+            plan.maxKB = std::max(plan.maxKB, W.maxKB);
+            plan.maxLocals = std::max(plan.maxLocals, W.maxLocals);
+            plan.maxBendPerTile = std::max(plan.maxBendPerTile, W.maxBend);
+            plan.maxStretchPerTile = std::max(plan.maxStretchPerTile, W.maxStretch);
+            plan.smemWavefrontsIdeal += W.wfIdeal;
+            plan.smemWavefrontsIdOrder += W.wfIdOrder;
+            plan.smemWavefronts += W.wfEmitted;
         }
     }
     // halo endpoints: replace the NO_SLOT marker by the dump-row ordinal of their constraint type
