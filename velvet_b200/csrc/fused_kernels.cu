@@ -341,6 +341,39 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- bulk copies (TMA, non-tensor form) with mbarrier completion: one thread moves a tile's whole record range
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P_OUT;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P_OUT, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P_OUT;\n\t}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, `bytes` a multiple of 16 (both addresses 16-byte aligned); completes one phase of `mbar`
+__device__ __forceinline__ void bulk_load(void* smemDst, const void* gmemSrc, unsigned bytes, unsigned mbar)
+{
+    if (bytes) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the buffer are ordered first
+        asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(gmemSrc), "r"(bytes), "r"(mbar)
+                     : "memory");
+    } else {
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+    }
+}
+
 // Persistent, software-pipelined form: CTA b walks the work items b, b + gridDim.x, ... (work item = tile x instance).
 // While tile k is being solved, the inputs of tile k+1 are already on their way into shared memory:
 //   top of k      : positions of k+1 (gathered by id with cp.async into the other half of the double-buffered sp)
@@ -372,6 +405,8 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     uint2* const s_srec = reinterpret_cast<uint2*>(s_brec + plan.maxBendPerTile);
     unsigned* const s_tdw = reinterpret_cast<unsigned*>(s_srec + ((plan.maxStretchPerTile + 1u) & ~1u));  // ring of 3 descriptors
     const TileDesc* const s_td = reinterpret_cast<const TileDesc*>(s_tdw);
+    const unsigned mbarS = (unsigned)__cvta_generic_to_shared(s_tdw + 3 * TD_WORDS);  // stretch / bend records of a tile landed
+    const unsigned mbarB = mbarS + 8u;
 
     const unsigned tid = threadIdx.x;
     const unsigned stride = gridDim.x;
@@ -389,13 +424,13 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         for (unsigned i = tid + T; i < d.nHalo; i += T)
             cp_async_16(sp + plan.tileSize + i, predIn + __ldg(plan.haloIds + d.haloOff + i));
     };
+    // record ranges are contiguous per tile: ONE bulk copy each by thread 0 (the per-thread cp.async form spent 3.5 % of
+    // the kernel's instructions on ~3.2 16-byte copies per thread and tile)
     auto issue_stretch = [&](const TileDesc& d) {
-        const uint4* g = reinterpret_cast<const uint4*>(plan.stretchRec + d.stretchOff);  // even offset: 16-byte aligned
-        const unsigned pairs = (d.nStretch + 1) >> 1;
-        for (unsigned c = tid; c < pairs; c += T) cp_async_16(reinterpret_cast<uint4*>(s_srec) + c, g + c);
+        if (tid == 0) bulk_load(s_srec, plan.stretchRec + d.stretchOff, ((d.nStretch + 1u) >> 1) * 16u, mbarS);  // even offset: aligned
     };
     auto issue_bend = [&](const TileDesc& d) {
-        for (unsigned c = tid; c < d.nBend; c += T) cp_async_16(s_brec + c, plan.bendRec + d.bendOff + c);
+        if (tid == 0) bulk_load(s_brec, plan.bendRec + d.bendOff, d.nBend * 16u, mbarB);
     };
     auto load_ids = [&](const TileDesc& d, unsigned& gid, unsigned& hid) {
         gid = tid < d.nOwned ? __ldg(plan.ownedIds + d.ownedOff + tid) : 0u;
@@ -410,6 +445,11 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     };
 
     // ---- pipeline prologue: descriptors of the first two items, everything of the first, ids of the second
+    if (tid == 0) {
+        mbar_init(mbarS, 1);
+        mbar_init(mbarB, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (tid < TD_WORDS) s_tdw[tid] = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w)) + tid);
     if (tid >= 32 && tid < 32 + TD_WORDS && w + stride < totalWork)
         s_tdw[TD_WORDS + tid - 32] = __ldg(reinterpret_cast<const unsigned*>(plan.tiles + tile_of(w + stride)) + tid - 32);
@@ -421,10 +461,8 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         load_ids(s_td[0], gidCur, hid);
         issue_positions(spBase, s_td[0], predInAll + (size_t)inst_of(w) * inst.particles, gidCur, hid);
         cp_async_commit();  // P(0)
-        issue_stretch(s_td[0]);
-        cp_async_commit();  // S(0)
-        issue_bend(s_td[0]);
-        cp_async_commit();  // B(0)
+        issue_stretch(s_td[0]);  // S(0)
+        issue_bend(s_td[0]);     // B(0)
         if (w + stride < totalWork) load_ids(s_td[1], gidNext, hidNext);
     }
 
@@ -445,7 +483,8 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
                             predInAll + (size_t)inst_of(w + stride) * inst.particles, gidNext, hidNext);
         cp_async_commit();      // P(k+1)
         const unsigned cntNext = hasNext ? load_counts(s_td[slotNext]) : 0u;
-        cp_async_wait_group<2>();  // P(k) and S(k) have landed; B(k), P(k+1) may still be in flight
+        cp_async_wait_group<1>();  // P(k) has landed; P(k+1) may still be in flight
+        mbar_wait(mbarS, k & 1u);  // S(k) has landed
         __syncthreads();
         if (hasNN && tid < TD_WORDS) s_tdw[slotNN * TD_WORDS + tid] = tdWord;
         const unsigned cntS = cntCur & 0xffu, cntB = cntCur >> 8;
@@ -486,8 +525,7 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         }
         __syncthreads();
 
-        if (hasNext) issue_stretch(s_td[slotNext]);
-        cp_async_commit();  // S(k+1)
+        if (hasNext) issue_stretch(s_td[slotNext]);  // S(k+1): every thread is past its last read of s_srec
         unsigned gidNN = 0, hidNN = 0;
         if (hasNN) load_ids(s_td[slotNN], gidNN, hidNN);  // consumed at the top of k+1
 
@@ -511,15 +549,14 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
                 }
             }
         }
-        cp_async_wait_group<2>();  // B(k) has landed; P(k+1), S(k+1) may still be in flight
+        mbar_wait(mbarB, k & 1u);  // B(k) has landed
         __syncthreads();           // slots are reused by the bending phase
 
         // ---- SolveBending_Kernel, L128-188
         for (unsigned c = tid; c < td.nBend; c += T) bend_to_slots<LOG2T>(s_brec[c], sp, slots, xpbd_bend, plan.maxKB);
         __syncthreads();
 
-        if (hasNext) issue_bend(s_td[slotNext]);
-        cp_async_commit();  // B(k+1)
+        if (hasNext) issue_bend(s_td[slotNext]);  // B(k+1)
         if (owner) {
             sum_slots<LOG2T>(slots, tid, cntB, delta, count);
             // ApplyDeltas_Kernel, L257-263
@@ -643,7 +680,7 @@ size_t iterate_smem_bytes(const TilePlanDev& plan)
     // + a ring of three tile descriptors
     const size_t rows = (size_t)(plan.maxKS > plan.maxKB ? plan.maxKS : plan.maxKB);
     return sizeof(float4) * (2 * (size_t)plan.maxLocals + rows * plan.threads + plan.maxBendPerTile + ((size_t)plan.maxStretchPerTile + 1) / 2) +
-           3 * sizeof(TileDesc);
+           3 * sizeof(TileDesc) + 16;  // + two mbarriers
 }
 
 // kernel variants: (slot-row width, threads)
