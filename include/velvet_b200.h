@@ -207,6 +207,13 @@ typedef enum VelvetMathMode {
                               contact-rich scene                                                                      */
 } VelvetMathMode;
 
+typedef enum VelvetIterateMode {
+    VELVET_ITERATE_AUTO = 0,  /* default: the implicit-grid Jacobi kernel when every registered cloth is a grid carrying exactly
+                                 the constraints VtClothObjectGPU generates (VtClothObjectGPU.hpp L75-132), else the tile kernel */
+    VELVET_ITERATE_TILES = 1, /* always the record-driven tile kernel (any mesh)                                                */
+    VELVET_ITERATE_GRID = 2   /* reported by velvet_solver_iterate_kernel only                                                  */
+} VelvetIterateMode;
+
 /* VtClothSolverGPU::Start (hpp L27-33): numParticles = 0.  params may be NULL (defaults).
  * device < 0 keeps the current CUDA device. */
 VELVET_API int velvet_solver_create(VelvetSolver** out, int device, const VtSimParams* params);
@@ -216,6 +223,10 @@ VELVET_API VtSimParams* velvet_solver_params(VelvetSolver* s);
 VELVET_API int velvet_solver_set_pipeline(VelvetSolver* s, int pipeline);
 /* Fused pipeline only: VelvetMathMode.  The spatial hash is bit-exact in both modes. */
 VELVET_API int velvet_solver_set_math_mode(VelvetSolver* s, int mode);
+/* Fused pipeline only: VELVET_ITERATE_AUTO or VELVET_ITERATE_TILES.  Both kernels are bit-identical. */
+VELVET_API int velvet_solver_set_iterate_mode(VelvetSolver* s, int mode);
+/* Writes the Jacobi kernel the next frame will run (VELVET_ITERATE_TILES or VELVET_ITERATE_GRID) to *kernel. */
+VELVET_API int velvet_solver_iterate_kernel(VelvetSolver* s, int* kernel);
 /* Fused pipeline only: particles per Jacobi tile (0 = default, else 128 / 256 / 512). */
 VELVET_API int velvet_solver_set_tile_size(VelvetSolver* s, int particlesPerTile);
 

@@ -12,6 +12,17 @@ from oracle import o1
 from util import EXTENT, gpu_params, max_abs_diff, to_o1_collider, to_o1_params, valid_prefix_table
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["grid", "tiles"])
+def iterate_kernel_param(request, monkeypatch):
+    """Every test runs twice: with the implicit-grid Jacobi kernel (the default for grid cloths) and with the record-driven
+    tile kernel forced (VELVET_ITERATE=tiles is read when a solver builds its plans)."""
+    if request.param == "tiles":
+        monkeypatch.setenv("VELVET_ITERATE", "tiles")
+    else:
+        monkeypatch.delenv("VELVET_ITERATE", raising=False)
+    return request.param
 TOL_1 = 1e-4 * EXTENT
 
 

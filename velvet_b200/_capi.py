@@ -44,6 +44,7 @@ assert C.sizeof(VtSimParams) == 80 and C.sizeof(VtSDFCollider) == 196 and C.size
 COLLIDER_SPHERE, COLLIDER_PLANE, COLLIDER_CUBE = 0, 1, 2
 PIPELINE_FUSED, PIPELINE_SEAM = 0, 1
 MATH_EXACT, MATH_FAST = 0, 1
+ITERATE_AUTO, ITERATE_TILES, ITERATE_GRID = 0, 1, 2
 
 BUFFER_IDS = {name: i for i, name in enumerate([
     "positions", "normals", "indices", "velocities", "predicted", "deltas", "deltaCounts", "invMasses",
@@ -59,7 +60,7 @@ EXPORTED_SYMBOLS = [
     "velvet_CollideParticles", "velvet_Finalize", "velvet_ComputeNormal", "velvet_HashObjects", "velvet_SortPairs",
     "velvet_seam_set_stream", "velvet_selftest_division", "velvet_selftest_constraints", "velvet_device_synchronize", "velvet_alloc", "velvet_free", "velvet_copy",
     "velvet_solver_create", "velvet_solver_destroy", "velvet_solver_params", "velvet_solver_set_pipeline",
-    "velvet_solver_set_math_mode", "velvet_solver_set_tile_size", "velvet_solver_add_cloth", "velvet_solver_add_stretch",
+    "velvet_solver_set_math_mode", "velvet_solver_set_iterate_mode", "velvet_solver_iterate_kernel", "velvet_solver_set_tile_size", "velvet_solver_add_cloth", "velvet_solver_add_stretch",
     "velvet_solver_add_attach_slot", "velvet_solver_add_attach", "velvet_solver_add_bend",
     "velvet_solver_update_colliders", "velvet_make_collider", "velvet_solver_simulate", "velvet_solver_simulate_dt",
     "velvet_solver_synchronize", "velvet_solver_hash", "velvet_solver_hash_fused", "velvet_solver_buffer", "velvet_solver_download",
@@ -122,6 +123,8 @@ def load():
         "velvet_solver_set_pipeline": [v, i],
         "velvet_solver_set_tile_size": [v, i],
         "velvet_solver_set_math_mode": [v, i],
+        "velvet_solver_set_iterate_mode": [v, i],
+        "velvet_solver_iterate_kernel": [v, C.POINTER(i)],
         "velvet_solver_add_cloth": [v, v, i, v, i, v, f, C.POINTER(i)],
         "velvet_solver_add_stretch": [v, i, i, f],
         "velvet_solver_add_attach_slot": [v, v],

@@ -134,6 +134,22 @@ int velvet_solver_set_math_mode(VelvetSolver* s, int mode)
     VT_API_END
 }
 
+int velvet_solver_set_iterate_mode(VelvetSolver* s, int mode)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.setIterateMode(mode);
+    VT_API_END
+}
+
+int velvet_solver_iterate_kernel(VelvetSolver* s, int* kernel)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && kernel, "NULL argument");
+    *kernel = s->impl.iterateKernel();
+    VT_API_END
+}
+
 int velvet_solver_set_tile_size(VelvetSolver* s, int n)
 {
     VT_API_BEGIN

@@ -573,6 +573,277 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     cp_async_wait_all();
 }
 
+// ---------------------------------------------------------------- implicit-grid Jacobi iteration (round 2)
+//
+// ncu on the record-driven kernel above (round 1/2): only a third of its executed instructions are floating-point math; the
+// rest decodes records, computes slot addresses, tests ordinals and keeps a three-stage tile pipeline alive.  For a grid
+// cloth -- the only kind the reference creates, VtClothObjectGPU.hpp L75-132 -- all of that is implied by the vertex
+// coordinates (grid_plan.hpp), so this kernel has no index records at all:
+//   * a tile owns 15 x 15 particles and evaluates the 16 x 16 "bundles" of constraints generated at the vertices
+//     (x0-1 .. x0+14) x (y0-1 .. y0+14): thread (bx, by) holds the four corners c00 c01 c10 c11 of its quad in registers and
+//     evaluates the bundle's four stretch constraints (vertical c00-c01, horizontal c00-c10, diagonal c00-c11, anti-diagonal
+//     c01-c10) and its bending constraint (p0 p1 p2 p3 = c00 c11 c01 c10) -- one trip, every thread the same work, and the
+//     edge vectors are shared: the bend's e = p3 - p2 is minus the anti-diagonal difference (same length, same bits), its
+//     normals are cross products of the stretch differences;
+//   * corrections for the three far corners go to eight slot arrays indexed by THREAD id (static addresses), those for the
+//     thread's own particle c00 stay in registers: particle (x, y) sums, in constraint-id order, the slots of bundles
+//     (x-1,y-1), (x-1,y), (x,y-1) and then its own -- the order of the oracle, bit-identical to the record-driven kernel;
+//   * two barriers per tile; the next tile's positions, rest lengths and rest angles are in flight (cp.async) while the
+//     current one is solved; tile coordinates are arithmetic on the work index.
+// Algorithmic bytes per particle: 16 (position in) + 16 (out) + 16 (rest lengths) + 4 (rest angle) = 52.
+constexpr int GRID_B = GRID_TILE + 1;  // bundles per tile side
+constexpr int GRID_V = GRID_TILE + 2;  // staged vertices per tile side
+// 2 x 17 x 17 positions, 2 x 256 rest-length quadruples, 8 x 256 slots, 2 x 256 rest angles, the cloth table
+constexpr size_t GRID_SMEM_BYTES = sizeof(float4) * (2 * GRID_V * GRID_V + 10 * 256 + 256 / 2) + sizeof(GridCloth) * GRID_MAX_CLOTHS;
+
+__device__ __forceinline__ void cp_async_4(void* smemDst, const void* gmemSrc)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmemSrc));
+}
+
+struct GridStretchOut {
+    vec3 c1, c2;
+    float flag;
+};
+struct GridBendOut {
+    vec3 c0, c1, c2, c3;
+    float flag;
+};
+#if !VT_FAST_MATH
+// rare paths (degenerate or non-finite geometry): the branchy evaluators, out of line
+__device__ __noinline__ GridStretchOut grid_stretch_slow(float4 pa, float4 pb, float rest)
+{
+    GridStretchOut o;
+    o.c1 = o.c2 = V3(0, 0, 0);
+    o.flag = stretch_eval(V3(pa), V3(pb), pa.w, pb.w, rest, o.c1, o.c2) ? 1.0f : 0.0f;
+    return o;
+}
+__device__ __noinline__ GridBendOut grid_bend_slow(float4 p0, float4 p1, float4 p2, float4 p3, float restAngle, float xpbd_bend)
+{
+    GridBendOut o;
+    o.c0 = o.c1 = o.c2 = o.c3 = V3(0, 0, 0);
+    o.flag = bend_eval(V3(p0), V3(p1), V3(p2), V3(p3), p0.w, p1.w, p2.w, p3.w, restAngle, xpbd_bend, o.c0, o.c1, o.c2, o.c3) ? 1.0f : 0.0f;
+    return o;
+}
+#endif
+
+#ifndef VT_GRID_BLOCKS
+#define VT_GRID_BLOCKS 4  // resident CTAs per SM the register budget is sized for
+#endif
+__global__ void __launch_bounds__(256, VT_GRID_BLOCKS)
+iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const GridPlanDev plan,
+                    const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
+                    const unsigned totalWork)
+{
+    constexpr unsigned NT = 256;
+    extern __shared__ float4 s_mem[];  // GRID_SMEM_BYTES, carved below (more than the 48 KB a static allocation may take)
+    float4(*const s_sp)[GRID_V * GRID_V] = reinterpret_cast<float4(*)[GRID_V * GRID_V]>(s_mem);
+    float4(*const s_rest)[NT] = reinterpret_cast<float4(*)[NT]>(s_mem + 2 * GRID_V * GRID_V);
+    float4(*const s_slots)[NT] = reinterpret_cast<float4(*)[NT]>(s_mem + 2 * GRID_V * GRID_V + 2 * NT);
+    float(*const s_angle)[NT] = reinterpret_cast<float(*)[NT]>(s_mem + 2 * GRID_V * GRID_V + 10 * NT);
+    GridCloth* const s_cloth = reinterpret_cast<GridCloth*>(s_mem + 2 * GRID_V * GRID_V + 10 * NT + NT / 2);
+
+    const unsigned tid = threadIdx.x;
+    const int by = (int)(tid & 15u), bx = (int)(tid >> 4);
+    const unsigned stride = gridDim.x;
+    unsigned w = blockIdx.x;
+    if (w >= totalWork) return;
+    if (tid < plan.numCloths) s_cloth[tid] = plan.cloths[tid];
+    const float xpbd_bend = fp->xpbdBend;
+    const float relaxation = fp->P.relaxationFactor;
+    const float lrs = fp->P.longRangeStretchiness;
+    __syncthreads();
+
+    // work item -> first particle of its cloth (instance included), grid side, tile origin
+    auto locate = [&](unsigned item, unsigned& base, int& side, int& x0, int& y0, unsigned& attBase) {
+        unsigned tile = item, in = 0;
+        if (inst.count > 1) {
+            in = item / plan.numTiles;
+            tile = item - in * plan.numTiles;
+        }
+        unsigned c = 0;
+        while (c + 1 < plan.numCloths && tile >= s_cloth[c + 1].firstTile) c++;
+        const GridCloth g = s_cloth[c];
+        const unsigned lt = tile - g.firstTile, tx = lt / g.tilesY;
+        base = in * inst.particles + g.base;
+        attBase = g.base;  // attach CSR, rest lengths and angles cover one instance
+        side = (int)g.side;
+        x0 = (int)tx * GRID_TILE;
+        y0 = (int)(lt - tx * g.tilesY) * GRID_TILE;
+    };
+    // stage the 17 x 17 vertices around the tile, the bundle's rest lengths and rest angle (vertices outside the cloth are skipped)
+    auto issue_tile = [&](unsigned buf, unsigned base, unsigned planBase, int side, int x0, int y0) {
+        const int gx = x0 - 1 + bx, gy = y0 - 1 + by;
+        const bool inX = (unsigned)gx < (unsigned)side, inY = (unsigned)gy < (unsigned)side;
+        const bool inX1 = (unsigned)(gx + 1) < (unsigned)side, inY1 = (unsigned)(gy + 1) < (unsigned)side;
+        const int idx = gx * side + gy;
+        const float4* src = predInAll + base + idx;
+        float4* dst = &s_sp[buf][bx * GRID_V + by];
+        if (inX && inY) {
+            cp_async_16(dst, src);
+            cp_async_16(&s_rest[buf][tid], plan.rest4 + planBase + idx);
+            cp_async_4(&s_angle[buf][tid], plan.restAngle + planBase + idx);
+        }
+        if (by == GRID_B - 1 && inX && inY1) cp_async_16(dst + 1, src + 1);
+        if (bx == GRID_B - 1) {
+            if (inX1 && inY) cp_async_16(dst + GRID_V, src + side);
+            if (by == GRID_B - 1 && inX1 && inY1) cp_async_16(dst + GRID_V + 1, src + side + 1);
+        }
+    };
+
+    unsigned baseCur, attCur;
+    int sideCur, x0Cur, y0Cur;
+    locate(w, baseCur, sideCur, x0Cur, y0Cur, attCur);
+    issue_tile(0, baseCur, attCur, sideCur, x0Cur, y0Cur);
+    cp_async_commit();
+
+    for (unsigned k = 0; w < totalWork; k++, w += stride) {
+        const unsigned buf = k & 1u;
+        const bool hasNext = w + stride < totalWork;
+        unsigned baseNext = 0, attNext = 0;
+        int sideNext = 0, x0Next = 0, y0Next = 0;
+        if (hasNext) {
+            locate(w + stride, baseNext, sideNext, x0Next, y0Next, attNext);
+            issue_tile(buf ^ 1u, baseNext, attNext, sideNext, x0Next, y0Next);
+        }
+        cp_async_commit();
+        cp_async_wait_group<1>();  // this tile has landed; the next one may still be in flight
+        __syncthreads();           // ... for every thread; and every thread is past the sums of the previous tile
+
+        // ---- which constraints of this bundle exist (cloth border, partially filled tiles)
+        const int gx = x0Cur - 1 + bx, gy = y0Cur - 1 + by;
+        const bool inGrid = (unsigned)gx < (unsigned)sideCur && (unsigned)gy < (unsigned)sideCur;
+        const bool vV = inGrid && gy + 1 < sideCur;  // (x,y)-(x,y+1)
+        const bool vH = inGrid && gx + 1 < sideCur;  // (x,y)-(x+1,y)
+        const bool vQ = vV && vH;                    // both diagonals and the bending constraint of the quad
+
+        const float4* sp = &s_sp[buf][bx * GRID_V + by];
+        const float4 c00 = sp[0], c01 = sp[1], c10 = sp[GRID_V], c11 = sp[GRID_V + 1];
+        const float4 rest = s_rest[buf][tid];
+        const float restAngle = s_angle[buf][tid];
+
+        // SolveStretch_Kernel, VtClothSolverGPU.cu L76-101 (four constraints) and SolveBending_Kernel, L128-188 (one)
+        const vec3 dV = V3(c00) - V3(c01), dH = V3(c00) - V3(c10), dD = V3(c00) - V3(c11), dA = V3(c01) - V3(c10);
+        GridStretchOut oV, oH, oD, oA;
+        GridBendOut oB;
+#if VT_FAST_MATH
+        {
+            const bool aV = stretch_eval_flagged(V3(c00), V3(c01), c00.w, c01.w, rest.x, oV.c1, oV.c2) && vV;
+            const bool aH = stretch_eval_flagged(V3(c00), V3(c10), c00.w, c10.w, rest.y, oH.c1, oH.c2) && vH;
+            const bool aD = stretch_eval_flagged(V3(c00), V3(c11), c00.w, c11.w, rest.z, oD.c1, oD.c2) && vQ;
+            const bool aA = stretch_eval_flagged(V3(c01), V3(c10), c01.w, c10.w, rest.w, oA.c1, oA.c2) && vQ;
+            if (!aV) oV.c1 = oV.c2 = V3(0, 0, 0);
+            if (!aH) oH.c1 = oH.c2 = V3(0, 0, 0);
+            if (!aD) oD.c1 = oD.c2 = V3(0, 0, 0);
+            if (!aA) oA.c1 = oA.c2 = V3(0, 0, 0);
+            oV.flag = aV ? 1.0f : 0.0f;
+            oH.flag = aH ? 1.0f : 0.0f;
+            oD.flag = aD ? 1.0f : 0.0f;
+            oA.flag = aA ? 1.0f : 0.0f;
+            oB.c0 = oB.c1 = oB.c2 = oB.c3 = V3(0, 0, 0);
+            const bool aB = vQ && bend_eval_dv(-dA, length(dA), -dV, -dH, V3(c10) - V3(c11), V3(c01) - V3(c11), c00.w, c11.w, c01.w,
+                                               c10.w, restAngle, xpbd_bend, oB.c0, oB.c1, oB.c2, oB.c3);
+            if (!aB) oB.c0 = oB.c1 = oB.c2 = oB.c3 = V3(0, 0, 0);
+            oB.flag = aB ? 1.0f : 0.0f;
+        }
+#else
+        {
+            bool okV = true, okH = true, okD = true, okLenA = true;
+            const StretchHalf hV = stretch_begin_len(dV, vt_sqrt_u(dot(dV, dV), okV), c00.w, c01.w, rest.x);
+            const StretchHalf hH = stretch_begin_len(dH, vt_sqrt_u(dot(dH, dH), okH), c00.w, c10.w, rest.y);
+            const StretchHalf hD = stretch_begin_len(dD, vt_sqrt_u(dot(dD, dD), okD), c00.w, c11.w, rest.z);
+            const StretchHalf hA = stretch_begin_len(dA, vt_sqrt_u(dot(dA, dA), okLenA), c01.w, c10.w, rest.w);
+            bool okA = okLenA, okB = okLenA;
+            const bool aV = vV && hV.active, aH = vH && hH.active, aD = vQ && hD.active, aA = vQ && hA.active;
+            oV.c1 = oV.c2 = oH.c1 = oH.c2 = oD.c1 = oD.c2 = oA.c1 = oA.c2 = V3(0, 0, 0);
+            if (aV || aH || aD || aA) {  // a freely falling, undeformed cloth keeps every distance at rest: no divisions then
+                stretch_finish_u(hV, c00.w, c01.w, rest.x, oV.c1, oV.c2, okV);
+                stretch_finish_u(hH, c00.w, c10.w, rest.y, oH.c1, oH.c2, okH);
+                stretch_finish_u(hD, c00.w, c11.w, rest.z, oD.c1, oD.c2, okD);
+                stretch_finish_u(hA, c01.w, c10.w, rest.w, oA.c1, oA.c2, okA);
+                if (!aV) oV.c1 = oV.c2 = V3(0, 0, 0);
+                if (!aH) oH.c1 = oH.c2 = V3(0, 0, 0);
+                if (!aD) oD.c1 = oD.c2 = V3(0, 0, 0);
+                if (!aA) oA.c1 = oA.c2 = V3(0, 0, 0);
+            }
+            oV.flag = aV ? 1.0f : 0.0f;
+            oH.flag = aH ? 1.0f : 0.0f;
+            oD.flag = aD ? 1.0f : 0.0f;
+            oA.flag = aA ? 1.0f : 0.0f;
+            if (vV && !okV) oV = grid_stretch_slow(c00, c01, rest.x);
+            if (vH && !okH) oH = grid_stretch_slow(c00, c10, rest.y);
+            if (vQ && !okD) oD = grid_stretch_slow(c00, c11, rest.z);
+            if (vQ && !okA) oA = grid_stretch_slow(c01, c10, rest.w);
+
+            // p0 p1 p2 p3 = c00 c11 c01 c10: e = p3 - p2 = -dA, p2 - p0 = -dV, p3 - p0 = -dH
+            const bool aB = bend_eval_dv_u(-dA, hA.distance, -dV, -dH, V3(c10) - V3(c11), V3(c01) - V3(c11), c00.w, c11.w, c01.w,
+                                           c10.w, restAngle, xpbd_bend, oB.c0, oB.c1, oB.c2, oB.c3, okB) && vQ;
+            if (!aB) oB.c0 = oB.c1 = oB.c2 = oB.c3 = V3(0, 0, 0);
+            oB.flag = aB ? 1.0f : 0.0f;
+            if (vQ && !okB) oB = grid_bend_slow(c00, c11, c01, c10, restAngle, xpbd_bend);
+        }
+#endif
+        // far corners: slots by thread id; own particle: registers
+        s_slots[0][tid] = F4(oD.c2, oD.flag);  // diagonal      -> c11
+        s_slots[1][tid] = F4(oH.c2, oH.flag);  // horizontal    -> c10
+        s_slots[2][tid] = F4(oA.c2, oA.flag);  // anti-diagonal -> c10
+        s_slots[3][tid] = F4(oV.c2, oV.flag);  // vertical      -> c01
+        s_slots[4][tid] = F4(oA.c1, oA.flag);  // anti-diagonal -> c01
+        s_slots[5][tid] = F4(oB.c1, oB.flag);  // bending p1    -> c11
+        s_slots[6][tid] = F4(oB.c3, oB.flag);  // bending p3    -> c10
+        s_slots[7][tid] = F4(oB.c2, oB.flag);  // bending p2    -> c01
+        __syncthreads();
+
+        // ---- particle (gx, gy): stretch constraints generated at (gx-1,gy-1), (gx-1,gy), (gx,gy-1), (gx,gy) in that (= id)
+        // order, attachments, bending constraints of the same four quads; ApplyDeltas_Kernel, L257-263
+        if (bx > 0 && by > 0 && inGrid) {
+            vec3 delta = V3(0, 0, 0);
+            float count = 0;
+            auto add = [&](const float4 v) {
+                delta.x += v.x;
+                delta.y += v.y;
+                delta.z += v.z;
+                count += v.w;
+            };
+            add(s_slots[0][tid - GRID_B - 1]);
+            add(s_slots[1][tid - GRID_B]);
+            add(s_slots[2][tid - GRID_B]);
+            add(s_slots[3][tid - 1]);
+            add(s_slots[4][tid - 1]);
+            add(F4(oV.c1, oV.flag));
+            add(F4(oH.c1, oH.flag));
+            add(F4(oD.c1, oD.flag));
+            const unsigned local = (unsigned)(gx * sideCur + gy);
+            if (plan.hasAttach) {  // SolveAttachment_Kernel, L218-234
+                const float* attachSlotPositions = attachSlotsAll + (size_t)((baseCur - attCur) / inst.particles) * inst.slots * 3;
+                const unsigned a1 = __ldg(plan.attOff + attCur + local + 1);
+                for (unsigned a = __ldg(plan.attOff + attCur + local); a < a1; a++) {
+                    const uint2 r = __ldg(plan.attachRec + a);
+                    vec3 corr;
+                    if (attach_eval(V3(c00), c00.w, load3(attachSlotPositions, r.x), __uint_as_float(r.y), lrs, corr)) {
+                        delta += corr;
+                        count += 1.0f;
+                    }
+                }
+            }
+            add(s_slots[5][tid - GRID_B - 1]);
+            add(s_slots[6][tid - GRID_B]);
+            add(s_slots[7][tid - 1]);
+            add(F4(oB.c0, oB.flag));
+            vec3 p = V3(c00);
+            if (count > 0) p += delta / count * relaxation;
+            predOutAll[baseCur + local] = F4(p, c00.w);
+        }
+        baseCur = baseNext;
+        attCur = attNext;
+        sideCur = sideNext;
+        x0Cur = x0Next;
+        y0Cur = y0Next;
+    }
+    cp_async_wait_all();
+}
+
 __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restrict__ predIn, float4* __restrict__ pos4,
                                                          float4* __restrict__ vel4, float4* __restrict__ predNext,
                                                          int last, float* __restrict__ positionsOut,
@@ -717,6 +988,26 @@ unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned c
     VT_ITERATE_VARIANTS(VT_CONFIG)
 #undef VT_CONFIG
     if (perSm < 1) throw Error(VELVET_ERR_UNSUPPORTED, "the Jacobi tile kernel does not fit on an SM");
+    return (unsigned)(sms * perSm);
+}
+
+void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst)
+{
+    const unsigned total = plan.numTiles * inst.count;
+    if (!total) return;
+    const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
+    iterate_grid_kernel<<<grid, 256, GRID_SMEM_BYTES, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total);
+}
+
+unsigned configure_iterate_grid_kernel()
+{
+    int dev = 0, sms = 0, perSm = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    VT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VT_CUDA(cudaFuncSetAttribute(iterate_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM_BYTES));
+    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_grid_kernel, 256, GRID_SMEM_BYTES));
+    if (perSm < 1) throw Error(VELVET_ERR_UNSUPPORTED, "the grid Jacobi kernel does not fit on an SM");
     return (unsigned)(sms * perSm);
 }
 

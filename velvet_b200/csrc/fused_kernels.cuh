@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include "grid_plan.hpp"
 #include "tile_plan.hpp"
 #include "vt_math.cuh"
 
@@ -31,6 +32,17 @@ struct TilePlanDev {
     unsigned threads;     // slot-row width: the power of two >= tileSize
     unsigned ctaThreads;  // CTA size: `threads`, or 1.25x that when a tile has more bending constraints than particles
     unsigned hasAttach;
+};
+
+// Grid cloths recognised among the registered constraints (grid_plan.hpp): everything iterate_grid_kernel reads.
+struct GridPlanDev {
+    const GridCloth* cloths;
+    const float4* rest4;      // per particle: rest lengths of the stretch constraints generated at that vertex
+    const float* restAngle;   // per particle: rest angle of the quad's bending constraint
+    const unsigned* attOff;   // attach CSR by particle
+    const uint2* attachRec;   // {slot id, distance bits}
+    unsigned numCloths, numTiles, hasAttach;
+    unsigned residentCtas;
 };
 
 constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)
@@ -79,6 +91,10 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
+// The same iteration for grid cloths without index records (iterate_grid_kernel): bit-identical to launch_iterate.
+void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
+unsigned configure_iterate_grid_kernel();  // returns resident CTAs on the device
 unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
 // Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
@@ -136,6 +152,10 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
+// The same iteration for grid cloths without index records (iterate_grid_kernel): bit-identical to launch_iterate.
+void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
+unsigned configure_iterate_grid_kernel();  // returns resident CTAs on the device
 unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
 // Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
@@ -156,6 +176,7 @@ struct FusedOps {
     decltype(&exact_math::launch_begin_frame) begin_frame;
     decltype(&exact_math::launch_collide) collide;
     decltype(&exact_math::launch_iterate) iterate;
+    decltype(&exact_math::launch_iterate_grid) iterate_grid;
     decltype(&exact_math::iterate_smem_bytes) iterate_smem_bytes;
     decltype(&exact_math::configure_iterate_kernel) configure_iterate_kernel;
     decltype(&exact_math::launch_end_substep) end_substep;
@@ -165,10 +186,10 @@ inline FusedOps fused_ops(bool fastMath)
 {
     if (fastMath)
         return FusedOps{&fast_math::launch_prepare_inputs, &fast_math::launch_begin_frame, &fast_math::launch_collide,
-                        &fast_math::launch_iterate, &fast_math::iterate_smem_bytes, &fast_math::configure_iterate_kernel,
+                        &fast_math::launch_iterate, &fast_math::launch_iterate_grid, &fast_math::iterate_smem_bytes, &fast_math::configure_iterate_kernel,
                         &fast_math::launch_end_substep, &fast_math::launch_normals};
     return FusedOps{&exact_math::launch_prepare_inputs, &exact_math::launch_begin_frame, &exact_math::launch_collide,
-                    &exact_math::launch_iterate, &exact_math::iterate_smem_bytes, &exact_math::configure_iterate_kernel,
+                    &exact_math::launch_iterate, &exact_math::launch_iterate_grid, &exact_math::iterate_smem_bytes, &exact_math::configure_iterate_kernel,
                     &exact_math::launch_end_substep, &exact_math::launch_normals};
 }
 

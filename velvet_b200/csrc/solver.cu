@@ -278,6 +278,21 @@ void VtClothSolverGPU::setMathMode(int mode)
     m_mathMode = mode;  // the graph key includes the mode: the next Simulate re-captures, nothing else is rebuilt
 }
 
+void VtClothSolverGPU::setIterateMode(int mode)
+{
+    if (mode != VELVET_ITERATE_AUTO && mode != VELVET_ITERATE_TILES) throw Error(VELVET_ERR_INVALID_ARGUMENT, "unknown iterate mode");
+    if (mode == m_iterateMode) return;
+    m_iterateMode = mode;
+    invalidate();
+}
+
+int VtClothSolverGPU::iterateKernel()
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    ensureFusedResources();
+    return m_gridUsable ? VELVET_ITERATE_GRID : VELVET_ITERATE_TILES;
+}
+
 void VtClothSolverGPU::setTileSize(int particlesPerTile)
 {
     if (particlesPerTile != 0 && (particlesPerTile < 32 || particlesPerTile > VT_MAX_TILE || particlesPerTile % 32))
@@ -296,6 +311,7 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
     Synchronize();
     const int prevNumParticles = (int)simParams.numParticles;
     const int newParticles = numVertices;
+    m_clothRanges.push_back(ClothRange{(uint)prevNumParticles, (uint)newParticles});
 
     // global parameters, hpp L122-125
     simParams.numParticles += (uint)newParticles;
@@ -384,6 +400,7 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
                                                      simParams.maxNumNeighbors);
     m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
     m_instancing = Instancing{(uint)numInstances, (uint)n, (uint)numAttached};
+    m_clothRanges.assign(1, ClothRange{0u, (uint)n});  // one topology, shared by every instance
     m_instanced = true;
     invalidate();
 }
@@ -635,6 +652,37 @@ void VtClothSolverGPU::ensureFusedResources()
     m_planDev.residentCtas = std::min(exact_math::configure_iterate_kernel(smem, m_planDev.threads, m_planDev.ctaThreads),
                                       fast_math::configure_iterate_kernel(smem, m_planDev.threads, m_planDev.ctaThreads));
 
+    // grid cloths carrying exactly the reference's constraint pattern get the implicit-grid kernel (grid_plan.hpp)
+    m_gridUsable = false;
+    m_gridPlan = GridPlan{};
+    {
+        int mode = m_iterateMode;
+        if (const char* e = getenv("VELVET_ITERATE"))
+            if (std::string(e) == "tiles") mode = VELVET_ITERATE_TILES;
+        if (mode == VELVET_ITERATE_AUTO) {
+            m_gridPlan = build_grid_plan(planN, m_clothRanges, stretchIndices.data(), stretchLengths.data(), stretchLengths.size(),
+                                         bendIndices.data(), bendAngles.data(), bendAngles.size(), attachParticleIDs.data(),
+                                         attachSlotIDs.data(), attachDistances.data(), attachParticleIDs.size());
+            if (m_gridPlan.valid) {
+                m_gCloths.upload(m_gridPlan.cloths, st);
+                m_gRest4.upload(reinterpret_cast<const float4*>(m_gridPlan.rest4.data()), planN, st);
+                m_gAngle.upload(m_gridPlan.restAngle, st);
+                m_gAttOff.upload(m_gridPlan.attOff, st);
+                m_gAttachRec.upload(reinterpret_cast<const uint2*>(m_gridPlan.attachRec.data()), m_gridPlan.attachRec.size() / 2, st);
+                m_gridDev.cloths = m_gCloths;
+                m_gridDev.rest4 = m_gRest4;
+                m_gridDev.restAngle = m_gAngle;
+                m_gridDev.attOff = m_gAttOff;
+                m_gridDev.attachRec = m_gAttachRec;
+                m_gridDev.numCloths = (uint)m_gridPlan.cloths.size();
+                m_gridDev.numTiles = m_gridPlan.numTiles;
+                m_gridDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
+                m_gridDev.residentCtas = std::min(exact_math::configure_iterate_grid_kernel(), fast_math::configure_iterate_grid_kernel());
+                m_gridUsable = true;
+            }
+        }
+    }
+
     // vertex -> incident triangles, ascending triangle id
     {
         const size_t T = indices.size() / 3;
@@ -704,6 +752,7 @@ unsigned long long VtClothSolverGPU::topologyKey() const
     mix(attachSlotPositions.size());
     mix((unsigned long long)(uintptr_t)m_spatialHash.get());
     mix((unsigned)m_mathMode);
+    mix((unsigned)m_iterateMode);
     return h;
 }
 
@@ -772,7 +821,10 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
 
         STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
         for (int iteration = 0; iteration < P.numIterations; iteration++) {
-            ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp, m_instancing);
+            if (m_gridUsable)
+                ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing);
+            else
+                ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp, m_instancing);
             launches++;
             std::swap(cur, other);
         }

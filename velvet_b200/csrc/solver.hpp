@@ -12,6 +12,7 @@
 
 #include "dd_peer.cuh"
 #include "fused_kernels.cuh"
+#include "grid_plan.hpp"
 #include "radix_sort.cuh"
 #include "seam.hpp"
 #include "tile_plan.hpp"
@@ -172,6 +173,12 @@ public:
     int pipeline() const { return m_pipeline; }
     void setTileSize(int particlesPerTile);
     void setMathMode(int mode);  // VELVET_MATH_EXACT (default) or VELVET_MATH_FAST
+    // Jacobi kernel selection: VELVET_ITERATE_AUTO (default) runs the implicit-grid kernel when every registered cloth is a
+    // grid with the reference's constraint pattern (grid_plan.hpp) and the record-driven tile kernel otherwise;
+    // VELVET_ITERATE_TILES always runs the tile kernel.  Both give bit-identical results.
+    void setIterateMode(int mode);
+    int iterateKernel();  // the kernel the next frame will run: VELVET_ITERATE_TILES or VELVET_ITERATE_GRID (builds the plans if needed)
+    const GridPlan& gridPlan() const { return m_gridPlan; }
     int mathMode() const { return m_mathMode; }
     cudaStream_t stream() const { return m_stream; }
     int device() const { return m_device; }
@@ -197,6 +204,8 @@ private:
     int m_pipeline = 0;
     int m_tileSize = 0;
     int m_mathMode = VELVET_MATH_EXACT;
+    int m_iterateMode = VELVET_ITERATE_AUTO;
+    std::vector<ClothRange> m_clothRanges;  // particle range of every AddCloth call
     Instancing m_instancing{1, 0, 0};
     // domain decomposition state
     ExchangePlan m_dd;
@@ -247,6 +256,15 @@ private:
     DeviceBuffer<uint16_t> m_dCnt16;
     DeviceBuffer<uint2> m_dStretchRec, m_dAttachRec;
     DeviceBuffer<uint4> m_dBendRec;
+    // implicit-grid plan (valid when every cloth is a grid with the reference's constraint pattern)
+    GridPlan m_gridPlan;
+    GridPlanDev m_gridDev{};
+    bool m_gridUsable = false;
+    DeviceBuffer<GridCloth> m_gCloths;
+    DeviceBuffer<float4> m_gRest4;
+    DeviceBuffer<float> m_gAngle;
+    DeviceBuffer<uint> m_gAttOff;
+    DeviceBuffer<uint2> m_gAttachRec;
 };
 
 // Constraint generation of the reference's cloth component (VtClothObjectGPU.hpp L43-148) for grid meshes

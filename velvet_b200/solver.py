@@ -15,7 +15,7 @@ import math
 import numpy as np
 
 from . import _capi
-from ._capi import (BUFFER_IDS, COLLIDER_CUBE, COLLIDER_PLANE, COLLIDER_SPHERE, MATH_EXACT, MATH_FAST, PIPELINE_FUSED, PIPELINE_SEAM,
+from ._capi import (BUFFER_IDS, COLLIDER_CUBE, COLLIDER_PLANE, COLLIDER_SPHERE, ITERATE_AUTO, ITERATE_GRID, ITERATE_TILES, MATH_EXACT, MATH_FAST, PIPELINE_FUSED, PIPELINE_SEAM,
                     VtHashParams, VtSDFCollider, VtSimParams, check)
 
 _BUF_DTYPE = {
@@ -94,6 +94,17 @@ class VtClothSolverGPU:
 
     def SetMathMode(self, mode: int):
         check(self._L.velvet_solver_set_math_mode(self._h, mode))
+
+    def SetIterateMode(self, mode: int):
+        """ITERATE_AUTO (default: implicit-grid Jacobi kernel for grid cloths) or ITERATE_TILES (record-driven tile kernel)."""
+        check(self._L.velvet_solver_set_iterate_mode(self._h, mode))
+
+    @property
+    def iterateKernel(self) -> int:
+        """ITERATE_TILES or ITERATE_GRID: the Jacobi kernel the next frame runs."""
+        k = C.c_int()
+        check(self._L.velvet_solver_iterate_kernel(self._h, C.byref(k)))
+        return k.value
 
     def close(self):
         if getattr(self, "_h", None):
