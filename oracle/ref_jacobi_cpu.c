@@ -5,7 +5,8 @@
  *
  * Sequential fp32 restatement of the kernels of VtClothSolverGPU.cu / SpatialHashGPU.cu and
  * of the host orchestration in VtClothSolverGPU.hpp / SpatialHashGPU.hpp /
- * VtClothObjectGPU.hpp.  Build: gcc -O2 -ffp-contract=off -fno-fast-math.
+ * VtClothObjectGPU.hpp.  Build: gcc -O2 -ffp-contract=off -fno-fast-math (twice: portable, and with -mfma so that
+ * fmaf() is one instruction; both give the same bits).
  */
 #include "ref_jacobi_cpu.h"
 
@@ -36,12 +37,29 @@ static inline v3 mulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 muls(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
 static inline v3 divs(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
 static inline v3 neg(v3 a) { return V(-a.x, -a.y, -a.z); }
-static inline float dot3(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+/* The reference's nvcc build contracts a*b+c into FMAs wherever its compiler chooses, which cannot be reproduced off the
+ * device.  The oracle and the product therefore WRITE the contractions: the device-side dot and cross products, the weighted
+ * sums of the bending constraint and the acos polynomials are explicit fmaf() calls, identical on both sides
+ * (velvet_b200/csrc/vt_math.cuh); everything else is compiled without contraction (-ffp-contract=off / -fmad=false).
+ * The spatial hash's candidate tests and the host-side constraint generation (MSVC host code in the reference) use the
+ * plain forms. */
+static inline float dot3(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+static inline float dot3_plain(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 static inline float len3(v3 a) { return sqrtf(dot3(a, a)); }
+static inline float len3_plain(v3 a) { return sqrtf(dot3_plain(a, a)); }
 static inline v3 normalize3(v3 a) { return muls(a, 1.0f / sqrtf(dot3(a, a))); }
 static inline v3 cross3(v3 a, v3 b)
 {
-    return V(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+    return V(fmaf(a.y, b.z, -(b.y * a.z)), fmaf(a.z, b.x, -(b.z * a.x)), fmaf(a.x, b.y, -(b.x * a.y)));
+}
+/* s*a + t*b per component; weighted sum of four scalars (contracted left to right like the dot product) */
+static inline v3 lincomb3(float s, v3 a, float t, v3 b)
+{
+    return V(fmaf(t, b.x, s * a.x), fmaf(t, b.y, s * a.y), fmaf(t, b.z, s * a.z));
+}
+static inline float wsum4(float w0, float a0, float w1, float a1, float w2, float a2, float w3, float a3)
+{
+    return fmaf(w3, a3, fmaf(w2, a2, fmaf(w1, a1, w0 * a0)));
 }
 static inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
@@ -140,13 +158,20 @@ static inline float i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
 /* acos(float) of VtClothSolverGPU.cu L163.  The reference calls CUDA's acosf (<= 2 ulp, unspecified last bit);
  * the oracle and the product both use the published fdlibm e_acosf.c algorithm (< 1 ulp, only + - * / sqrt) so
  * that the bending constraint is bit-reproducible between CPU and GPU. */
+static inline float acos_p(float z)
+{ /* Horner with one rounding per step */
+    const float pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f,
+                pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f;
+    return z * fmaf(z, fmaf(z, fmaf(z, fmaf(z, fmaf(z, pS5, pS4), pS3), pS2), pS1), pS0);
+}
+static inline float acos_q(float z)
+{
+    const float qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f, qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+    return fmaf(z, fmaf(z, fmaf(z, fmaf(z, qS4, qS3), qS2), qS1), 1.0f);
+}
 float o1_acosf(float x)
 {
-    const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f,
-                pio2_lo = 7.5497894159e-08f, pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f,
-                pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f, pS4 = 7.9153501429e-04f,
-                pS5 = 3.4793309169e-05f, qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f,
-                qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+    const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f;
     const int hx = f2i(x);
     const int ix = hx & 0x7fffffff;
     if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo;
@@ -154,28 +179,28 @@ float o1_acosf(float x)
     if (ix < 0x3f000000) {
         if (ix <= 0x23000000) return pio2_hi + pio2_lo;
         const float z = x * x;
-        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
-        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float p = acos_p(z);
+        const float q = acos_q(z);
         const float r = p / q;
-        return pio2_hi - (x - (pio2_lo - x * r));
+        return pio2_hi - (x - fmaf(-x, r, pio2_lo));
     }
     if (hx < 0) {
         const float z = (one + x) * 0.5f;
-        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
-        const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float p = acos_p(z);
+        const float q = acos_q(z);
         const float s = sqrtf(z);
         const float r = p / q;
-        const float w = r * s - pio2_lo;
+        const float w = fmaf(r, s, -pio2_lo);
         return pi - 2.0f * (s + w);
     }
     const float z = (one - x) * 0.5f;
     const float s = sqrtf(z);
     const float df = i2f(f2i(s) & (int)0xfffff000);
-    const float c = (z - df * df) / (s + df);
-    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
-    const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float c = fmaf(-df, df, z) / (s + df);
+    const float p = acos_p(z);
+    const float q = acos_q(z);
     const float r = p / q;
-    const float w = r * s + c;
+    const float w = fmaf(r, s, c);
     return 2.0f * (df + w);
 }
 
@@ -201,15 +226,15 @@ void o1_solve_bending(const O1SimParams* P, float* predicted, float* deltas, int
 
         v3 d0 = muls(n1, elen);
         v3 d1 = muls(n2, elen);
-        v3 d2 = add(muls(n1, dot3(sub(p0, p3), e) * invElen), muls(n2, dot3(sub(p1, p3), e) * invElen));
-        v3 d3 = add(muls(n1, dot3(sub(p2, p0), e) * invElen), muls(n2, dot3(sub(p2, p1), e) * invElen));
+        v3 d2 = lincomb3(dot3(sub(p0, p3), e) * invElen, n1, dot3(sub(p1, p3), e) * invElen, n2);
+        v3 d3 = lincomb3(dot3(sub(p2, p0), e) * invElen, n1, dot3(sub(p2, p1), e) * invElen, n2);
 
         n1 = normalize3(n1);
         n2 = normalize3(n2);
         float d = clampf(dot3(n1, n2), -1.0f, 1.0f);
         float phi = o1_acosf(d);
 
-        float lambda = w0 * dot3(d0, d0) + w1 * dot3(d1, d1) + w2 * dot3(d2, d2) + w3 * dot3(d3, d3);
+        float lambda = wsum4(w0, dot3(d0, d0), w1, dot3(d1, d1), w2, dot3(d2, d2), w3, dot3(d3, d3));
         if (lambda < O1_EPSILON) continue;
 
         float xpbd_bend = P->bendCompliance / dt / dt;
@@ -469,7 +494,7 @@ static void stable_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t n, int bi
     free(a); free(b);
 }
 
-static inline float length2_3(v3 v) { return dot3(v, v); } /* Common.cuh L48-51 */
+static inline float length2_3(v3 v) { return dot3_plain(v, v); } /* Common.cuh L48-51 */
 
 /* SpatialHashGPU.cu L159-196 (H1 L34-42, H2 L133-157, H3 L44-77 + memset L185, H4 L79-130) */
 void o1_hash_objects(uint32_t* particleHash, uint32_t* particleIndex, uint32_t* cellStart,
@@ -828,14 +853,14 @@ int o1_cloth_object_start(O1Solver* s, int resolution, const float* vertices, co
 {
     const int S = resolution + 1;
     const int nv = S * S, ni = 6 * resolution * resolution;
-    float diameter = len3(sub(ld3(vertices, 0), ld3(vertices, 1))) * s->P.particleDiameterScalar;
+    float diameter = len3_plain(sub(ld3(vertices, 0), ld3(vertices, 1))) * s->P.particleDiameterScalar;
     int off = o1_solver_add_cloth(s, vertices, nv, indices, ni, model16, diameter);
 
     float* pos = (float*)malloc(sizeof(float) * 3 * (size_t)nv); /* ApplyTransform L67-73 */
     for (int i = 0; i < nv; i++) st3(pos, (size_t)i, mat4_mul_point(model16, ld3(vertices, (size_t)i), 1.0f));
 
 #define VAT(x, y) ((x) * S + (y))
-#define DIST(a, b) len3(sub(ld3(pos, (size_t)(a)), ld3(pos, (size_t)(b))))
+#define DIST(a, b) len3_plain(sub(ld3(pos, (size_t)(a)), ld3(pos, (size_t)(b))))
     for (int x = 0; x < S; x++) /* GenerateStretch L75-116 */
         for (int y = 0; y < S; y++) {
             int a, b;
@@ -851,7 +876,7 @@ int o1_cloth_object_start(O1Solver* s, int resolution, const float* vertices, co
         float sp[3] = {slotPos.x, slotPos.y, slotPos.z};
         o1_solver_add_attach_slot(s, sp);
         for (int i = 0; i < nv; i++)
-            o1_solver_add_attach(s, off + i, slot, len3(sub(slotPos, ld3(pos, (size_t)i))));
+            o1_solver_add_attach(s, off + i, slot, len3_plain(sub(slotPos, ld3(pos, (size_t)i))));
     }
     for (int i = 0; i < ni; i += 6) /* GenerateBending L118-132 */
         o1_solver_add_bend(s, (uint32_t)off + indices[i], (uint32_t)off + indices[i + 5],

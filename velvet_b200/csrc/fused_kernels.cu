@@ -593,8 +593,14 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
 // Algorithmic bytes per particle: 16 (position in) + 16 (out) + 16 (rest lengths) + 4 (rest angle) = 52.
 constexpr int GRID_B = GRID_TILE + 1;  // bundles per tile side
 constexpr int GRID_V = GRID_TILE + 2;  // staged vertices per tile side
-// 2 x 17 x 17 positions, 2 x 256 rest-length quadruples, 8 x 256 slots, 2 x 256 rest angles, the cloth table
-constexpr size_t GRID_SMEM_BYTES = sizeof(float4) * (2 * GRID_V * GRID_V + 10 * 256 + 256 / 2) + sizeof(GridCloth) * GRID_MAX_CLOTHS;
+struct GridTileCoord {
+    unsigned base, planBase, instance;  // first particle of the tile's cloth in the state arrays / in the plan arrays; instance
+    int side, x0, y0;                   // vertices per cloth side; first owned vertex of the tile
+    unsigned pad[2];
+};
+// 2 x 17 x 17 positions, 2 x 256 rest-length quadruples, 8 x 256 slots, 2 x 256 rest angles, three tile coordinates, the cloth table
+constexpr size_t GRID_SMEM_BYTES = sizeof(float4) * (2 * GRID_V * GRID_V + 10 * 256 + 256 / 2) + 3 * sizeof(GridTileCoord) +
+                                   sizeof(GridCloth) * GRID_MAX_CLOTHS;
 
 __device__ __forceinline__ void cp_async_4(void* smemDst, const void* gmemSrc)
 {
@@ -629,7 +635,7 @@ __device__ __noinline__ GridBendOut grid_bend_slow(float4 p0, float4 p1, float4 
 #endif
 
 #ifndef VT_GRID_BLOCKS
-#define VT_GRID_BLOCKS 4  // resident CTAs per SM the register budget is sized for
+#define VT_GRID_BLOCKS 3  // resident CTAs per SM the register budget is sized for (80 registers; at 4 x 64 the kernel spills: 41.0 vs 39.2 us)
 #endif
 __global__ void __launch_bounds__(256, VT_GRID_BLOCKS)
 iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const GridPlanDev plan,
@@ -642,7 +648,8 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     float4(*const s_rest)[NT] = reinterpret_cast<float4(*)[NT]>(s_mem + 2 * GRID_V * GRID_V);
     float4(*const s_slots)[NT] = reinterpret_cast<float4(*)[NT]>(s_mem + 2 * GRID_V * GRID_V + 2 * NT);
     float(*const s_angle)[NT] = reinterpret_cast<float(*)[NT]>(s_mem + 2 * GRID_V * GRID_V + 10 * NT);
-    GridCloth* const s_cloth = reinterpret_cast<GridCloth*>(s_mem + 2 * GRID_V * GRID_V + 10 * NT + NT / 2);
+    GridTileCoord* const s_tile = reinterpret_cast<GridTileCoord*>(s_mem + 2 * GRID_V * GRID_V + 10 * NT + NT / 2);  // ring of three
+    GridCloth* const s_cloth = reinterpret_cast<GridCloth*>(s_tile + 3);
 
     const unsigned tid = threadIdx.x;
     const int by = (int)(tid & 15u), bx = (int)(tid >> 4);
@@ -650,13 +657,16 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     unsigned w = blockIdx.x;
     if (w >= totalWork) return;
     if (tid < plan.numCloths) s_cloth[tid] = plan.cloths[tid];
+    // vertices outside the cloth are never staged: whatever their entries hold must at least be finite
+    for (unsigned i = tid; i < 2 * GRID_V * GRID_V + 2 * NT; i += NT) s_mem[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const float xpbd_bend = fp->xpbdBend;
     const float relaxation = fp->P.relaxationFactor;
     const float lrs = fp->P.longRangeStretchiness;
     __syncthreads();
 
-    // work item -> first particle of its cloth (instance included), grid side, tile origin
-    auto locate = [&](unsigned item, unsigned& base, int& side, int& x0, int& y0, unsigned& attBase) {
+    // work item -> first particle of its cloth (instance included), grid side, tile origin.  One thread does this (an integer
+    // division and a table walk) two tiles ahead and leaves the result in shared memory for the others.
+    auto locate = [&](unsigned item) {
         unsigned tile = item, in = 0;
         if (inst.count > 1) {
             in = item / plan.numTiles;
@@ -666,50 +676,61 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         while (c + 1 < plan.numCloths && tile >= s_cloth[c + 1].firstTile) c++;
         const GridCloth g = s_cloth[c];
         const unsigned lt = tile - g.firstTile, tx = lt / g.tilesY;
-        base = in * inst.particles + g.base;
-        attBase = g.base;  // attach CSR, rest lengths and angles cover one instance
-        side = (int)g.side;
-        x0 = (int)tx * GRID_TILE;
-        y0 = (int)(lt - tx * g.tilesY) * GRID_TILE;
+        GridTileCoord t;
+        t.base = in * inst.particles + g.base;
+        t.planBase = g.base;  // attach CSR, rest lengths and angles cover one instance
+        t.instance = in;
+        t.side = (int)g.side;
+        t.x0 = (int)tx * GRID_TILE;
+        t.y0 = (int)(lt - tx * g.tilesY) * GRID_TILE;
+        return t;
     };
     // stage the 17 x 17 vertices around the tile, the bundle's rest lengths and rest angle (vertices outside the cloth are skipped)
-    auto issue_tile = [&](unsigned buf, unsigned base, unsigned planBase, int side, int x0, int y0) {
-        const int gx = x0 - 1 + bx, gy = y0 - 1 + by;
-        const bool inX = (unsigned)gx < (unsigned)side, inY = (unsigned)gy < (unsigned)side;
-        const bool inX1 = (unsigned)(gx + 1) < (unsigned)side, inY1 = (unsigned)(gy + 1) < (unsigned)side;
-        const int idx = gx * side + gy;
-        const float4* src = predInAll + base + idx;
-        float4* dst = &s_sp[buf][bx * GRID_V + by];
+    const unsigned spAddr = (unsigned)__cvta_generic_to_shared(&s_sp[0][bx * GRID_V + by]);
+    const unsigned restAddr = (unsigned)__cvta_generic_to_shared(&s_rest[0][tid]);
+    const unsigned angleAddr = (unsigned)__cvta_generic_to_shared(&s_angle[0][tid]);
+    constexpr unsigned SP_BYTES = GRID_V * GRID_V * 16, V16 = GRID_V * 16;
+    auto cp16 = [](unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
+    auto cp4 = [](unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src)); };
+    auto issue_tile = [&](unsigned buf, const GridTileCoord& t) {
+        const int gx = t.x0 - 1 + bx, gy = t.y0 - 1 + by;
+        const bool inX = (unsigned)gx < (unsigned)t.side, inY = (unsigned)gy < (unsigned)t.side;
+        const bool inX1 = (unsigned)(gx + 1) < (unsigned)t.side, inY1 = (unsigned)(gy + 1) < (unsigned)t.side;
+        const int idx = gx * t.side + gy;
+        const float4* src = predInAll + t.base + idx;
+        const unsigned dst = spAddr + buf * SP_BYTES;
         if (inX && inY) {
-            cp_async_16(dst, src);
-            cp_async_16(&s_rest[buf][tid], plan.rest4 + planBase + idx);
-            cp_async_4(&s_angle[buf][tid], plan.restAngle + planBase + idx);
+            cp16(dst, src);
+            cp16(restAddr + buf * (NT * 16), plan.rest4 + t.planBase + idx);
+            if (plan.restAngle) cp4(angleAddr + buf * (NT * 4), plan.restAngle + t.planBase + idx);
         }
-        if (by == GRID_B - 1 && inX && inY1) cp_async_16(dst + 1, src + 1);
+        if (by == GRID_B - 1 && inX && inY1) cp16(dst + 16, src + 1);
         if (bx == GRID_B - 1) {
-            if (inX1 && inY) cp_async_16(dst + GRID_V, src + side);
-            if (by == GRID_B - 1 && inX1 && inY1) cp_async_16(dst + GRID_V + 1, src + side + 1);
+            if (inX1 && inY) cp16(dst + V16, src + t.side);
+            if (by == GRID_B - 1 && inX1 && inY1) cp16(dst + V16 + 16, src + t.side + 1);
         }
     };
 
-    unsigned baseCur, attCur;
-    int sideCur, x0Cur, y0Cur;
-    locate(w, baseCur, sideCur, x0Cur, y0Cur, attCur);
-    issue_tile(0, baseCur, attCur, sideCur, x0Cur, y0Cur);
+    // ring of three tile coordinates: tile k + 2 is written while k and k + 1 are still being read
+    if (tid == 0) {
+        s_tile[0] = locate(w);
+        if (w + stride < totalWork) s_tile[1] = locate(w + stride);
+    }
+    __syncthreads();
+    issue_tile(0, s_tile[0]);
     cp_async_commit();
 
+    unsigned slotCur = 0;  // k % 3
     for (unsigned k = 0; w < totalWork; k++, w += stride) {
         const unsigned buf = k & 1u;
-        const bool hasNext = w + stride < totalWork;
-        unsigned baseNext = 0, attNext = 0;
-        int sideNext = 0, x0Next = 0, y0Next = 0;
-        if (hasNext) {
-            locate(w + stride, baseNext, sideNext, x0Next, y0Next, attNext);
-            issue_tile(buf ^ 1u, baseNext, attNext, sideNext, x0Next, y0Next);
-        }
+        const unsigned slotNext = slotCur == 2 ? 0 : slotCur + 1, slotNN = slotNext == 2 ? 0 : slotNext + 1;
+        if (w + stride < totalWork) issue_tile(buf ^ 1u, s_tile[slotNext]);
         cp_async_commit();
         cp_async_wait_group<1>();  // this tile has landed; the next one may still be in flight
         __syncthreads();           // ... for every thread; and every thread is past the sums of the previous tile
+        // (whose coordinates sat in the ring slot that now takes tile k + 2)
+        if (tid == 0 && w + 2 * (size_t)stride < totalWork) s_tile[slotNN] = locate(w + 2 * stride);
+        const int sideCur = s_tile[slotCur].side, x0Cur = s_tile[slotCur].x0, y0Cur = s_tile[slotCur].y0;
 
         // ---- which constraints of this bundle exist (cloth border, partially filled tiles)
         const int gx = x0Cur - 1 + bx, gy = y0Cur - 1 + by;
@@ -721,7 +742,7 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         const float4* sp = &s_sp[buf][bx * GRID_V + by];
         const float4 c00 = sp[0], c01 = sp[1], c10 = sp[GRID_V], c11 = sp[GRID_V + 1];
         const float4 rest = s_rest[buf][tid];
-        const float restAngle = s_angle[buf][tid];
+        const float restAngle = plan.restAngle ? s_angle[buf][tid] : plan.uniformAngle;
 
         // SolveStretch_Kernel, VtClothSolverGPU.cu L76-101 (four constraints) and SolveBending_Kernel, L128-188 (one)
         const vec3 dV = V3(c00) - V3(c01), dH = V3(c00) - V3(c10), dD = V3(c00) - V3(c11), dA = V3(c01) - V3(c10);
@@ -749,40 +770,54 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         }
 #else
         {
-            bool okV = true, okH = true, okD = true, okLenA = true;
-            const StretchHalf hV = stretch_begin_len(dV, vt_sqrt_u(dot(dV, dV), okV), c00.w, c01.w, rest.x);
-            const StretchHalf hH = stretch_begin_len(dH, vt_sqrt_u(dot(dH, dH), okH), c00.w, c10.w, rest.y);
-            const StretchHalf hD = stretch_begin_len(dD, vt_sqrt_u(dot(dD, dD), okD), c00.w, c11.w, rest.z);
-            const StretchHalf hA = stretch_begin_len(dA, vt_sqrt_u(dot(dA, dA), okLenA), c01.w, c10.w, rest.w);
-            bool okA = okLenA, okB = okLenA;
-            const bool aV = vV && hV.active, aH = vH && hH.active, aD = vQ && hD.active, aA = vQ && hA.active;
-            oV.c1 = oV.c2 = oH.c1 = oH.c2 = oD.c1 = oD.c2 = oA.c1 = oA.c2 = V3(0, 0, 0);
-            if (aV || aH || aD || aA) {  // a freely falling, undeformed cloth keeps every distance at rest: no divisions then
-                stretch_finish_u(hV, c00.w, c01.w, rest.x, oV.c1, oV.c2, okV);
-                stretch_finish_u(hH, c00.w, c10.w, rest.y, oH.c1, oH.c2, okH);
-                stretch_finish_u(hD, c00.w, c11.w, rest.z, oD.c1, oD.c2, okD);
-                stretch_finish_u(hA, c01.w, c10.w, rest.w, oA.c1, oA.c2, okA);
-                if (!aV) oV.c1 = oV.c2 = V3(0, 0, 0);
-                if (!aH) oH.c1 = oH.c2 = V3(0, 0, 0);
-                if (!aD) oD.c1 = oD.c2 = V3(0, 0, 0);
-                if (!aA) oA.c1 = oA.c2 = V3(0, 0, 0);
-            }
-            oV.flag = aV ? 1.0f : 0.0f;
-            oH.flag = aH ? 1.0f : 0.0f;
-            oD.flag = aD ? 1.0f : 0.0f;
-            oA.flag = aA ? 1.0f : 0.0f;
-            if (vV && !okV) oV = grid_stretch_slow(c00, c01, rest.x);
-            if (vH && !okH) oH = grid_stretch_slow(c00, c10, rest.y);
-            if (vQ && !okD) oD = grid_stretch_slow(c00, c11, rest.z);
-            if (vQ && !okA) oA = grid_stretch_slow(c01, c10, rest.w);
-
-            // p0 p1 p2 p3 = c00 c11 c01 c10: e = p3 - p2 = -dA, p2 - p0 = -dV, p3 - p0 = -dH
-            const bool aB = bend_eval_dv_u(-dA, hA.distance, -dV, -dH, V3(c10) - V3(c11), V3(c01) - V3(c11), c00.w, c11.w, c01.w,
-                                           c10.w, restAngle, xpbd_bend, oB.c0, oB.c1, oB.c2, oB.c3, okB) && vQ;
+            // the bend first (it needs the most registers; its three far-corner corrections leave for their slots at once),
+            // then the four stretches.  p0 p1 p2 p3 = c00 c11 c01 c10: e = p3 - p2 = -dA, p2 - p0 = -dV, p3 - p0 = -dH
+            bool okLenA = true;
+            const float lenA = vt_sqrt_u(dot(dA, dA), okLenA);
+            bool okB = okLenA;
+            const bool aB = bend_eval_dv_u(-dA, lenA, -dV, -dH, V3(c10) - V3(c11), V3(c01) - V3(c11), c00.w, c11.w, c01.w, c10.w,
+                                           restAngle, xpbd_bend, oB.c0, oB.c1, oB.c2, oB.c3, okB) && vQ;
             if (!aB) oB.c0 = oB.c1 = oB.c2 = oB.c3 = V3(0, 0, 0);
             oB.flag = aB ? 1.0f : 0.0f;
             if (vQ && !okB) oB = grid_bend_slow(c00, c11, c01, c10, restAngle, xpbd_bend);
+            s_slots[5][tid] = F4(oB.c1, oB.flag);  // bending p1 -> c11
+            s_slots[6][tid] = F4(oB.c3, oB.flag);  // bending p3 -> c10
+            s_slots[7][tid] = F4(oB.c2, oB.flag);  // bending p2 -> c01
+
+            bool okV = true, okH = true, okD = true, okA = okLenA;
+            StretchHalf hV = stretch_begin_len(dV, vt_sqrt_u(dot(dV, dV), okV), c00.w, c01.w, rest.x);
+            StretchHalf hH = stretch_begin_len(dH, vt_sqrt_u(dot(dH, dH), okH), c00.w, c10.w, rest.y);
+            StretchHalf hD = stretch_begin_len(dD, vt_sqrt_u(dot(dD, dD), okD), c00.w, c11.w, rest.z);
+            StretchHalf hA = stretch_begin_len(dA, lenA, c01.w, c10.w, rest.w);
+            hV.active = hV.active && vV;
+            hH.active = hH.active && vH;
+            hD.active = hD.active && vQ;
+            hA.active = hA.active && vQ;
+            oV.c1 = oV.c2 = oH.c1 = oH.c2 = oD.c1 = oD.c2 = oA.c1 = oA.c2 = V3(0, 0, 0);
+            if (hV.active || hH.active || hD.active || hA.active) {  // a freely falling, undeformed cloth keeps every distance at rest: no divisions then
+                // an inactive constraint (or one whose vertices lie outside the cloth: the staged values there are stale but
+                // finite) gets lambda = 0, hence corrections of +-0
+                stretch_finish_masked_u(hV, c00.w, c01.w, rest.x, oV.c1, oV.c2, okV);
+                stretch_finish_masked_u(hH, c00.w, c10.w, rest.y, oH.c1, oH.c2, okH);
+                stretch_finish_masked_u(hD, c00.w, c11.w, rest.z, oD.c1, oD.c2, okD);
+                stretch_finish_masked_u(hA, c01.w, c10.w, rest.w, oA.c1, oA.c2, okA);
+            }
+            oV.flag = hV.active ? 1.0f : 0.0f;
+            oH.flag = hH.active ? 1.0f : 0.0f;
+            oD.flag = hD.active ? 1.0f : 0.0f;
+            oA.flag = hA.active ? 1.0f : 0.0f;
+            if ((vV && !okV) || (vH && !okH) || (vQ && !(okD && okA))) {  // rare: degenerate or non-finite geometry
+                if (vV && !okV) oV = grid_stretch_slow(c00, c01, rest.x);
+                if (vH && !okH) oH = grid_stretch_slow(c00, c10, rest.y);
+                if (vQ && !okD) oD = grid_stretch_slow(c00, c11, rest.z);
+                if (vQ && !okA) oA = grid_stretch_slow(c01, c10, rest.w);
+            }
         }
+#endif
+#if VT_FAST_MATH
+        s_slots[5][tid] = F4(oB.c1, oB.flag);  // bending p1    -> c11
+        s_slots[6][tid] = F4(oB.c3, oB.flag);  // bending p3    -> c10
+        s_slots[7][tid] = F4(oB.c2, oB.flag);  // bending p2    -> c01
 #endif
         // far corners: slots by thread id; own particle: registers
         s_slots[0][tid] = F4(oD.c2, oD.flag);  // diagonal      -> c11
@@ -790,9 +825,6 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         s_slots[2][tid] = F4(oA.c2, oA.flag);  // anti-diagonal -> c10
         s_slots[3][tid] = F4(oV.c2, oV.flag);  // vertical      -> c01
         s_slots[4][tid] = F4(oA.c1, oA.flag);  // anti-diagonal -> c01
-        s_slots[5][tid] = F4(oB.c1, oB.flag);  // bending p1    -> c11
-        s_slots[6][tid] = F4(oB.c3, oB.flag);  // bending p3    -> c10
-        s_slots[7][tid] = F4(oB.c2, oB.flag);  // bending p2    -> c01
         __syncthreads();
 
         // ---- particle (gx, gy): stretch constraints generated at (gx-1,gy-1), (gx-1,gy), (gx,gy-1), (gx,gy) in that (= id)
@@ -816,7 +848,8 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             add(F4(oD.c1, oD.flag));
             const unsigned local = (unsigned)(gx * sideCur + gy);
             if (plan.hasAttach) {  // SolveAttachment_Kernel, L218-234
-                const float* attachSlotPositions = attachSlotsAll + (size_t)((baseCur - attCur) / inst.particles) * inst.slots * 3;
+                const float* attachSlotPositions = attachSlotsAll + (size_t)s_tile[slotCur].instance * inst.slots * 3;
+                const unsigned attCur = s_tile[slotCur].planBase;
                 const unsigned a1 = __ldg(plan.attOff + attCur + local + 1);
                 for (unsigned a = __ldg(plan.attOff + attCur + local); a < a1; a++) {
                     const uint2 r = __ldg(plan.attachRec + a);
@@ -833,13 +866,9 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             add(F4(oB.c0, oB.flag));
             vec3 p = V3(c00);
             if (count > 0) p += delta / count * relaxation;
-            predOutAll[baseCur + local] = F4(p, c00.w);
+            predOutAll[s_tile[slotCur].base + local] = F4(p, c00.w);
         }
-        baseCur = baseNext;
-        attCur = attNext;
-        sideCur = sideNext;
-        x0Cur = x0Next;
-        y0Cur = y0Next;
+        slotCur = slotNext;
     }
     cp_async_wait_all();
 }

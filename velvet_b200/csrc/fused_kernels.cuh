@@ -38,7 +38,8 @@ struct TilePlanDev {
 struct GridPlanDev {
     const GridCloth* cloths;
     const float4* rest4;      // per particle: rest lengths of the stretch constraints generated at that vertex
-    const float* restAngle;   // per particle: rest angle of the quad's bending constraint
+    const float* restAngle;   // per particle: rest angle of the quad's bending constraint; NULL when all are `uniformAngle`
+    float uniformAngle;       // (the reference registers 0 for every quad, VtClothObjectGPU.hpp L128-129)
     const unsigned* attOff;   // attach CSR by particle
     const uint2* attachRec;   // {slot id, distance bits}
     unsigned numCloths, numTiles, hasAttach;

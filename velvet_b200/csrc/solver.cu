@@ -672,6 +672,15 @@ void VtClothSolverGPU::ensureFusedResources()
                 m_gridDev.cloths = m_gCloths;
                 m_gridDev.rest4 = m_gRest4;
                 m_gridDev.restAngle = m_gAngle;
+                m_gridDev.uniformAngle = 0.0f;
+                {  // one rest angle for every quad (what the reference registers): the kernel takes it as a scalar
+                    bool uniform = true;
+                    for (size_t i = 1; i < bendAngles.size() && uniform; i++) uniform = bendAngles[i] == bendAngles[0];
+                    if (uniform && bendAngles.size()) {
+                        m_gridDev.restAngle = nullptr;
+                        m_gridDev.uniformAngle = bendAngles[0];
+                    }
+                }
                 m_gridDev.attOff = m_gAttOff;
                 m_gridDev.attachRec = m_gAttachRec;
                 m_gridDev.numCloths = (uint)m_gridPlan.cloths.size();
@@ -1491,12 +1500,12 @@ GridConstraints GenerateGridConstraints(int R, const float* vertices, const uint
     const size_t nv = (size_t)side * side;
     const size_t ni = (size_t)6 * R * R;
     auto vtx = [&](size_t i) { return load3(vertices, i); };
-    g.particleDiameter = length(vtx(0) - vtx(1)) * particleDiameterScalar;  // VtClothObjectGPU.hpp L49
+    g.particleDiameter = length_plain(vtx(0) - vtx(1)) * particleDiameterScalar;  // VtClothObjectGPU.hpp L49
 
     // ApplyTransform (L67-73): host copy of the world-space positions, used for rest lengths only
     std::vector<vec3> world(nv);
     for (size_t i = 0; i < nv; i++) world[i] = mul_point(M, vtx(i), 1.0f);
-    auto dist = [&](int a, int b) { return length(world[(size_t)a] - world[(size_t)b]); };
+    auto dist = [&](int a, int b) { return length_plain(world[(size_t)a] - world[(size_t)b]); };
     auto at = [side](int x, int y) { return x * side + y; };
 
     // GenerateStretch (L75-116): structural (y, x) then the two shear diagonals, in that emission order
@@ -1526,7 +1535,7 @@ GridConstraints GenerateGridConstraints(int R, const float* vertices, const uint
         for (size_t i = 0; i < nv; i++) {
             g.attachPid.push_back(off + (int)i);
             g.attachSlot.push_back((int)slot);
-            g.attachDist.push_back(length(slotPos - world[i]));
+            g.attachDist.push_back(length_plain(slotPos - world[i]));
         }
     }
 
@@ -1548,7 +1557,7 @@ void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, con
     const int R = m_resolution;
     const size_t nv = (size_t)(R + 1) * (R + 1);
     const size_t ni = (size_t)6 * R * R;
-    m_particleDiameter = length(load3(vertices, 0) - load3(vertices, 1)) * m_solver->simParams.particleDiameterScalar;  // L49
+    m_particleDiameter = length_plain(load3(vertices, 0) - load3(vertices, 1)) * m_solver->simParams.particleDiameterScalar;  // L49
     m_indexOffset = m_solver->AddCloth(vertices, (int)nv, meshIndices, (int)ni, M, m_particleDiameter);
     const GridConstraints g = GenerateGridConstraints(R, vertices, meshIndices, M, m_attachedIndices,
                                                       m_solver->simParams.particleDiameterScalar, m_indexOffset);
