@@ -3,12 +3,16 @@
 self-collision, 1M particles; ms/frame).
 
     python bench.py --gpus N --steps K --warmup W             # this repo's sm_100a solver
-    python bench.py --impl reference --gpus N --steps K ...    # the reference's own CPU solver (port, oracle/)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's own CPU solver (port, oracle/), SAME config
 
 One "step" = one Simulate() frame (1/60 s: 5 substeps x 10 Jacobi iterations, hash rebuilt every 3rd substep)
 of BASELINE.json configs[2]: a 1024x1024 cloth (1,048,576 particles) draped over an SDF sphere + plane with
 particle self-collision.  Under torchrun (N > 1) every rank simulates its own independent cloth on its own
-GPU -- the batched-independent-instances mode: no data-path collective, weak scaling.
+GPU -- the batched-independent-instances mode: no data-path collective, weak scaling.  Every line also carries
+`sub_records` for the two multi-GPU configurations of BASELINE.json: configs[3] (4,096 independent 64x64 cloths sharded over
+the N GPUs, strong scaling) and configs[4] (ONE 4096x4096 cloth decomposed over the N GPUs with NVLink halo exchange,
+strong scaling; a plain single-GPU solver at N = 1), and at N = 1 a `ref_cuda` block: the reference's own CUDA kernels
+(oracle/_ref, unmodified, compiled for sm_100a) timed on the same box and the same frames -- north_star's ">= 10x" denominator.
 
 Timing: W >= 3 warm-up frames; K frames bracketed by barrier + synchronize on both sides, timed with CUDA
 events recorded on the solver's stream, max over ranks.  `value` has every input resident in HBM; `e2e` goes
@@ -66,6 +70,16 @@ def algorithmic_bytes(N, S, B, A, rebuilds_per_frame, nbar):
     per_substep = 48 + collide + 36 + ITERATIONS * per_iter + 48
     per_frame = SUBSTEPS * per_substep + rebuilds_per_frame * hash_rebuild + 24 + (24 + 12 * 2)
     return {"iterate_per_launch": N * per_iter, "frame": N * per_frame, "per_particle_iter": per_iter}
+
+
+def workload_config(R, world, interleaved_hash=3):
+    """The ONE description of the headline workload, shared verbatim by both arms (`--impl reference` prints the same dict)."""
+    n = (R + 1) * (R + 1)
+    return {"workload": (f"{R + 1}x{R + 1} cloth ({n} particles) self-colliding drape over SDF sphere + plane, "
+                         f"{SUBSTEPS} substeps x {ITERATIONS} iterations, hash every {interleaved_hash} substeps"
+                         + (f"; {world} independent cloths, one per GPU, no communication" if world > 1 else "")),
+            "particles_per_gpu": n, "stretch": 4 * R * R + 2 * R, "bend": R * R, "attach": 0, "substeps": SUBSTEPS,
+            "iterations": ITERATIONS}
 
 
 # ---------------------------------------------------------------------------------------------- clocks sampler
@@ -135,27 +149,139 @@ def run_cpu_reference(resolution, frames, warm_frames=0):
 def reference_main(args, rank, world):
     if rank != 0:
         return 0
-    # Each step is one frame of the same scene on a bounded sample: the single-threaded CPU solver needs ~25 s per
-    # 1M-particle frame, so the default sample is a 256x256 cloth (65,536 particles, ~1.4 s per frame).
-    res = args.cpu_resolution
-    steps = max(1, min(args.steps, 5))
-    warm = 1 if args.warmup > 0 else 0
+    # The reference's CPU solver (VtClothSolverCPU: single-threaded Gauss-Seidel, restated in oracle/ref_gs_cpu.c) on the SAME
+    # workload as the velvet arm: the same 1024x1024 drape, W warm-up frames, K timed frames (~12 s each on one host core --
+    # the algorithm is sequential, so one core is all it can use).  Under torchrun this is one of the N identical cloths.
+    res = args.cpu_resolution if args.cpu_resolution is not None else args.resolution
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     value, sec_per_frame, n = run_cpu_reference(res, steps, warm)
+    same = res == args.resolution
+    cfg = workload_config(args.resolution, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec_per_frame * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{res + 1}x{res + 1} cloth ({n} particles) self-colliding drape over SDF sphere + plane, "
-                               f"{SUBSTEPS} substeps x {ITERATIONS} iterations (bounded sample of the 1024x1024 headline workload)",
-                   "substeps": SUBSTEPS, "iterations": ITERATIONS},
+        "config": cfg, "same_config": same,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{steps} frame(s) of a {res + 1}x{res + 1} cloth; VtClothSolverCPU restated "
-                                   f"(oracle/ref_gs_cpu.c), single thread like the reference (Gauss-Seidel is sequential)"},
+                         "sample": (f"{steps} timed + {warm} warm-up frame(s) of "
+                                    + ("the same workload (one cloth)" if same else f"a {res + 1}x{res + 1} sample of the workload")
+                                    + "; VtClothSolverCPU restated (oracle/ref_gs_cpu.c), single thread like the reference "
+                                      f"(Gauss-Seidel is sequential); host has {os.cpu_count()} cores")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+# ---------------------------------------------------------------------------------------------- extra records
+def timed_frames(torch, simulate, synchronize, stream, barrier, group, frames, warm):
+    """W untimed + K timed frames bracketed by barrier + synchronize, CUDA events on the solver stream, max over ranks."""
+    for _ in range(warm):
+        simulate()
+    synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(frames):
+        simulate()
+    e1.record(stream)
+    synchronize()
+    barrier()
+    return group.max(e0.elapsed_time(e1)) / frames
+
+
+def sub_record_batch64(torch, vb, group, rank, world, local_rank, barrier, instances=4096, frames=5, warm=2):
+    """BASELINE configs[3]: `instances` independent 64x64 cloths in total, sharded over the ranks with no communication."""
+    from velvet_b200.distributed import instance_model_height, shard_instances
+    p = vb.default_params()
+    p.numSubsteps, p.numIterations = SUBSTEPS, ITERATIONS
+    R = 63
+    mine = shard_instances(instances, world, rank)
+    g = vb.VtClothSolverGPU(p, device=local_rank)
+    v, idx = vb.GenerateClothMesh(R)
+    g.AddClothInstances(R, v, idx, [vb.TransformMatrix((0, instance_model_height(k), 1.0), (90, 0, 0), (1, 1, 1)) for k in mine])
+    g.UpdateColliders(vb.sphere_plane_colliders())
+    stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local_rank))
+    ms = timed_frames(torch, lambda: g.Simulate(sync=False), g.Synchronize, stream, barrier, group, frames, warm)
+    particles = group.sum(float(g.simParams.numParticles))
+    kernel = "grid" if g.iterateKernel == vb.ITERATE_GRID else "tiles"
+    finite = bool(__import__("numpy").isfinite(g.download("positions")).all())
+    g.close()
+    return {"config": f"{instances} independent 64x64 cloths ({int(particles)} particles) sharded over {world} GPU(s), no communication, "
+                      f"self-collision + SDF sphere + plane, {SUBSTEPS} substeps x {ITERATIONS} iterations",
+            "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "value": particles * SUBSTEPS / (ms * 1e-3), "unit": UNIT,
+            "steps": frames, "warmup": warm, "instances_this_rank": len(mine), "iterate_kernel": kernel, "result_finite": finite}
+
+
+def sub_record_decomposed(torch, vb, group, rank, world, local_rank, barrier, resolution=4095, frames=5, warm=2):
+    """BASELINE configs[4]: ONE cloth decomposed over the ranks (NVLink peer-memory halo exchange once per Jacobi iteration,
+    cross-partition self-collision); at world == 1 the plain single-GPU solver of the same cloth (the strong-scaling base)."""
+    import numpy as np
+    p = vb.default_params()
+    p.numSubsteps, p.numIterations = SUBSTEPS, ITERATIONS
+    g = vb.build_scene(resolution, p, device=local_rank)
+    g.UpdateColliders(vb.sphere_plane_colliders())
+    n = g.simParams.numParticles
+    stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local_rank))
+    rec = {"config": f"one {resolution + 1}x{resolution + 1} cloth ({n} particles) "
+                     + (f"domain-decomposed over {world} GPUs, halo exchange once per Jacobi iteration, cross-partition self-collision"
+                        if world > 1 else "on one GPU (strong-scaling base of the decomposed runs)")
+                     + f", drape over SDF sphere + plane, {SUBSTEPS} substeps x {ITERATIONS} iterations",
+           "scaling": "strong", "n_gpus": world, "unit": UNIT, "steps": frames, "warmup": warm}
+    if world == 1:
+        ms = timed_frames(torch, lambda: g.Simulate(sync=False), g.Synchronize, stream, barrier, group, frames, warm)
+        rec.update({"transport": "none", "iterate_kernel": "grid" if g.iterateKernel == vb.ITERATE_GRID else "tiles",
+                    "launches_per_step": g.lastLaunchCount})
+    else:
+        from velvet_b200.decomposed import DecomposedCloth
+        dd = DecomposedCloth(g, local_rank, transport="peer")
+        ms = timed_frames(torch, lambda: dd.Simulate(sync=False), g.Synchronize, stream, barrier, group, frames, warm)
+        rec.update({"transport": dd.transport, "owned_particles_this_rank": int(dd.info.ownedCount),
+                    "halo_bytes_per_iteration_this_rank": int(dd.halo_bytes_per_iteration),
+                    "launches_per_step": int(g._L.velvet_solver_last_launch_count(g._h))})
+    # every rank must hold the same full state: checksum of the positions, compared across ranks
+    pos = g.download("positions")
+    chk = float(np.sum(pos.astype(np.float64)))
+    rec["positions_checksum"] = chk
+    rec["ranks_agree"] = len(set(group.gather_all(chk))) == 1
+    rec["result_finite"] = bool(np.isfinite(pos).all())
+    rec["ms_per_step"] = ms
+    rec["value"] = n * SUBSTEPS / (ms * 1e-3)
+    if world > 1:
+        dd.close()
+    g.close()
+    return rec
+
+
+def run_ref_cuda(R, frames, warm):
+    """O3: the reference's own VtClothSolverGPU.cu / SpatialHashGPU.cu, unmodified, compiled for sm_100a on stand-in headers
+    (oracle/ref_cuda/build_ref_cuda.sh -> oracle/_ref), on the same scene and frames.  A reported baseline like cpu_baseline:
+    test infrastructure, timed after every velvet measurement is finished."""
+    from oracle import o1, refcuda
+    if not refcuda.available():
+        return {"unavailable": "oracle/_ref/libvelvet_refcuda.so not built (needs /root/reference at build time)"}
+    p = o1.default_params()
+    p.numSubsteps, p.numIterations = SUBSTEPS, ITERATIONS
+    M = o1.transform_matrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1))
+    o = o1.O1Solver(p)
+    v, idx = o1.generate_cloth_mesh(R)
+    o.cloth_object_start(R, v, idx, M, [])
+    r = refcuda.RefCudaSolver(p)
+    r.register_like(o, R, M, [])
+    r.set_colliders([o1.make_collider(o1.PLANE, (0, 0, 0), (1, 1, 1)), o1.make_collider(o1.SPHERE, (0, 0.6, 0), (0.6, 0.6, 0.6))])
+    for _ in range(warm):
+        r.simulate()
+    total, t0 = 0.0, time.perf_counter()
+    for _ in range(frames):
+        r.simulate()
+        total += r.timers().get("Solver_Total", 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / frames
+    n = (R + 1) ** 2
+    ms = total / frames  # its own cudaEvent pair around the Simulate() body
+    return {"impl": "reference CUDA kernels (VtClothSolverGPU.cu + SpatialHashGPU.cu unmodified, nvcc sm_100a, oracle/_ref)",
+            "ms_per_step": ms, "wall_ms_per_step": wall_ms, "value": n * SUBSTEPS / (ms * 1e-3), "unit": UNIT, "steps": frames,
+            "warmup": warm, "how": "the reference's own Solver_Total event timer per Simulate(), same scene, same frame indices"}
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -204,6 +330,7 @@ def velvet_main(args, rank, world, local_rank):
     B = g.buffer_ptr("bendAngles")[1] * ninst
     A = g.buffer_ptr("attachDistances")[1] * ninst
     launches = g.lastLaunchCount
+    iterate_kernel = "iterate_grid_kernel" if g.iterateKernel == vb.ITERATE_GRID else "iterate_tile_kernel"
     log(f"[rank {rank}] setup {setup_s:.2f}s  N={N} S={S} B={B} A={A}  launches/frame={launches}")
 
     stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local_rank))
@@ -292,6 +419,19 @@ def velvet_main(args, rank, world, local_rank):
     g.Synchronize()
     e2e_serial_ms = s0.elapsed_time(s1) / serial_steps
 
+    # ---- the two multi-GPU configurations of BASELINE.json as sub-records (collective: every rank takes part)
+    sub_records = None
+    if not args.no_sub_records and not batch:
+        sub_records = {}
+        for name, fn in (("batch64_4096_cloths", sub_record_batch64), ("decomposed_4096x4096", sub_record_decomposed)):
+            try:
+                log(f"[rank {rank}] sub-record {name} ...")
+                sub_records[name] = fn(torch, vb, group, rank, world, local_rank, barrier)
+            except Exception as e:
+                sub_records[name] = {"failed": f"{type(e).__name__}: {e}"}
+                log(f"[rank {rank}] sub-record {name} failed: {e}")
+            barrier()
+
     if rank != 0:
         group.barrier()  # rank 0 is still measuring stages / the CPU baseline
         group.close()
@@ -312,14 +452,17 @@ def velvet_main(args, rank, world, local_rank):
     iter_launch_ms = stages.get("Solver_Iterate", 0.0) / (SUBSTEPS * ITERATIONS)
     peak, peak_src = measured_peak_gbs()
     achieved = alg["iterate_per_launch"] / (iter_launch_ms * 1e-3) / 1e9 if iter_launch_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("iterate_tile_kernel_dram_bytes_per_launch")
+    traffic, traffic_src = None, None
+    try:  # static: one `ncu --set full` capture of this kernel on this workload, committed with its summary under profiles/
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(iterate_kernel + "_dram_bytes_per_launch")
+        traffic_src = tj.get("source")
     except Exception:
         pass
     frame_gbs = alg["frame"] / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "iterate_tile_kernel (SolveStretch+SolveAttach+SolveBending+ApplyDeltas fused)",
+    roofline = {"bound": "hbm", "kernel": iterate_kernel + " (SolveStretch+SolveAttach+SolveBending+ApplyDeltas fused)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": ("static, not measured in this run: " + str(traffic_src)) if traffic is not None else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["iterate_per_launch"],
                 "algorithmic_bytes_per_particle": alg["per_particle_iter"], "launch_ms": iter_launch_ms,
                 "how": f"CUDA events per stage on the solver stream, un-graphed pass over the middle frames of the timed region, "
@@ -353,28 +496,35 @@ def velvet_main(args, rank, world, local_rank):
                         "sample": f"1 frame of the same {R + 1}x{R + 1} workload ({spf:.1f} s); VtClothSolverCPU restated in "
                                   f"oracle/ref_gs_cpu.c, single thread like the reference; host has {os.cpu_count()} cores"}
 
+    ref_cuda = None
+    if world == 1 and not args.no_sub_records and not batch:
+        log("timing the reference's own CUDA kernels (oracle/_ref) on the same frames ...")
+        try:
+            ref_cuda = run_ref_cuda(R, args.steps, W)
+            if "value" in ref_cuda:
+                ref_cuda["velvet_over_ref_cuda"] = value / ref_cuda["value"]
+        except Exception as e:  # a baseline must never take the product line down
+            ref_cuda = {"unavailable": f"{type(e).__name__}: {e}"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if batch else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"{args.instances} independent {R + 1}x{R + 1} cloths ({int(total_particles)} particles in total) batched in one "
-                                f"solver per GPU, sharded over {world} GPU(s) with no communication, self-collision + SDF sphere + plane, "
-                                f"{SUBSTEPS} substeps x {ITERATIONS} iterations" if batch else
-                                f"{R + 1}x{R + 1} cloth ({N} particles) self-colliding drape over SDF sphere + plane, "
-                                f"{SUBSTEPS} substeps x {ITERATIONS} iterations, hash every {p.interleavedHash} substeps"
-                                + (f"; {world} independent cloths, one per GPU, no communication" if world > 1 else "")),
-                   "particles_per_gpu": N, "stretch": S, "bend": B, "attach": A, "substeps": SUBSTEPS,
-                   "iterations": ITERATIONS, "mean_neighbors": nbar, "pipeline": "fused", "tile": args.tile or 256,
-                   "math": args.math + (" (bit-identical to the CPU oracle)" if args.math == "exact" else " (FMA + approximate div/sqrt)"),
-                   "l2": "per-frame working set (SoA state 64 MB + constraints ~50 MB + neighbor table ~60 MB + hash / "
-                         "packed-float3 buffers ~100 MB) exceeds the 126 MB L2; no flush between frames"},
+        "config": ({"workload": f"{args.instances} independent {R + 1}x{R + 1} cloths ({int(total_particles)} particles in total) batched in one "
+                               f"solver per GPU, sharded over {world} GPU(s) with no communication, self-collision + SDF sphere + plane, "
+                               f"{SUBSTEPS} substeps x {ITERATIONS} iterations", "particles_per_gpu": N, "stretch": S, "bend": B, "attach": A,
+                    "substeps": SUBSTEPS, "iterations": ITERATIONS} if batch else workload_config(R, world, p.interleavedHash)),
+        "implementation": {"pipeline": "fused", "iterate_kernel": iterate_kernel, "mean_neighbors": nbar, "tile": args.tile or 256,
+                           "math": args.math + (" (bit-identical to the CPU oracle)" if args.math == "exact" else " (approximate div/sqrt)"),
+                           "l2": "per-frame working set (SoA state 64 MB + rest lengths 17 MB + neighbor table ~60 MB + hash / "
+                                 "packed-float3 buffers ~100 MB) exceeds the 126 MB L2; no flush between frames"},
         "ms_per_frame": ms_per_step, "wall_ms_per_step": wall * 1e3 / args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "result_finite": finite,
                 "how": "double-buffered read-back on a copy stream (frame k over PCIe while frame k+1 is simulated)",
                 "serial_ms_per_step": e2e_serial_ms},
         "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "ref_cuda": ref_cuda, "sub_records": sub_records,
         "stages_ms": {k: round(v, 4) for k, v in stages.items()}, "setup_s": setup_s,
         "other_math_mode": other,
     }
@@ -391,7 +541,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="velvet", choices=["velvet", "reference"])
     ap.add_argument("--resolution", type=int, default=1023, help="cloth resolution R (particles = (R+1)^2)")
-    ap.add_argument("--cpu-resolution", type=int, default=255, help="--impl reference: resolution of the bounded CPU sample")
+    ap.add_argument("--cpu-resolution", type=int, default=None,
+                    help="--impl reference: resolution of a smaller CPU sample (default: the same cloth as --resolution)")
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the configs[3] / configs[4] sub-records and the ref_cuda block")
     ap.add_argument("--tile", type=int, default=0, help="particles per Jacobi tile (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="drape1m", choices=["drape1m", "batch64"],

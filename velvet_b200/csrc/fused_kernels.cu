@@ -602,12 +602,6 @@ struct GridTileCoord {
 constexpr size_t GRID_SMEM_BYTES = sizeof(float4) * (2 * GRID_V * GRID_V + 10 * 256 + 256 / 2) + 3 * sizeof(GridTileCoord) +
                                    sizeof(GridCloth) * GRID_MAX_CLOTHS;
 
-__device__ __forceinline__ void cp_async_4(void* smemDst, const void* gmemSrc)
-{
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmemSrc));
-}
-
 struct GridStretchOut {
     vec3 c1, c2;
     float flag;

@@ -67,6 +67,14 @@ class Group:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather_all(self, obj) -> list:
+        """Every rank's picklable `obj`, rank-ordered, on every rank (bookkeeping only: checksums, counts)."""
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
     def close(self):
         if self.dist is not None:
             self.dist.destroy_process_group()
