@@ -1,11 +1,3 @@
-mkdir -p gpurun_out/r2f
-timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/r2f/bench_n1.json 2> gpurun_out/r2f/bench_n1.err
-tail -5 gpurun_out/r2f/bench_n1.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r2f/bench_n1.json"))
-print("ms/frame", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "frac", d["roofline"]["frac"])
-print("ref_cuda", d["ref_cuda"])
-print("sub", json.dumps(d["sub_records"], indent=1)[:3000])
-print("cpu", d["cpu_baseline"])
-PY
+mkdir -p gpurun_out/golden
+timeout 900 python tests/golden/make_golden.py gpurun_out/golden --only-hash-1m 2>&1 | tail -3
+timeout 1500 python -m pytest tests/test_decomposed_gpu.py tests/test_instances_gpu.py "tests/test_solver_gpu.py::test_headline_1m_one_frame_against_the_oracle" "tests/test_solver_gpu.py::test_iterate_kernel_selection" "tests/test_solver_gpu.py::test_two_grid_cloths_in_one_solver_match_the_oracle" -m gpu -x -q 2>&1 | tail -12

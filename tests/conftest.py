@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: a full-size oracle run (tens of seconds of CPU)")
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -13,6 +13,8 @@ Fixtures (all small, np.savez_compressed):
   refcuda_hash_R{31,63}.npz   spatial hash on a seeded perturbed sheet: inputs (predicted, initialPositions) and the
                               reference's particleHash, particleIndex, cellStart, cellEnd, neighbour table (entries
                               after each column's terminator masked: they are stale and never read)
+  refcuda_hash_R1023_digest.npz  the same at the headline size (1,048,576 particles): SHA-256 of every output buffer and the
+                              full neighbour lists of 4,096 sampled particles; inputs are regenerated from seeds
   refcuda_cfg1.npz            BASELINE configs[0] (32x32, 2 attach points, plane + moving sphere, 5 substeps x 10
                               iterations): positions after frames 1, 5, 10, 15 (contact-free, where the reference is
                               self-consistent), velocities + normals after frame 1
@@ -76,6 +78,45 @@ def hash_fixture(R, out):
                         cellStart=cs, cellEnd=ce, neighbors=masked_table(r.buffer("neighbors"), n))
 
 
+def hash_inputs_1m(o):
+    """Inputs of the headline-size hash fixture, regenerated from seeds by every consumer: the O1 registration of the
+    1024x1024 drape (initialPositions) and its positions plus seeded noise of a fifth of a cell (predicted)."""
+    n = 1 << 20
+    rng = np.random.default_rng(2024)
+    init = o.buffer("initialPositions").copy()
+    pred = (o.buffer("positions") + rng.normal(0, 0.0009, 3 * n)).astype(np.float32)
+    return init, pred
+
+
+def digest(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def hash_digest_fixture(out):
+    """BASELINE configs[2] size: the reference kernels' hash of 1,048,576 particles.  The full outputs are 280 MB, so the
+    fixture keeps SHA-256 digests of every buffer plus the complete neighbour lists of 4,096 sampled particles."""
+    R = 1023
+    p = params()
+    o, r = pair(R, p, (0, 1.5, 1.0), (90, 0, 0), [])
+    n = (R + 1) ** 2
+    init, pred = hash_inputs_1m(o)
+    r.buffer("initialPositions")[:] = init
+    r.buffer("predicted")[:] = pred
+    r.hash_predicted()
+    cs = r.buffer("cellStart").copy()
+    ce = r.buffer("cellEnd").copy()
+    ce[cs == 0xFFFFFFFF] = 0
+    tab = masked_table(r.buffer("neighbors"), n)
+    sample = np.sort(np.random.default_rng(7).choice(n, 4096, replace=False)).astype(np.uint32)
+    np.savez_compressed(os.path.join(out, "refcuda_hash_R1023_digest.npz"), resolution=R,
+                        particleDiameter=np.float32(r.params.particleDiameter), inputs_digest=digest(np.concatenate([init, pred])),
+                        particleHash=digest(r.buffer("particleHash")), particleIndex=digest(r.buffer("particleIndex")),
+                        cellStart=digest(cs), cellEnd=digest(ce), neighbors=digest(tab), neighbor_count=int((tab != 0xFFFFFFFF).sum()),
+                        sample=sample, sample_neighbors=tab[:, sample], sample_particleIndex=r.buffer("particleIndex")[::256].copy(),
+                        sample_particleHash=r.buffer("particleHash")[::256].copy())
+
+
 def cfg1_fixture(out):
     p = params(numSubsteps=5, numIterations=10)
     o, r = pair(31, p, (0, 2.5, 0), (0, 0, 0), [0, 31])
@@ -130,8 +171,13 @@ if __name__ == "__main__":
     os.makedirs(out, exist_ok=True)
     o1.build()
     assert refcuda.available(), "oracle/_ref/libvelvet_refcuda.so missing: run oracle/ref_cuda/build_ref_cuda.sh where /root/reference exists"
+    if "--only-hash-1m" in sys.argv:
+        hash_digest_fixture(out)
+        print("written", sorted(os.listdir(out)))
+        sys.exit(0)
     for R in (31, 63):
         hash_fixture(R, out)
+    hash_digest_fixture(out)
     cfg1_fixture(out)
     drape_fixture(out)
     cube_fixture(out)

@@ -1,5 +1,9 @@
-"""Domain-decomposed single cloth (north_star mode 2) on real GPUs: needs at least 2 devices (run with
-`gpurun --gpus 2 -- python -m pytest tests/test_decomposed_gpu.py -m gpu`); skipped on a 1-GPU box."""
+"""Domain-decomposed single cloth (north_star mode 2, BASELINE configs[4]).
+
+* One-GPU box: all shards on one device in one process (velvet_b200.decomposed.LocalShards): ownership, exchange lists,
+  owned-only collide / neighbour walk and the stepped schedule against the single-GPU solver, bit for bit.
+* Two or more GPUs (`gpurun --gpus 2 -- python -m pytest tests/test_decomposed_gpu.py -m gpu`): one process per GPU with the
+  NVLink peer-memory transport and with NCCL."""
 import json
 import os
 import socket
@@ -37,3 +41,32 @@ def test_decomposed_cloth_is_bit_identical_to_single_gpu(tmp_path, resolution, t
         assert o["transport"] == transport, o
         assert o["halo_send"] > 0 and o["halo_recv"] > 0 and o["halo_send"] < o["owned"]
     assert sum(o["owned"] for o in outs) == outs[0]["particles"]
+
+
+@pytest.mark.parametrize("resolution,shards,attached", [(63, 3, ()), (127, 4, (0, 127)), (255, 2, ())])
+def test_logical_shards_on_one_device_match_the_single_gpu_solver(resolution, shards, attached):
+    import numpy as np
+
+    import velvet_b200 as vb
+    from velvet_b200.decomposed import LocalShards
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import gpu_params
+
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    cols = vb.sphere_plane_colliders()
+    ref = vb.build_scene(resolution, p, attached=attached)
+    ref.UpdateColliders(cols)
+    parts = [vb.build_scene(resolution, p, attached=attached) for _ in range(shards)]
+    for s in parts:
+        s.UpdateColliders(cols)
+    dd = LocalShards(parts)
+    owned = [int(i.ownedCount) for i in dd.info]
+    assert sum(owned) == ref.simParams.numParticles and min(owned) > 0
+    assert all(int(i.sendTotal) > 0 and int(i.recvTotal) > 0 for i in dd.info)
+    for _ in range(3):
+        ref.Simulate()
+        dd.Simulate()
+    for name in ("positions", "velocities", "normals", "predicted"):
+        a = ref.download(name)
+        for r, s in enumerate(parts):
+            assert np.array_equal(a, s.download(name)), f"{name}: shard {r} of {shards} differs from the single-GPU solver"

@@ -198,3 +198,34 @@ def test_fused_hash_dense_cluster_and_small_caps():
     assert ((tab != 0xFFFFFFFF).sum(0) == 64).any()
     tab, _ = _hash_fused_vs_oracle(pos, init, R, k=7)
     assert ((tab != 0xFFFFFFFF).sum(0) == 7).any()
+
+
+def test_fused_hash_at_headline_size_matches_reference_kernel_digests():
+    """1,048,576 particles (BASELINE configs[2]): the fused pipeline's hash stage against SHA-256 digests of the REFERENCE's
+    own kernels' output (tests/golden/refcuda_hash_R1023_digest.npz, produced on a B200 by tests/golden/make_golden.py) and
+    the full neighbour lists of 4,096 sampled particles."""
+    import hashlib
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "refcuda_hash_R1023_digest.npz")
+    gold = np.load(path)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    n = 1 << 20
+    g = vb.build_scene(1023, vb.default_params())
+    assert np.float32(g.simParams.particleDiameter) == gold["particleDiameter"]
+    g.HashFused()  # builds the fused resources before the buffers are overwritten
+    rng = np.random.default_rng(2024)
+    init = g.download("initialPositions").reshape(-1).copy()
+    pred = (g.download("positions").reshape(-1) + rng.normal(0, 0.0009, 3 * n)).astype(np.float32)
+    assert sha(np.concatenate([init, pred])) == str(gold["inputs_digest"]), "the seeded inputs are not the fixture's"
+    g.upload("predicted", pred)
+    g.HashFused()
+    assert sha(g.download("particleHash")) == str(gold["particleHash"])
+    assert sha(g.download("particleIndex")) == str(gold["particleIndex"])
+    cs = g.download("cellStart").copy()
+    assert sha(cs) == str(gold["cellStart"])
+    ce = g.download("cellEnd").copy()
+    ce[cs == 0xFFFFFFFF] = 0
+    assert sha(ce) == str(gold["cellEnd"])
+    tab = valid_prefix_table(g.download("neighbors"), n, 64)
+    assert np.array_equal(tab[:, gold["sample"]], gold["sample_neighbors"])
+    assert sha(tab) == str(gold["neighbors"])

@@ -94,6 +94,45 @@ def test_instances_are_bit_identical_to_standalone_oracles(attached):
         assert np.array_equal(nb[:, i * n:(i + 1) * n].astype(np.int64), ref), f"neighbour lists of instance {i}"
 
 
+def test_config4_shape_64x64_cloths_match_their_oracles(iterate_kernel_param):
+    """BASELINE configs[3] at its real cloth size: 64 instances of the 64x64 cloth in one solver (the bench runs 4,096 of
+    them); a sample of the instances is checked bit for bit against stand-alone oracles, hash buffers included."""
+    R, K = 63, 64
+    n = (R + 1) ** 2
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    from velvet_b200.distributed import instance_model_height
+    models = [vb.TransformMatrix((0, instance_model_height(i), 1.0), (90, 0, 0), (1, 1, 1)) for i in range(K)]
+    v, idx = vb.GenerateClothMesh(R)
+    g = vb.VtClothSolverGPU(p)
+    g.AddClothInstances(R, v, idx, models, ())
+    assert g.iterateKernel == (vb.ITERATE_GRID if iterate_kernel_param == "grid" else vb.ITERATE_TILES)
+    sample = [0, 1, 31, 32, 63]
+    all_oracles = _oracles(R, p, [models[0]] + [models[i] for i in sample[1:]], [], shared=True)
+    oracles = dict(zip(sample, all_oracles))
+    cols = vb.sphere_plane_colliders()
+    g.UpdateColliders(cols)
+    for o in oracles.values():
+        o.set_colliders([to_o1_collider(c) for c in cols])
+    for _ in range(3):
+        g.Simulate()
+        for o in oracles.values():
+            o.simulate()
+    pos = g.download("positions").reshape(K, n, 3)
+    nrm = g.download("normals").reshape(K, n, 3)
+    ph, pi = g.download("particleHash"), g.download("particleIndex")
+    nb = valid_prefix_table(g.download("neighbors"), K * n, 64)
+    for i, o in oracles.items():
+        assert np.array_equal(pos[i].reshape(-1), o.buffer("positions")), f"instance {i}"
+        assert np.array_equal(nrm[i].reshape(-1), o.buffer("normals")), f"instance {i}"
+        assert np.array_equal(ph[i * n:(i + 1) * n], o.buffer("particleHash") + i * 2 * n)
+        assert np.array_equal(pi[i * n:(i + 1) * n], o.buffer("particleIndex") + i * n)
+        ref = valid_prefix_table(o.buffer("neighbors"), n, 64).astype(np.int64)
+        ref = np.where(ref == 0xFFFFFFFF, 0xFFFFFFFF, ref + i * n)
+        assert np.array_equal(nb[:, i * n:(i + 1) * n].astype(np.int64), ref), f"neighbour lists of instance {i}"
+    # instances 0 and 32 share a model height (k mod 32): identical cloths must stay identical
+    assert np.array_equal(pos[0], pos[32])
+
+
 def test_instances_do_not_interact_and_errors():
     R, K = 16, 4
     n = (R + 1) ** 2

@@ -243,6 +243,48 @@ def test_oracle_hash_is_bit_exact_against_reference_kernel_golden(R):
     assert (g["neighbors"] != 0xFFFFFFFF).sum() > 4 * n
 
 
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def hash_inputs_1m(s):
+    """The seeded inputs of tests/golden/refcuda_hash_R1023_digest.npz (tests/golden/make_golden.py: hash_inputs_1m)."""
+    n = 1 << 20
+    rng = np.random.default_rng(2024)
+    init = s.buffer("initialPositions").copy()
+    pred = (s.buffer("positions") + rng.normal(0, 0.0009, 3 * n)).astype(np.float32)
+    return init, pred
+
+
+def test_oracle_hash_at_headline_size_matches_reference_kernel_digests():
+    """1,048,576 particles (BASELINE configs[2]): every hash buffer of the oracle has the SHA-256 of the reference kernels'
+    output, and the neighbour lists of 4,096 sampled particles match entry by entry."""
+    g = _golden("refcuda_hash_R1023_digest")
+    n = 1 << 20
+    s = o1.O1Solver(o1.default_params())
+    v, idx = o1.generate_cloth_mesh(1023)
+    s.cloth_object_start(1023, v, idx, o1.transform_matrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1)), [])
+    assert np.float32(s.params.particleDiameter) == g["particleDiameter"]
+    init, pred = hash_inputs_1m(s)
+    assert _sha(np.concatenate([init, pred])) == str(g["inputs_digest"]), "the seeded inputs are not the fixture's"
+    s.buffer("predicted")[:] = pred
+    s.hash()
+    assert _sha(s.buffer("particleHash")) == str(g["particleHash"])
+    assert _sha(s.buffer("particleIndex")) == str(g["particleIndex"])
+    cs = s.buffer("cellStart").copy()
+    assert _sha(cs) == str(g["cellStart"])
+    ce = s.buffer("cellEnd").copy()
+    ce[cs == 0xFFFFFFFF] = 0
+    assert _sha(ce) == str(g["cellEnd"])
+    tab = _masked_table(s.buffer("neighbors"), n)
+    assert np.array_equal(tab[:, g["sample"]], g["sample_neighbors"])
+    assert int((tab != 0xFFFFFFFF).sum()) == int(g["neighbor_count"])
+    assert _sha(tab) == str(g["neighbors"])
+    assert np.array_equal(s.buffer("particleIndex")[::256], g["sample_particleIndex"])
+    assert np.array_equal(s.buffer("particleHash")[::256], g["sample_particleHash"])
+
+
 def test_oracle_positions_within_tolerance_of_reference_kernel_golden_cfg1():
     g = _golden("refcuda_cfg1")
     tol = 1e-4 * 2.0

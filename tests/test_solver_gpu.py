@@ -13,7 +13,7 @@ import pytest
 import velvet_b200 as vb
 from oracle import o1
 
-from util import EXTENT, ColliderTrack, gpu_params, make_pair, max_abs_diff, set_colliders, valid_prefix_table
+from util import EXTENT, ColliderTrack, gpu_params, make_pair, max_abs_diff, set_colliders, to_o1_params, valid_prefix_table
 
 pytestmark = pytest.mark.gpu
 
@@ -348,6 +348,72 @@ def test_fused_is_deterministic_and_matches_seam_at_1m():
     # the FAST math mode is deterministic too (fixed summation order) and within tolerance of the EXACT one
     assert np.array_equal(outs[3][0], outs[4][0]), "fast math mode is run-to-run deterministic"
     assert max_abs_diff(outs[3][0], outs[0][0]) <= TOL_1
+
+
+@pytest.mark.slow
+def test_headline_1m_one_frame_against_the_oracle(iterate_kernel_param):
+    """BASELINE configs[2], the benchmarked workload itself: one frame (5 x 10) of the 1024x1024 self-colliding drape against
+    the O1 oracle (about 20 s of CPU): positions / velocities / normals / predicted bit for bit, and the spatial hash of the
+    frame's last rebuild (keys, sorted order, cell table, neighbour lists)."""
+    p = gpu_params(numSubsteps=5, numIterations=10)
+    g, o = make_pair(1023, p)
+    assert g.iterateKernel == (vb.ITERATE_GRID if iterate_kernel_param == "grid" else vb.ITERATE_TILES)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    g.Simulate()
+    o.simulate()
+    assert_fused_parity(g, o, TOL_1)
+    N = 1 << 20
+    assert np.array_equal(g.download("particleHash"), o.buffer("particleHash"))
+    assert np.array_equal(g.download("particleIndex"), o.buffer("particleIndex"))
+    cs_g, cs_o = g.download("cellStart"), o.buffer("cellStart")
+    assert np.array_equal(cs_g, cs_o)
+    occupied = cs_o != 0xFFFFFFFF
+    assert np.array_equal(g.download("cellEnd")[occupied], o.buffer("cellEnd")[occupied])
+    assert np.array_equal(valid_prefix_table(g.download("neighbors"), N, 64), valid_prefix_table(o.buffer("neighbors"), N, 64))
+    g.close()
+
+
+def test_iterate_kernel_selection():
+    """Grid cloths carrying exactly the reference's constraint pattern run the implicit-grid kernel; anything else (an extra
+    constraint, a second triangulation, a generic mesh) keeps the record-driven tile kernel -- same results either way."""
+    if os.environ.get("VELVET_ITERATE") == "tiles":
+        pytest.skip("kernel choice forced by the environment")
+    p = gpu_params()
+    g, _ = make_pair(20, p, oracle=False)
+    assert g.iterateKernel == vb.ITERATE_GRID
+    g.AddStretch(0, 5, 0.3)  # one constraint beyond the pattern
+    assert g.iterateKernel == vb.ITERATE_TILES
+    g2, _ = make_pair(20, p, oracle=False)
+    g2.SetIterateMode(vb.ITERATE_TILES)
+    assert g2.iterateKernel == vb.ITERATE_TILES
+    g2.SetIterateMode(vb.ITERATE_AUTO)
+    assert g2.iterateKernel == vb.ITERATE_GRID
+    # two grid cloths of different size in one solver: both recognised, one kernel launch covers both
+    g3 = vb.VtClothSolverGPU(p)
+    for R, pos in ((12, (0, 1.5, 1.0)), (17, (0.3, 1.9, 1.0))):
+        v, idx = vb.GenerateClothMesh(R)
+        obj = vb.VtClothObjectGPU(R, g3)
+        obj.Start(v, idx, vb.TransformMatrix(pos, (90, 0, 0), (1, 1, 1)))
+    assert g3.iterateKernel == vb.ITERATE_GRID
+
+
+def test_two_grid_cloths_in_one_solver_match_the_oracle(iterate_kernel_param):
+    """Two cloths of different resolution registered one after the other (their particles collide with each other through
+    the shared hash): the grid kernel's cloth table against the oracle."""
+    p = gpu_params(numSubsteps=3, numIterations=6)
+    g = vb.VtClothSolverGPU(p)
+    o = o1.O1Solver(to_o1_params(p))
+    for R, pos in ((30, (0, 1.5, 1.0)), (19, (0.1, 1.62, 0.9))):
+        v, idx = vb.GenerateClothMesh(R)
+        M = vb.TransformMatrix(pos, (90, 0, 0), (1, 1, 1))
+        vb.VtClothObjectGPU(R, g).Start(v, idx, M)
+        ov, oidx = o1.generate_cloth_mesh(R)
+        o.cloth_object_start(R, ov, oidx, o1.transform_matrix(pos, (90, 0, 0), (1, 1, 1)), [])
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    for _ in range(8):
+        g.Simulate()
+        o.simulate()
+    assert_fused_parity(g, o, TOL_60)
 
 
 def _register_generic(g, o, vertices, tri_indices, model, stretch, bends, attach_slots, attaches, diameter):

@@ -168,3 +168,89 @@ class DecomposedCloth:
             self._step(DD_FRAME_END)
         if sync:
             self.solver.Synchronize()
+
+
+class LocalShards:
+    """The decomposed cloth with all G shards on ONE device in ONE process: G solvers carrying the same cloth, solver r set
+    up as rank r of G, driven through the same stepped C ABI as the NCCL transport, with the halo exchange and the
+    per-substep all-gather done as device-to-device copies between the solvers' buffers.  No throughput to be had -- it
+    exists so that the decomposition logic (ownership, exchange lists, owned-only collide / neighbour walk, the stepped
+    schedule) is checked against the single-GPU solver on a one-GPU box (tests/test_decomposed_gpu.py)."""
+
+    def __init__(self, solvers, device_index: int = 0):
+        import torch
+        self.torch = torch
+        self.solvers = list(solvers)
+        self.world = len(self.solvers)
+        self._L = _capi.load()
+        self._L.velvet_solver_dd_setup.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self._L.velvet_solver_dd_info.argtypes = [C.c_void_p, C.POINTER(VelvetDDInfo)]
+        self._L.velvet_solver_dd_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._L.velvet_solver_dd_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
+        dev = torch.device("cuda", device_index)
+        alias = lambda ptr, n: torch.as_tensor(_DevicePtr(ptr, 4 * max(n, 1)), device=dev)
+        self.info, self.send_off, self.recv_off = [], [], []
+        self.send, self.recv, self.gather_send, self.gather_recv = [], [], [], []
+        for r, s in enumerate(self.solvers):
+            check(self._L.velvet_solver_dd_setup(s._h, r, self.world))
+            info = VelvetDDInfo()
+            check(self._L.velvet_solver_dd_info(s._h, C.byref(info)))
+            so = (C.c_uint * (self.world + 1))()
+            ro = (C.c_uint * (self.world + 1))()
+            check(self._L.velvet_solver_dd_offsets(s._h, so, ro))
+            self.info.append(info)
+            self.send_off.append(list(so))
+            self.recv_off.append(list(ro))
+            self.send.append(alias(info.sendBuf, info.sendTotal))
+            self.recv.append(alias(info.recvBuf, info.recvTotal))
+            self.gather_send.append(alias(info.gatherSend, info.maxOwnedCount))
+            self.gather_recv.append(alias(info.gatherRecv, info.maxOwnedCount * self.world))
+
+    def _all(self, op, arg=0, farg=0.0):
+        for s in self.solvers:
+            check(self._L.velvet_solver_dd_step(s._h, op, arg, farg))
+
+    def _sync(self):
+        for s in self.solvers:
+            s.Synchronize()
+        self.torch.cuda.synchronize()
+
+    def _exchange_halo(self):
+        self._sync()
+        for r in range(self.world):
+            for q in range(self.world):
+                if q == r:
+                    continue
+                s0, s1 = 4 * self.send_off[r][q], 4 * self.send_off[r][q + 1]
+                r0, r1 = 4 * self.recv_off[q][r], 4 * self.recv_off[q][r + 1]
+                assert s1 - s0 == r1 - r0, "exchange lists must be symmetric"
+                if s1 > s0:
+                    self.recv[q][r0:r1].copy_(self.send[r][s0:s1])
+        self._sync()
+
+    def _all_gather(self):
+        self._sync()
+        m = 4 * self.info[0].maxOwnedCount
+        for q in range(self.world):
+            for r in range(self.world):
+                self.gather_recv[q][r * m:(r + 1) * m].copy_(self.gather_send[r][:m])
+        self._sync()
+
+    def Simulate(self, dt: float = 1.0 / 60.0):
+        P = self.solvers[0].simParams
+        self._all(DD_FRAME_BEGIN, 0, dt)
+        for sub in range(P.numSubsteps):
+            self._all(DD_SUBSTEP_BEGIN, sub)
+            self._exchange_halo()
+            self._all(DD_ITERATE_FINISH)
+            for _ in range(P.numIterations):
+                self._all(DD_ITERATE_OWNED)
+                self._exchange_halo()
+                self._all(DD_ITERATE_FINISH)
+            if self.world > 1:
+                self._all(DD_GATHER_PACK)
+                self._all_gather()
+                self._all(DD_GATHER_UNPACK)
+            self._all(DD_SUBSTEP_END, sub)
+        self._all(DD_FRAME_END)
+        self._sync()
