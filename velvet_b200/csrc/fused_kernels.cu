@@ -46,7 +46,7 @@ __device__ __forceinline__ float4 F4(vec3 v, float w) { return make_float4(v.x, 
 __device__ __forceinline__ void stage_colliders(PreparedCollider* s_col, const PreparedCollider* __restrict__ g_col,
                                                 unsigned n)
 {
-    // 196-byte structs copied as 49 words each
+    // 196-byte structs copied as 49 words each (callers clamp n to the VT_MAX_COLLIDERS entries of the stage)
     const unsigned words = n * (unsigned)(sizeof(PreparedCollider) / 4);
     const unsigned* src = reinterpret_cast<const unsigned*>(g_col);
     unsigned* dst = reinterpret_cast<unsigned*>(s_col);
@@ -59,7 +59,7 @@ __global__ void prepare_inputs_kernel(const VtSDFCollider* __restrict__ collider
                                       unsigned numSlotFloats, const FrameParams* __restrict__ fp)
 {
     const unsigned i = threadIdx.x;
-    if (i < fp->numColliders) prepare_collider(colliders[i], prepared[i]);
+    if (i < min(fp->numColliders, VT_MAX_COLLIDERS)) prepare_collider(colliders[i], prepared[i]);
     for (unsigned k = i; k < numSlotFloats; k += blockDim.x) slotPositionsOut[k] = slotPositions[k];
 }
 
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict
                                                          const FrameParams* __restrict__ fp, unsigned n)
 {
     __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
-    const unsigned nc = fp->numColliders;
+    const unsigned nc = min(fp->numColliders, VT_MAX_COLLIDERS);
     stage_colliders(s_col, colliders, nc);
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(PB, 5) collide_kernel(const float4* __restrict
                                                      const unsigned* __restrict__ subset, unsigned subsetCount)
 {
     __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
-    const unsigned nc = fp->numColliders;
+    const unsigned nc = min(fp->numColliders, VT_MAX_COLLIDERS);
     stage_colliders(s_col, colliders, nc);
     // subset != nullptr: only the listed particles (the ones this rank owns in the domain-decomposed mode)
     const unsigned tidx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -12,6 +12,8 @@
 #include "capi_util.hpp"
 #include "hash_kernels.cuh"
 #include "radix_sort.cuh"
+#include <map>
+
 #include "seam.hpp"
 #include "vt_math.cuh"
 
@@ -24,9 +26,32 @@ bool g_paramsSet = false;
 cudaStream_t g_stream = 0;
 std::mutex g_mutex;
 
-// scratch for HashObjects / SortPairs (the reference keeps a function-static VtBuffer, SpatialHashGPU.cu L140)
-RadixSorter g_sorter;
-DeviceBuffer<unsigned> g_keysAlt, g_valsAlt;
+// Scratch for HashObjects / SortPairs (the reference keeps a function-static VtBuffer, SpatialHashGPU.cu L140).  One set per
+// DEVICE (a pointer allocated on device 0 must never be handed to a kernel on device 1), grow-only, and handed from one
+// user to the next through an event: callers run on their own non-blocking streams, so the next sort waits (on the device)
+// for the previous one instead of overwriting scratch that is still being read.  g_mutex covers the bookkeeping only.
+struct SortScratch {
+    RadixSorter sorter;
+    DeviceBuffer<unsigned> keysAlt, valsAlt;
+    cudaEvent_t lastUse = nullptr;
+};
+std::map<int, SortScratch> g_scratch;
+
+// g_mutex must be held.  Orders `st` after the previous user of this device's scratch and makes room for n items.
+SortScratch& acquire_scratch(unsigned n, cudaStream_t st)
+{
+    int dev = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    SortScratch& s = g_scratch[dev];
+    if (s.lastUse && (n > s.keysAlt.size() || n > s.valsAlt.size())) VT_CUDA(cudaEventSynchronize(s.lastUse));  // about to reallocate
+    s.keysAlt.reserve(n);
+    s.valsAlt.reserve(n);
+    s.sorter.reserve(n);
+    if (!s.lastUse) VT_CUDA(cudaEventCreateWithFlags(&s.lastUse, cudaEventDisableTiming));
+    else VT_CUDA(cudaStreamWaitEvent(st, s.lastUse, 0));
+    return s;
+}
+void release_scratch(SortScratch& s, cudaStream_t st) { VT_CUDA(cudaEventRecord(s.lastUse, st)); }
 
 constexpr int BLOCK = 256;  // Common.cuh L46
 inline unsigned grid_for(unsigned n) { return (n + BLOCK - 1) / BLOCK; }
@@ -361,23 +386,22 @@ void HashObjects(unsigned* particleHash, unsigned* particleIndex, unsigned* cell
     if (hp.tableSize <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "HashObjects: tableSize <= 0");
     std::lock_guard<std::mutex> lk(g_mutex);  // shared sort scratch (function-static in the reference, .cu L140)
     const int maxBit = (int)ceil(log2((double)hp.tableSize));  // SpatialHashGPU.cu L179
-    g_keysAlt.allocate(n);
-    g_valsAlt.allocate(n);
-    g_sorter.reserve(n);
+    SortScratch& S = acquire_scratch(n, st);
     // With an odd number of digit passes the keys are produced in the alternate buffer so that the sorted
     // result lands in the caller's particleHash / particleIndex (in-place semantics of the reference).
     const bool odd = RadixSorter::numPasses(maxBit) & 1;
-    unsigned* k0 = odd ? g_keysAlt.data() : particleHash;
-    unsigned* v0 = odd ? g_valsAlt.data() : particleIndex;
-    unsigned* k1 = odd ? particleHash : g_keysAlt.data();
-    unsigned* v1 = odd ? particleIndex : g_valsAlt.data();
+    unsigned* k0 = odd ? S.keysAlt.data() : particleHash;
+    unsigned* v0 = odd ? S.valsAlt.data() : particleIndex;
+    unsigned* k1 = odd ? particleHash : S.keysAlt.data();
+    unsigned* v1 = odd ? particleIndex : S.valsAlt.data();
     hash_particles_kernel<PosPacked3><<<grid_for(n), BLOCK, 0, st>>>(k0, v0, PosPacked3{positions}, n, hp.cellSpacing, hp.tableSize, n);
-    g_sorter.sort(k0, v0, k1, v1, n, maxBit, st);
+    S.sorter.sort(k0, v0, k1, v1, n, maxBit, st);
+    release_scratch(S, st);
     VT_CUDA(cudaMemsetAsync(cellStart, 0xff, sizeof(unsigned) * (size_t)hp.tableSize, st));
     find_cell_start_kernel<<<grid_for(n), BLOCK, 0, st>>>(cellStart, cellEnd, particleHash, n);
     cache_neighbors_kernel<PosPacked3, PosPacked3><<<grid_for(n), BLOCK, 0, st>>>(
         neighbors, particleIndex, cellStart, cellEnd, PosPacked3{positions}, PosPacked3{originalPositions}, hp);
-    t_lastLaunches = 3 + g_sorter.lastLaunchCount();
+    t_lastLaunches = 3 + S.sorter.lastLaunchCount();
     VT_CUDA(cudaGetLastError());
 }
 
@@ -605,13 +629,13 @@ int velvet_SortPairs(unsigned* keys, unsigned* values, unsigned numItems, int en
     if (numItems == 0 || endBit <= 0) return VELVET_OK;
     VT_REQUIRE(keys && values && endBit <= 32, "SortPairs: bad argument");
     std::lock_guard<std::mutex> lk(g_mutex);
-    g_keysAlt.allocate(numItems);
-    g_valsAlt.allocate(numItems);
-    const int where = g_sorter.sort(keys, values, g_keysAlt.data(), g_valsAlt.data(), numItems, endBit, g_stream);
+    SortScratch& S = acquire_scratch(numItems, g_stream);
+    const int where = S.sorter.sort(keys, values, S.keysAlt.data(), S.valsAlt.data(), numItems, endBit, g_stream);
     if (where == 1) {
-        VT_CUDA(cudaMemcpyAsync(keys, g_keysAlt.data(), sizeof(unsigned) * numItems, cudaMemcpyDeviceToDevice, g_stream));
-        VT_CUDA(cudaMemcpyAsync(values, g_valsAlt.data(), sizeof(unsigned) * numItems, cudaMemcpyDeviceToDevice, g_stream));
+        VT_CUDA(cudaMemcpyAsync(keys, S.keysAlt.data(), sizeof(unsigned) * numItems, cudaMemcpyDeviceToDevice, g_stream));
+        VT_CUDA(cudaMemcpyAsync(values, S.valsAlt.data(), sizeof(unsigned) * numItems, cudaMemcpyDeviceToDevice, g_stream));
     }
+    release_scratch(S, g_stream);
     VT_API_END
 }
 

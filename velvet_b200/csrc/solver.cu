@@ -255,7 +255,26 @@ void VtClothSolverGPU::ReadbackWait(int ticket)
     if (m_copyPending[ticket]) VT_CUDA(cudaEventSynchronize(m_copyDone[ticket]));
 }
 
-void VtClothSolverGPU::Synchronize() { VT_CUDA(cudaStreamSynchronize(m_stream)); }
+void VtClothSolverGPU::Synchronize()
+{
+    VT_CUDA(cudaStreamSynchronize(m_stream));
+    m_mayBeBusy = false;
+}
+
+// The hash buffers were sized with the maxNumNeighbors of AddCloth time (SpatialHashGPU.hpp L18-28); a larger value written
+// into simParams afterwards must not make the collide kernels walk past the neighbour columns.
+void VtClothSolverGPU::clampNeighborBound(VtSimParams& P) const
+{
+    if (m_spatialHash && P.maxNumNeighbors > m_spatialHash->maxNumNeighbors()) P.maxNumNeighbors = m_spatialHash->maxNumNeighbors();
+}
+
+// Registration calls reallocate managed buffers: the device must be idle first, whichever device is current in the caller
+void VtClothSolverGPU::quiesce()
+{
+    if (!m_mayBeBusy) return;
+    VT_CUDA(cudaSetDevice(m_device));
+    Synchronize();
+}
 
 void VtClothSolverGPU::OnDestroy()
 {
@@ -307,6 +326,8 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
     if (!vertices || numVertices <= 0 || !modelMatrix16 || numIndices < 0 || (numIndices && !meshIndices))
         throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddCloth: bad argument");
     if (m_instanced) throw Error(VELVET_ERR_STATE, "AddCloth: the solver holds batched instances (AddClothInstances)");
+    if ((unsigned long long)simParams.numParticles + (unsigned long long)numVertices >= (1ull << 30))
+        throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddCloth: at most 2^30 - 1 particles (the hash table has 2 * numParticles int rows)");
     VT_CUDA(cudaSetDevice(m_device));
     Synchronize();
     const int prevNumParticles = (int)simParams.numParticles;
@@ -356,7 +377,7 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
     const size_t n = (size_t)(R + 1) * (R + 1);
     const size_t ni = (size_t)6 * R * R;
     const size_t total = n * (size_t)numInstances;
-    if (total >= (1ull << 31)) throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: too many particles");
+    if (total >= (1ull << 30)) throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: at most 2^30 - 1 particles in total");
     const std::vector<int> attached(attachedIndices, attachedIndices + numAttached);
     for (int a : attached)
         if (a < 0 || (size_t)a >= n) throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddClothInstances: attached index out of range");
@@ -407,6 +428,7 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
 
 void VtClothSolverGPU::AddStretch(int idx1, int idx2, float distance)
 {
+    quiesce();
     stretchIndices.push_back(idx1);
     stretchIndices.push_back(idx2);
     stretchLengths.push_back(distance);
@@ -415,12 +437,14 @@ void VtClothSolverGPU::AddStretch(int idx1, int idx2, float distance)
 
 void VtClothSolverGPU::AddAttachSlot(const float* p)
 {
+    quiesce();
     attachSlotPositions.push_back(V3(p[0], p[1], p[2]));
     invalidate();
 }
 
 void VtClothSolverGPU::AddAttach(int particleIndex, int slotIndex, float distance)
 {
+    quiesce();
     if (particleIndex < 0 || (size_t)particleIndex >= invMasses.size())
         throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddAttach: particle index out of range");
     if (distance == 0) invMasses[(size_t)particleIndex] = 0;  // hpp L172
@@ -432,6 +456,7 @@ void VtClothSolverGPU::AddAttach(int particleIndex, int slotIndex, float distanc
 
 void VtClothSolverGPU::AddBend(uint idx1, uint idx2, uint idx3, uint idx4, float angle)
 {
+    quiesce();
     bendIndices.push_back(idx1);
     bendIndices.push_back(idx2);
     bendIndices.push_back(idx3);
@@ -442,6 +467,7 @@ void VtClothSolverGPU::AddBend(uint idx1, uint idx2, uint idx3, uint idx4, float
 
 void VtClothSolverGPU::AddStretchBulk(const int* idxPairs, const float* distances, size_t n)
 {
+    quiesce();
     stretchIndices.append(idxPairs, 2 * n);
     stretchLengths.append(distances, n);
     invalidate();
@@ -449,6 +475,7 @@ void VtClothSolverGPU::AddStretchBulk(const int* idxPairs, const float* distance
 
 void VtClothSolverGPU::AddBendBulk(const uint* idxQuads, const float* angles, size_t n)
 {
+    quiesce();
     bendIndices.append(idxQuads, 4 * n);
     bendAngles.append(angles, n);
     invalidate();
@@ -456,6 +483,7 @@ void VtClothSolverGPU::AddBendBulk(const uint* idxQuads, const float* angles, si
 
 void VtClothSolverGPU::AddAttachBulk(const int* particleIds, const int* slotIds, const float* distances, size_t n)
 {
+    quiesce();
     for (size_t i = 0; i < n; i++) {
         if (particleIds[i] < 0 || (size_t)particleIds[i] >= invMasses.size())
             throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddAttach: particle index out of range");
@@ -473,6 +501,8 @@ void VtClothSolverGPU::UpdateColliders(const VtSDFCollider* colliders, int numCo
     VT_CUDA(cudaSetDevice(m_device));
     // The seam pipeline reads the managed block directly (like the reference): drain the previous frame first.
     // The fused pipeline reads a device copy that is refreshed in stream order, so no host sync is needed.
+    if (m_ddReady && (unsigned)numColliders > VT_MAX_COLLIDERS)
+        throw Error(VELVET_ERR_UNSUPPORTED, "a decomposed cloth takes at most 64 SDF colliders");
     if (m_pipeline != VELVET_PIPELINE_FUSED) Synchronize();
     sdfColliders.resize((size_t)numColliders);
     if (numColliders) {
@@ -918,13 +948,25 @@ VtClothSolverGPU::DDBuffers VtClothSolverGPU::ddBuffers() const
                      m_ddSendOff[m_dd.world], m_ddRecvOff[m_dd.world], m_ddOwnedCount[m_dd.rank], m_ddMaxOwned};
 }
 
-void VtClothSolverGPU::ddFrameBegin(float frameTime)
+// Checks shared by every entry point that starts a decomposed frame.  The decomposed mode has no seam fallback, so what
+// the fused kernels cannot take (more colliders than their shared-memory stage holds) is an error here, not a silent
+// out-of-bounds read.
+void VtClothSolverGPU::ddValidateFrame() const
 {
     if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
-    VT_CUDA(cudaSetDevice(m_device));
     if (m_topologyDirty) throw Error(VELVET_ERR_STATE, "the cloth changed after ddSetup: call ddSetup again");
+    if (simParams.numSubsteps <= 0 || simParams.interleavedHash <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "bad substep parameters");
+    if (sdfColliders.size() > VT_MAX_COLLIDERS)
+        throw Error(VELVET_ERR_UNSUPPORTED, "a decomposed cloth takes at most 64 SDF colliders");
+}
+
+void VtClothSolverGPU::ddFrameBegin(float frameTime)
+{
+    ddValidateFrame();
+    VT_CUDA(cudaSetDevice(m_device));
     FrameParams hp;
     hp.P = simParams;
+    clampNeighborBound(hp.P);
     hp.frameTime = frameTime;
     hp.substepTime = frameTime / (float)simParams.numSubsteps;
     hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
@@ -1223,13 +1265,12 @@ void VtClothSolverGPU::recordDDFrame()
 
 void VtClothSolverGPU::ddSimulate(float frameTime)
 {
-    if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
+    ddValidateFrame();
     if (!m_ddPeersReady) throw Error(VELVET_ERR_STATE, "ddSimulate: peers are not mapped (ddPeerExport / ddPeerImport)");
     VT_CUDA(cudaSetDevice(m_device));
-    if (m_topologyDirty) throw Error(VELVET_ERR_STATE, "the cloth changed after ddSetup: call ddSetup again");
-    if (simParams.numSubsteps <= 0 || simParams.interleavedHash <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "bad substep parameters");
     FrameParams hp;
     hp.P = simParams;
+    clampNeighborBound(hp.P);
     hp.frameTime = frameTime;
     hp.substepTime = frameTime / (float)simParams.numSubsteps;
     hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
@@ -1255,6 +1296,7 @@ void VtClothSolverGPU::ddSimulate(float frameTime)
         m_ddGraphKey = key;
     }
     VT_CUDA(cudaGraphLaunch(m_ddGraphExec, m_stream));
+    m_mayBeBusy = true;
     m_lastLaunches = m_ddGraphLaunches;
 }
 
@@ -1263,6 +1305,7 @@ void VtClothSolverGPU::Simulate() { Simulate(kFixedDeltaTime); }
 void VtClothSolverGPU::Simulate(float frameTime)
 {
     VT_CUDA(cudaSetDevice(m_device));
+    m_mayBeBusy = true;  // until the next Synchronize()
     if (simParams.numSubsteps <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "numSubsteps must be positive");
     if (simParams.interleavedHash <= 0) throw Error(VELVET_ERR_INVALID_ARGUMENT, "interleavedHash must be positive");
     if (simParams.numParticles == 0) {
@@ -1284,6 +1327,7 @@ void VtClothSolverGPU::Simulate(float frameTime)
 
     FrameParams hp;
     hp.P = simParams;
+    clampNeighborBound(hp.P);
     hp.frameTime = frameTime;
     hp.substepTime = frameTime / (float)simParams.numSubsteps;
     hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
@@ -1314,6 +1358,7 @@ void VtClothSolverGPU::Simulate(float frameTime)
         m_graphKey = key;
     }
     VT_CUDA(cudaGraphLaunch(m_graphExec, m_stream));
+    m_mayBeBusy = true;
     m_lastLaunches = m_graphLaunches;
 }
 
@@ -1334,6 +1379,8 @@ StageTiming VtClothSolverGPU::SimulateTimed()
     } else {
         FrameParams hp;
         hp.P = simParams;
+        clampNeighborBound(hp.P);
+    clampNeighborBound(hp.P);
         hp.frameTime = kFixedDeltaTime;
         hp.substepTime = kFixedDeltaTime / (float)simParams.numSubsteps;
         hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;

@@ -192,6 +192,9 @@ private:
     void recordFusedFrame(Stage* timing);
     void ensureFusedResources();
     void invalidate() { m_topologyDirty = true; }
+    void clampNeighborBound(VtSimParams& P) const;
+    void quiesce();  // drains an asynchronous frame before a registration call touches managed buffers
+    bool m_mayBeBusy = false;
     unsigned long long topologyKey() const;
 
     int m_device = 0;
@@ -217,6 +220,7 @@ private:
     DeviceBuffer<float4> m_ddSendBuf, m_ddRecvBuf, m_ddGatherSend, m_ddGatherRecv;
     float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
     void recordDDFrame();
+    void ddValidateFrame() const;
     DeviceBuffer<unsigned> m_ddFlags;
     DeviceBuffer<ddpeer::Control> m_ddCtl;
     DeviceBuffer<unsigned char> m_ddSendPeer;

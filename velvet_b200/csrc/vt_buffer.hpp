@@ -206,6 +206,12 @@ public:
         if (count) VT_CUDA(cudaMalloc((void**)&m_data, count * sizeof(T)));
         m_count = count;
     }
+    // Grow-only variant for scratch that is reused at changing sizes: never shrinks, grows by at least 1.5x.
+    void reserve(size_t count)
+    {
+        if (count <= m_count && m_data) return;
+        allocate(count > m_count + m_count / 2 ? count : m_count + m_count / 2);
+    }
     void upload(const T* host, size_t count, cudaStream_t st = 0)
     {
         allocate(count);
