@@ -25,6 +25,11 @@ struct Control {
     unsigned blocksDone; // last-block counter of the push kernels
     unsigned error;      // 1 = a wait timed out (peer missing); sticky until ddPeerReset
     unsigned pad;
+    // ---- strip protocol (grid cloths, see below)
+    unsigned seq;        // exchange launches completed by this rank: stable while a launch runs (its last block bumps it)
+    unsigned sendsDone;  // blocks / boundary tiles of the running launch whose peer stores are performed
+    unsigned exits;      // blocks that left the running launch
+    unsigned pad2;
 };
 
 struct PeerTable {
@@ -42,6 +47,68 @@ void launch_push_owned(cudaStream_t st, const PeerTable* table, Control* ctl, in
 // no data: "I am done reading my buffers of the previous phase"
 void launch_signal(cudaStream_t st, const PeerTable* table, Control* ctl);
 void launch_wait(cudaStream_t st, const PeerTable* table, Control* ctl, const unsigned* localFlags, unsigned long long timeoutNs);
+
+// ---- strip protocol: a grid cloth decomposed into strips of particle rows (contiguous index ranges).
+// Exchange launch number L of a rank (every rank runs the same sequence) publishes the value L + 1 into flags[rank] of every
+// peer once its peer stores are performed, and bumps Control::seq to L + 1 when its last block leaves.  A consumer reads
+// seq at its start and waits until the flags of the ranks it depends on have reached it.  The Jacobi kernel takes part
+// itself (fused_kernels.cu: iterate_grid_kernel processes its boundary tiles first, stores their outermost rows straight
+// into the neighbours' arrays and publishes from the tile that finishes last), so an iteration needs no exchange launch.
+constexpr int kStripFlagBase = 64;  // the strip protocol's flag words sit behind the epoch protocol's in the same exported array
+struct StripArgs {
+    PeerTable T;
+    Control* ctl;
+    const unsigned* localFlags;
+    unsigned long long timeoutNs;
+    int which;                 // output buffer of this launch (0 = predA, 1 = predB)
+    int up, down;              // neighbour ranks (-1: none)
+    unsigned tileRowBegin, tileRowEnd;  // owned tile rows of the cloth
+    unsigned rowFirst, rowLast;         // first / last owned particle row
+    int enabled;
+};
+// src[begin, begin + count) -> the same range of every peer's buffer `which`; publishes, bumps seq
+void launch_strip_push_range(cudaStream_t st, const PeerTable* table, Control* ctl, int which, const float4* src, unsigned begin,
+                             unsigned count);
+// particle rows rowFirst -> rank `up`, rowLast -> rank `down` (side particles each); publishes, bumps seq
+void launch_strip_push_rows(cudaStream_t st, const StripArgs& a, const float4* src, unsigned side);
+void launch_strip_signal(cudaStream_t st, const PeerTable* table, Control* ctl);  // no data
+void launch_strip_wait_all(cudaStream_t st, const PeerTable* table, Control* ctl, const unsigned* localFlags, unsigned long long timeoutNs);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void strip_st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned strip_ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void strip_publish(const PeerTable& T, unsigned value)
+{
+    for (int q = 0; q < T.world; q++)
+        if (q != T.rank) strip_st_release_sys(T.flags[q] + kStripFlagBase + T.rank, value);
+}
+// one thread: spin until rank q has published `value` (wall-clock timeout -> sticky error, like the wait kernel)
+__device__ __forceinline__ void strip_wait_for(const unsigned* localFlags, int q, unsigned value, Control* ctl, unsigned long long timeoutNs)
+{
+    if (q < 0 || *(volatile unsigned*)&ctl->error) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while ((int)(strip_ld_acquire_sys(localFlags + kStripFlagBase + q) - value) < 0) {
+        if ((++spins & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeoutNs) {
+                *(volatile unsigned*)&ctl->error = 1u;
+                break;
+            }
+        }
+    }
+}
+#endif
 
 }  // namespace ddpeer
 }  // namespace velvet

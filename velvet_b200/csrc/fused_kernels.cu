@@ -101,15 +101,17 @@ __global__ void __launch_bounds__(PB, 5) collide_kernel(const float4* __restrict
                                                      const unsigned* __restrict__ neighbors,
                                                      const PreparedCollider* __restrict__ colliders,
                                                      const FrameParams* __restrict__ fp, unsigned N, int selfCollision,
-                                                     const unsigned* __restrict__ subset, unsigned subsetCount)
+                                                     const unsigned* __restrict__ subset, unsigned subsetCount,
+                                                     unsigned rangeBegin)
 {
     __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
     const unsigned nc = min(fp->numColliders, VT_MAX_COLLIDERS);
     stage_colliders(s_col, colliders, nc);
-    // subset != nullptr: only the listed particles (the ones this rank owns in the domain-decomposed mode)
+    // domain-decomposed mode: only the particles this rank owns -- a list (subset != nullptr) or the contiguous range
+    // [rangeBegin, rangeBegin + subsetCount) of a strip
     const unsigned tidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tidx >= (subset ? subsetCount : N)) return;
-    const unsigned id = subset ? __ldg(subset + tidx) : tidx;
+    if (tidx >= ((subset || subsetCount) ? subsetCount : N)) return;
+    const unsigned id = subset ? __ldg(subset + tidx) : rangeBegin + tidx;
     const VtSimParams& P = fp->P;
     const float4 pi4 = predIn[id];
     const float4 xi4 = pos4[id];
@@ -634,7 +636,7 @@ __device__ __noinline__ GridBendOut grid_bend_slow(float4 p0, float4 p1, float4 
 __global__ void __launch_bounds__(256, VT_GRID_BLOCKS)
 iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const GridPlanDev plan,
                     const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
-                    const unsigned totalWork)
+                    const unsigned totalWork, const ddpeer::StripArgs strip)
 {
     constexpr unsigned NT = 256;
     extern __shared__ float4 s_mem[];  // GRID_SMEM_BYTES, carved below (more than the 48 KB a static allocation may take)
@@ -658,9 +660,47 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     const float lrs = fp->P.longRangeStretchiness;
     __syncthreads();
 
+    // ---- one strip of a decomposed cloth (dd_peer.cuh): this rank owns the tile rows [tileRowBegin, tileRowEnd) of the single
+    // cloth.  The tile rows next to another rank come FIRST in the work order: their outermost particle rows go straight into
+    // the neighbours' output arrays and the launch publishes as soon as the last of them is done, so the transfer and the
+    // neighbours' wait overlap the interior tiles.  The neighbours' rows this launch reads were published by their previous
+    // launch, early in it, for the same reason.
+    unsigned stripSeq = 0, stripBoundaryTiles = 0, stripBoundaryRows = 0;
+    bool stripHasA = false;
+    if (strip.enabled) {
+        stripHasA = strip.up >= 0;
+        const bool hasB = strip.down >= 0 && (!stripHasA || strip.tileRowEnd - 1 != strip.tileRowBegin);
+        stripBoundaryRows = (stripHasA ? 1u : 0u) + (hasB ? 1u : 0u);
+        stripBoundaryTiles = stripBoundaryRows * s_cloth[0].tilesY;
+        if (tid == 0) {
+            stripSeq = strip.ctl->seq;
+            ddpeer::strip_wait_for(strip.localFlags, strip.up, stripSeq, strip.ctl, strip.timeoutNs);
+            ddpeer::strip_wait_for(strip.localFlags, strip.down, stripSeq, strip.ctl, strip.timeoutNs);
+            if (stripBoundaryTiles == 0 && blockIdx.x == 0) ddpeer::strip_publish(strip.T, stripSeq + 1);
+        }
+        __syncthreads();
+    }
+
     // work item -> first particle of its cloth (instance included), grid side, tile origin.  One thread does this (an integer
     // division and a table walk) two tiles ahead and leaves the result in shared memory for the others.
     auto locate = [&](unsigned item) {
+        if (strip.enabled) {  // boundary tile rows first, then the interior rows in ascending order
+            const GridCloth g = s_cloth[0];
+            const unsigned r = item / g.tilesY, c = item - r * g.tilesY;
+            unsigned row;
+            if (r < stripBoundaryRows)
+                row = (r == 0 && stripHasA) ? strip.tileRowBegin : strip.tileRowEnd - 1;
+            else
+                row = strip.tileRowBegin + (r - stripBoundaryRows) + (stripHasA ? 1u : 0u);
+            GridTileCoord t;
+            t.base = g.base;
+            t.planBase = g.base;
+            t.instance = 0;
+            t.side = (int)g.side;
+            t.x0 = (int)row * GRID_TILE;
+            t.y0 = (int)c * GRID_TILE;
+            return t;
+        }
         unsigned tile = item, in = 0;
         if (inst.count > 1) {
             in = item / plan.numTiles;
@@ -860,11 +900,30 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             add(F4(oB.c0, oB.flag));
             vec3 p = V3(c00);
             if (count > 0) p += delta / count * relaxation;
-            predOutAll[s_tile[slotCur].base + local] = F4(p, c00.w);
+            const float4 result = F4(p, c00.w);
+            const unsigned idx = s_tile[slotCur].base + local;
+            predOutAll[idx] = result;
+            if (strip.enabled) {  // outermost owned rows: also into the neighbour's array, at the same index
+                if ((unsigned)gx == strip.rowFirst && strip.up >= 0) strip.T.pred[strip.which][strip.up][idx] = result;
+                if ((unsigned)gx == strip.rowLast && strip.down >= 0) strip.T.pred[strip.which][strip.down][idx] = result;
+            }
+        }
+        if (strip.enabled && w < stripBoundaryTiles) {  // the boundary tile that finishes last publishes this launch
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0 && atomicAdd(&strip.ctl->sendsDone, 1u) == stripBoundaryTiles - 1) {
+                __threadfence_system();
+                strip.ctl->sendsDone = 0;
+                ddpeer::strip_publish(strip.T, stripSeq + 1);
+            }
         }
         slotCur = slotNext;
     }
     cp_async_wait_all();
+    if (strip.enabled && tid == 0 && atomicAdd(&strip.ctl->exits, 1u) == gridDim.x - 1) {  // last block out completes the launch
+        strip.ctl->exits = 0;
+        strip.ctl->seq = stripSeq + 1;
+    }
 }
 
 __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restrict__ predIn, float4* __restrict__ pos4,
@@ -888,6 +947,7 @@ __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restric
         store3(positionsOut, id, newPos);
         store3(velocitiesOut, id, vel);
         store3(predictedOut, id, V3(pr));
+        predNext[id] = F4(newPos, po.w);  // the frame's positions as float4 (a decomposed cloth gathers them from here)
     } else {
         // PredictPositions of the next substep, .cu L51-52
         vel = vel + V3(P.gravity[0], P.gravity[1], P.gravity[2]) * dt;
@@ -934,6 +994,12 @@ __global__ void __launch_bounds__(PB) scatter_by_id_kernel(const float4* __restr
     if (i < n) dst[ids[i]] = in[i];
 }
 
+__global__ void __launch_bounds__(PB) unpack_float4_kernel(const float4* __restrict__ in, float* __restrict__ packed3, unsigned n)
+{
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id < n) store3(packed3, id, V3(in[id]));
+}
+
 __global__ void __launch_bounds__(PB) pack_float4_kernel(const float* __restrict__ packed3, float4* __restrict__ out, unsigned n)
 {
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -965,7 +1031,15 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
     const unsigned n = subset ? subsetCount : L.numParticles;
     if (!n) return;
     collide_kernel<<<pgrid(n), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
-                                                  selfCollision ? 1 : 0, subset, subsetCount);
+                                                  selfCollision ? 1 : 0, subset, subsetCount, 0u);
+}
+
+void launch_collide_range(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4, const unsigned* neighbors,
+                          const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision, unsigned begin, unsigned count)
+{
+    if (!count) return;
+    collide_kernel<<<pgrid(count), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
+                                                      selfCollision ? 1 : 0, nullptr, count, begin);
 }
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
@@ -1015,12 +1089,18 @@ unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned c
 }
 
 void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
-                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst)
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst, const ddpeer::StripArgs* strip)
 {
-    const unsigned total = plan.numTiles * inst.count;
+    ddpeer::StripArgs a{};
+    unsigned total = plan.numTiles * inst.count;
+    if (strip) {  // one strip of a decomposed cloth: the owned tile rows of the (single) cloth
+        a = *strip;
+        a.enabled = 1;
+        total = (a.tileRowEnd - a.tileRowBegin) * plan.tilesY0;
+    }
     if (!total) return;
     const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
-    iterate_grid_kernel<<<grid, 256, GRID_SMEM_BYTES, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total);
+    iterate_grid_kernel<<<grid, 256, GRID_SMEM_BYTES, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total, a);
 }
 
 unsigned configure_iterate_grid_kernel()
@@ -1103,6 +1183,11 @@ void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t w
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n)
 {
     if (n) pack_float4_kernel<<<pgrid(n), PB, 0, L.stream>>>(packed3, out, n);
+}
+
+void launch_unpack_float4(const FusedLaunch& L, const float4* in, float* packed3, unsigned n)
+{
+    if (n) unpack_float4_kernel<<<pgrid(n), PB, 0, L.stream>>>(in, packed3, n);
 }
 
 void launch_gather_by_id(const FusedLaunch& L, const float4* src, const unsigned* ids, unsigned n, float4* out)

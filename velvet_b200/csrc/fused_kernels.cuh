@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include "dd_peer.cuh"
 #include "grid_plan.hpp"
 #include "tile_plan.hpp"
 #include "vt_math.cuh"
@@ -44,6 +45,7 @@ struct GridPlanDev {
     const uint2* attachRec;   // {slot id, distance bits}
     unsigned numCloths, numTiles, hasAttach;
     unsigned residentCtas;
+    unsigned tilesY0;  // tiles along one side of cloth 0 (strip decomposition of a single cloth)
 };
 
 constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)
@@ -87,6 +89,9 @@ void launch_begin_frame(const FusedLaunch& L, const float* positions, const floa
 void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
                     const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp,
                     bool selfCollision, const unsigned* subset = nullptr, unsigned subsetCount = 0);
+// the same for the contiguous particle range [begin, begin + count) (one strip of a decomposed grid cloth)
+void launch_collide_range(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4, const unsigned* neighbors,
+                          const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision, unsigned begin, unsigned count);
 
 // One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
@@ -94,7 +99,8 @@ void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut,
 size_t iterate_smem_bytes(const TilePlanDev& plan);
 // The same iteration for grid cloths without index records (iterate_grid_kernel): bit-identical to launch_iterate.
 void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
-                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst,
+                         const ddpeer::StripArgs* strip = nullptr);  // strip: this rank's rows of a decomposed cloth (dd_peer.cuh)
 unsigned configure_iterate_grid_kernel();  // returns resident CTAs on the device
 unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
@@ -125,6 +131,7 @@ bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, co
                                    const unsigned char* ownedMask = nullptr);  // decomposed mode: lists of owned particles only
 void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t words);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
+void launch_unpack_float4(const FusedLaunch& L, const float4* in, float* packed3, unsigned n);  // xyz of n float4 -> packed float3
 // halo exchange plumbing of the domain-decomposed mode: out[i] = src[ids[i]]  /  dst[ids[i]] = in[i]
 void launch_gather_by_id(const FusedLaunch& L, const float4* src, const unsigned* ids, unsigned n, float4* out);
 void launch_scatter_by_id(const FusedLaunch& L, const float4* in, const unsigned* ids, unsigned n, float4* dst);
@@ -148,6 +155,9 @@ void launch_begin_frame(const FusedLaunch& L, const float* positions, const floa
 void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
                     const unsigned* neighbors, const PreparedCollider* colliders, const FrameParams* fp,
                     bool selfCollision, const unsigned* subset = nullptr, unsigned subsetCount = 0);
+// the same for the contiguous particle range [begin, begin + count) (one strip of a decomposed grid cloth)
+void launch_collide_range(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4, const unsigned* neighbors,
+                          const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision, unsigned begin, unsigned count);
 
 // One Jacobi iteration: SolveStretch + SolveAttachment + SolveBending + ApplyDeltas, predIn -> predOut.
 void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut, const TilePlanDev& plan,
@@ -155,7 +165,8 @@ void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut,
 size_t iterate_smem_bytes(const TilePlanDev& plan);
 // The same iteration for grid cloths without index records (iterate_grid_kernel): bit-identical to launch_iterate.
 void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
-                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst,
+                         const ddpeer::StripArgs* strip = nullptr);  // strip: this rank's rows of a decomposed cloth (dd_peer.cuh)
 unsigned configure_iterate_grid_kernel();  // returns resident CTAs on the device
 unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
@@ -176,6 +187,7 @@ struct FusedOps {
     decltype(&exact_math::launch_prepare_inputs) prepare_inputs;
     decltype(&exact_math::launch_begin_frame) begin_frame;
     decltype(&exact_math::launch_collide) collide;
+    decltype(&exact_math::launch_collide_range) collide_range;
     decltype(&exact_math::launch_iterate) iterate;
     decltype(&exact_math::launch_iterate_grid) iterate_grid;
     decltype(&exact_math::iterate_smem_bytes) iterate_smem_bytes;
@@ -186,10 +198,10 @@ struct FusedOps {
 inline FusedOps fused_ops(bool fastMath)
 {
     if (fastMath)
-        return FusedOps{&fast_math::launch_prepare_inputs, &fast_math::launch_begin_frame, &fast_math::launch_collide,
+        return FusedOps{&fast_math::launch_prepare_inputs, &fast_math::launch_begin_frame, &fast_math::launch_collide, &fast_math::launch_collide_range,
                         &fast_math::launch_iterate, &fast_math::launch_iterate_grid, &fast_math::iterate_smem_bytes, &fast_math::configure_iterate_kernel,
                         &fast_math::launch_end_substep, &fast_math::launch_normals};
-    return FusedOps{&exact_math::launch_prepare_inputs, &exact_math::launch_begin_frame, &exact_math::launch_collide,
+    return FusedOps{&exact_math::launch_prepare_inputs, &exact_math::launch_begin_frame, &exact_math::launch_collide, &exact_math::launch_collide_range,
                     &exact_math::launch_iterate, &exact_math::launch_iterate_grid, &exact_math::iterate_smem_bytes, &exact_math::configure_iterate_kernel,
                     &exact_math::launch_end_substep, &exact_math::launch_normals};
 }

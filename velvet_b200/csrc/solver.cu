@@ -715,6 +715,7 @@ void VtClothSolverGPU::ensureFusedResources()
                 m_gridDev.attachRec = m_gAttachRec;
                 m_gridDev.numCloths = (uint)m_gridPlan.cloths.size();
                 m_gridDev.numTiles = m_gridPlan.numTiles;
+                m_gridDev.tilesY0 = m_gridPlan.cloths[0].tilesY;
                 m_gridDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
                 m_gridDev.residentCtas = std::min(exact_math::configure_iterate_grid_kernel(), fast_math::configure_iterate_grid_kernel());
                 m_gridUsable = true;
@@ -861,7 +862,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
         STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
         for (int iteration = 0; iteration < P.numIterations; iteration++) {
             if (m_gridUsable)
-                ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing);
+                ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing, nullptr);
             else
                 ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp, m_instancing);
             launches++;
@@ -933,6 +934,25 @@ void VtClothSolverGPU::ddSetup(int rank, int world)
         for (int q = 0; q < world; q++)
             for (unsigned i = m_ddSendOff[q]; i < m_ddSendOff[q + 1]; i++) peerOf[i] = (unsigned char)q;
         m_ddSendPeer.upload(peerOf.empty() ? std::vector<unsigned char>(1, 0) : peerOf, m_stream);
+    }
+    // A single grid cloth is decomposed into strips of tile rows for the peer-memory transport (contiguous particle ranges,
+    // the implicit-grid Jacobi kernel with the exchange fused in); the tile-plan decomposition above keeps serving the
+    // stepped / NCCL transport and every other mesh.
+    m_ddStrip = false;
+    {
+        const char* e = getenv("VELVET_DD");
+        const bool forceTiles = e && std::string(e) == "tiles";
+        if (!forceTiles && m_gridUsable && m_gridPlan.cloths.size() == 1 && (unsigned)world <= m_gridPlan.cloths[0].tilesY) {
+            const unsigned rows = m_gridPlan.cloths[0].tilesY, side = m_gridPlan.cloths[0].side;
+            m_ddTileRow.assign(world + 1, 0);
+            for (int r = 0; r < world; r++) m_ddTileRow[r + 1] = m_ddTileRow[r] + rows / world + ((unsigned)r < rows % world ? 1u : 0u);
+            const unsigned rowFirst = m_ddTileRow[rank] * GRID_TILE;
+            const unsigned rowEnd = std::min(m_ddTileRow[rank + 1] * GRID_TILE, side);
+            std::vector<unsigned char> mask(N, 0);
+            std::fill(mask.begin() + (size_t)rowFirst * side, mask.begin() + (size_t)rowEnd * side, (unsigned char)1);
+            m_ddStripMask.upload(mask, m_stream);
+            m_ddStrip = true;
+        }
     }
     ddPeerClose();  // mappings of an earlier setup refer to buffers that may have moved
     m_ddGatherSend.allocate(m_ddMaxOwned);
@@ -1177,6 +1197,10 @@ void VtClothSolverGPU::recordDDFrame()
 {
     const VtSimParams& P = simParams;
     const uint N = P.numParticles;
+    if (m_ddStrip) {
+        recordDDStripFrame();
+        return;
+    }
     const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
     FusedLaunch L{m_stream, N};
     SpatialHashGPU& H = *m_spatialHash;
@@ -1251,6 +1275,110 @@ void VtClothSolverGPU::recordDDFrame()
         ddpeer::launch_push_owned(m_stream, T, ctl, cur, buf[cur], ownedIds, ownedCount);
         launches++;
         wait();
+        const bool last = substep == P.numSubsteps - 1;
+        ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
+                        reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
+        launches++;
+        if (!last) std::swap(cur, other);
+    }
+    ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()), m_instancing);
+    launches++;
+    VT_CUDA(cudaGetLastError());
+    m_ddGraphLaunches = launches;
+}
+
+// One frame of a strip-decomposed grid cloth (ddSetup: m_ddStrip).  Rank r owns the particle rows of its tile rows, i.e. the
+// contiguous index range [begin, begin + count).  Per substep:
+//   hash keys / sort / cell table on every rank (replicated: bit-identical lists need the global order); the candidate walk
+//   and collide only for the owned range; the two outermost owned rows to the neighbours;
+//   numIterations x iterate_grid_kernel over the owned tile rows -- the per-iteration row exchange happens INSIDE the kernel
+//   (boundary tiles first, peer stores from the epilogue, publish from the last boundary tile; the next launch waits for the
+//   neighbours' rows when it starts): no exchange launches between iterations;
+//   all-gather of the owned range (peer stores), then Finalize + Predict on every rank for every particle, which keeps
+//   pos4 / vel4 / the public buffers identical everywhere (collide reads pos4 of arbitrary neighbours).
+// The signal / wait pairs are the "I have stopped reading the buffer you are about to write" handshakes.
+void VtClothSolverGPU::recordDDStripFrame()
+{
+    const VtSimParams& P = simParams;
+    const uint N = P.numParticles;
+    const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
+    FusedLaunch L{m_stream, N};
+    SpatialHashGPU& H = *m_spatialHash;
+    const FrameParams* fp = m_frameParams;
+    const ddpeer::PeerTable* T = &m_ddPeers;
+    ddpeer::Control* ctl = m_ddCtl.data();
+    const unsigned long long timeoutNs = 20ull * 1000000000ull;
+    const int rank = m_dd.rank, world = m_dd.world;
+    const unsigned side = m_gridPlan.cloths[0].side;
+    ddpeer::StripArgs A{};
+    A.T = m_ddPeers;
+    A.ctl = ctl;
+    A.localFlags = m_ddFlags.data();
+    A.timeoutNs = timeoutNs;
+    A.up = rank > 0 ? rank - 1 : -1;
+    A.down = rank < world - 1 ? rank + 1 : -1;
+    A.tileRowBegin = m_ddTileRow[rank];
+    A.tileRowEnd = m_ddTileRow[rank + 1];
+    A.rowFirst = A.tileRowBegin * GRID_TILE;
+    A.rowLast = std::min(A.tileRowEnd * GRID_TILE, side) - 1;
+    const unsigned begin = A.rowFirst * side, count = (A.rowLast + 1 - A.rowFirst) * side;
+    float4* buf[2] = {m_predA.data(), m_predB.data()};
+    int cur = 0, other = 1;
+    int launches = 0;
+    auto wait_all = [&] {
+        ddpeer::launch_strip_wait_all(m_stream, T, ctl, m_ddFlags.data(), timeoutNs);
+        launches++;
+    };
+    auto signal = [&] {
+        ddpeer::launch_strip_signal(m_stream, T, ctl);
+        launches++;
+    };
+
+    ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()), m_slotsDev,
+                       (uint)(3 * attachSlotPositions.size()), fp);
+    ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
+                    m_pos4, m_vel4, buf[cur], m_prepared, fp);
+    launches += 2;
+    const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
+    const bool odd = RadixSorter::numPasses(maxBit) & 1;
+    for (int substep = 0; substep < P.numSubsteps; substep++) {
+        signal();  // begin_frame / end_substep are done with `other` (and with `cur` as an output): the neighbours may write rows
+        if (P.enableSelfCollision && substep % P.interleavedHash == 0) {
+            uint* k0 = odd ? m_keysAlt.data() : H.particleHash.data();
+            uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
+            uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
+            uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
+            exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing);
+            m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            launches += 2 + m_sorter.lastLaunchCount();
+            VtHashParams hp = H.MakeParams(N, P.particleDiameter);
+            if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, m_sorted,
+                                                          hp, m_instancing, m_ddStripMask)) {
+                launches += 2;
+            } else {
+                exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
+                launches++;
+            }
+        }
+        ops.collide_range(L, buf[cur], buf[other], m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0, begin, count);
+        launches++;
+        wait_all();  // every peer is past its end_substep: its `other` may take rows
+        A.which = other;
+        ddpeer::launch_strip_push_rows(m_stream, A, buf[other], side);
+        launches++;
+        std::swap(cur, other);
+        for (int iteration = 0; iteration < P.numIterations; iteration++) {
+            A.which = other;
+            ops.iterate_grid(L, buf[cur], buf[other], m_gridDev, m_slotsDev, fp, m_instancing, &A);
+            launches++;
+            std::swap(cur, other);
+        }
+        signal();    // my iterations are over ...
+        wait_all();  // ... and so are everybody's: nobody reads the buffer the ranges are gathered into
+        ddpeer::launch_strip_push_range(m_stream, T, ctl, cur, buf[cur], begin, count);
+        launches++;
+        wait_all();
         const bool last = substep == P.numSubsteps - 1;
         ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
                         reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);

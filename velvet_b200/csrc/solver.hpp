@@ -220,6 +220,10 @@ private:
     DeviceBuffer<float4> m_ddSendBuf, m_ddRecvBuf, m_ddGatherSend, m_ddGatherRecv;
     float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
     void recordDDFrame();
+    void recordDDStripFrame();
+    bool m_ddStrip = false;                 // single grid cloth: strips of tile rows, exchange fused into iterate_grid_kernel
+    std::vector<unsigned> m_ddTileRow;      // [world + 1] tile rows of every rank
+    DeviceBuffer<unsigned char> m_ddStripMask;
     void ddValidateFrame() const;
     DeviceBuffer<unsigned> m_ddFlags;
     DeviceBuffer<ddpeer::Control> m_ddCtl;
