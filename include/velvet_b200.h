@@ -39,7 +39,11 @@ extern "C" {
 
 /* ------------------------------------------------------------------ PODs (layout == reference) */
 
-/* Common.hpp L19-47, sizeof == 80. */
+/* Common.hpp L19-47, sizeof == 80.  A translation unit that already sees the reference's own (global-namespace) struct
+ * VtSimParams -- the kernel-level drop-in shim, velvet_b200/csrc/dropin/VelvetB200Shim.cpp -- defines
+ * VELVET_B200_USE_REFERENCE_SIMPARAMS before including this header; the prototypes below then take the reference's type,
+ * whose layout is the same (static_assert in the shim). */
+#ifndef VELVET_B200_USE_REFERENCE_SIMPARAMS
 typedef struct VtSimParams {
     int32_t numSubsteps;           /* 0  */
     int32_t numIterations;         /* 4  */
@@ -61,6 +65,7 @@ typedef struct VtSimParams {
     float particleDiameterScalar;  /* 72 */
     float hashCellSizeScalar;      /* 76 */
 } VtSimParams;
+#endif
 
 /* Common.hpp L113-118 */
 typedef enum VtColliderType { VT_COLLIDER_SPHERE = 0, VT_COLLIDER_PLANE = 1, VT_COLLIDER_CUBE = 2 } VtColliderType;

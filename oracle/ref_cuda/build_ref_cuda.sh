@@ -33,3 +33,16 @@ wait
 "$NVCC" -shared -o "$OUT/libvelvet_refcuda.so" "$TMP/VtClothSolverGPU.o" "$TMP/SpatialHashGPU.o" "$TMP/ref_driver.o" \
   -gencode arch=compute_100a,code=sm_100a -cudart static
 echo "$OUT/libvelvet_refcuda.so"
+
+# ---- the drop-in proof (tests/test_dropin_gpu.py): the SAME reference-side orchestration (ref_driver.cu over the reference's
+# VtBuffer / Timer / .cuh declarations), but the reference's two .cu files are replaced by the shim of INTEGRATION.md (way A),
+# which forwards the twelve seam functions to libvelvet_b200.so.
+SHIM="$HERE/../../velvet_b200/csrc/dropin/VelvetB200Shim.cpp"
+LIBDIR="$HERE/../../velvet_b200/lib"
+if [ -f "$SHIM" ] && [ -f "$LIBDIR/libvelvet_b200.so" ]; then
+  cp "$SHIM" "$TMP/VelvetB200Shim.cu"
+  "$NVCC" "${FLAGS[@]}" -I "$HERE/../../include" -c "$TMP/VelvetB200Shim.cu" -o "$TMP/VelvetB200Shim.o"
+  "$NVCC" -shared -o "$OUT/libvelvet_dropin.so" "$TMP/VelvetB200Shim.o" "$TMP/ref_driver.o" \
+    -gencode arch=compute_100a,code=sm_100a -cudart static -L "$LIBDIR" -lvelvet_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../velvet_b200/lib'
+  echo "$OUT/libvelvet_dropin.so"
+fi

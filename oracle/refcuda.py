@@ -11,7 +11,10 @@ from . import o1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libvelvet_refcuda.so")
-_LIB = None
+# the same reference-side driver with the reference's two .cu files REPLACED by the drop-in shim over libvelvet_b200.so
+# (velvet_b200/csrc/dropin/VelvetB200Shim.cpp; built by oracle/ref_cuda/build_ref_cuda.sh; tests/test_dropin_gpu.py)
+SO_DROPIN = os.path.join(_HERE, "_ref", "libvelvet_dropin.so")
+_LIBS = {}
 
 BUF = dict(o1.BUF)
 _DTYPE = {"indices": np.uint32, "deltaCounts": np.int32, "stretchIndices": np.int32, "bendIndices": np.uint32,
@@ -19,14 +22,13 @@ _DTYPE = {"indices": np.uint32, "deltaCounts": np.int32, "stretchIndices": np.in
           "particleIndex": np.uint32, "cellStart": np.uint32, "cellEnd": np.uint32}
 
 
-def available() -> bool:
-    return os.path.exists(SO)
+def available(so: str = SO) -> bool:
+    return os.path.exists(so)
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(SO)
+def lib(so: str = SO):
+    if so not in _LIBS:
+        L = C.CDLL(so)
         v = C.c_void_p
         L.refcuda_create.restype = v
         L.refcuda_create.argtypes = [v]
@@ -48,8 +50,8 @@ def lib():
         L.refcuda_label_ms.argtypes = [C.c_int]
         L.refcuda_buffer.restype = v
         L.refcuda_buffer.argtypes = [v, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-        _LIB = L
-    return _LIB
+        _LIBS[so] = L
+    return _LIBS[so]
 
 
 def _fp(a):
@@ -59,8 +61,8 @@ def _fp(a):
 class RefCudaSolver:
     """VtClothSolverGPU driven through the reference's own kernels."""
 
-    def __init__(self, params: o1.SimParams):
-        self._L = lib()
+    def __init__(self, params: o1.SimParams, so: str = SO):
+        self._L = lib(so)
         self._h = self._L.refcuda_create(C.byref(params))
 
     def __del__(self):

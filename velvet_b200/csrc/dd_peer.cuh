@@ -65,6 +65,7 @@ struct StripArgs {
     unsigned tileRowBegin, tileRowEnd;  // owned tile rows of the cloth
     unsigned rowFirst, rowLast;         // first / last owned particle row
     int enabled;
+    int gatherAll;             // this launch also stores EVERY owned result into every peer (the per-substep all-gather, fused)
 };
 // src[begin, begin + count) -> the same range of every peer's buffer `which`; publishes, bumps seq
 void launch_strip_push_range(cudaStream_t st, const PeerTable* table, Control* ctl, int which, const float4* src, unsigned begin,

@@ -903,9 +903,14 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             const float4 result = F4(p, c00.w);
             const unsigned idx = s_tile[slotCur].base + local;
             predOutAll[idx] = result;
-            if (strip.enabled) {  // outermost owned rows: also into the neighbour's array, at the same index
-                if ((unsigned)gx == strip.rowFirst && strip.up >= 0) strip.T.pred[strip.which][strip.up][idx] = result;
-                if ((unsigned)gx == strip.rowLast && strip.down >= 0) strip.T.pred[strip.which][strip.down][idx] = result;
+            if (strip.enabled) {
+                if (strip.gatherAll) {  // last iteration of a substep: the all-gather of the results rides on the epilogue
+                    for (int q = 0; q < strip.T.world; q++)
+                        if (q != strip.T.rank) strip.T.pred[strip.which][q][idx] = result;
+                } else {  // outermost owned rows: also into the neighbour's array, at the same index
+                    if ((unsigned)gx == strip.rowFirst && strip.up >= 0) strip.T.pred[strip.which][strip.up][idx] = result;
+                    if ((unsigned)gx == strip.rowLast && strip.down >= 0) strip.T.pred[strip.which][strip.down][idx] = result;
+                }
             }
         }
         if (strip.enabled && w < stripBoundaryTiles) {  // the boundary tile that finishes last publishes this launch

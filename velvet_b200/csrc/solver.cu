@@ -1370,14 +1370,23 @@ void VtClothSolverGPU::recordDDStripFrame()
         std::swap(cur, other);
         for (int iteration = 0; iteration < P.numIterations; iteration++) {
             A.which = other;
+            // The last iteration stores every result into every peer: the per-substep all-gather overlaps the Jacobi math.
+            // Nobody reads those rows of that buffer meanwhile: iterations only read the rows next to their own strip, and a
+            // neighbour has published (i.e. finished reading them) before this launch passes its wait.
+            A.gatherAll = iteration == P.numIterations - 1 ? 1 : 0;
             ops.iterate_grid(L, buf[cur], buf[other], m_gridDev, m_slotsDev, fp, m_instancing, &A);
             launches++;
             std::swap(cur, other);
         }
-        signal();    // my iterations are over ...
-        wait_all();  // ... and so are everybody's: nobody reads the buffer the ranges are gathered into
-        ddpeer::launch_strip_push_range(m_stream, T, ctl, cur, buf[cur], begin, count);
-        launches++;
+        A.gatherAll = 0;
+        if (P.numIterations <= 0) {  // nothing to ride on: gather the collide output with a launch of its own
+            signal();
+            wait_all();
+            ddpeer::launch_strip_push_range(m_stream, T, ctl, cur, buf[cur], begin, count);
+            launches++;
+        } else {
+            signal();  // stream order: the whole last iteration, all its peer stores included, is behind this
+        }
         wait_all();
         const bool last = substep == P.numSubsteps - 1;
         ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
