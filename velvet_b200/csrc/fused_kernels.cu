@@ -20,6 +20,8 @@
 #include "fused_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <utility>
 
 #include "hash_kernels.cuh"
 #include "vt_buffer.hpp"
@@ -41,6 +43,33 @@ namespace {
 constexpr int PB = 256;  // threads per CTA for per-particle kernels
 inline unsigned pgrid(unsigned n) { return (n + PB - 1) / PB; }
 
+// Launch with programmatic stream serialization (see vt_math.cuh: vt_pdl_wait): inside the frame's CUDA graph the edge to
+// the previous kernel becomes a programmatic dependency, which hides most of the ~4 us a full kernel-to-kernel dependency
+// costs (81 nodes per frame: it was two thirds of a 65k-particle frame).  VELVET_PDL=0 launches the ordinary way.
+inline bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("VELVET_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    VT_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 __device__ __forceinline__ float4 F4(vec3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 
 __device__ __forceinline__ void stage_colliders(PreparedCollider* s_col, const PreparedCollider* __restrict__ g_col,
@@ -58,6 +87,8 @@ __global__ void prepare_inputs_kernel(const VtSDFCollider* __restrict__ collider
                                       const float* __restrict__ slotPositions, float* __restrict__ slotPositionsOut,
                                       unsigned numSlotFloats, const FrameParams* __restrict__ fp)
 {
+    vt_pdl_trigger();
+    vt_pdl_wait();
     const unsigned i = threadIdx.x;
     if (i < min(fp->numColliders, VT_MAX_COLLIDERS)) prepare_collider(colliders[i], prepared[i]);
     for (unsigned k = i; k < numSlotFloats; k += blockDim.x) slotPositionsOut[k] = slotPositions[k];
@@ -78,6 +109,8 @@ __global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict
                                                          const PreparedCollider* __restrict__ colliders,
                                                          const FrameParams* __restrict__ fp, unsigned n)
 {
+    vt_pdl_trigger();
+    vt_pdl_wait();
     __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
     const unsigned nc = min(fp->numColliders, VT_MAX_COLLIDERS);
     stage_colliders(s_col, colliders, nc);
@@ -104,6 +137,8 @@ __global__ void __launch_bounds__(PB, 5) collide_kernel(const float4* __restrict
                                                      const unsigned* __restrict__ subset, unsigned subsetCount,
                                                      unsigned rangeBegin)
 {
+    vt_pdl_trigger();
+    vt_pdl_wait();
     __shared__ PreparedCollider s_col[VT_MAX_COLLIDERS];
     const unsigned nc = min(fp->numColliders, VT_MAX_COLLIDERS);
     stage_colliders(s_col, colliders, nc);
@@ -397,6 +432,8 @@ iterate_tile_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
                     const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
                     const unsigned totalWork)
 {
+    vt_pdl_trigger();
+    vt_pdl_wait();
     constexpr unsigned T = NT;  // stride of every cooperative loop
     constexpr unsigned TD_WORDS = sizeof(TileDesc) / 4;
     extern __shared__ float4 s_mem[];
@@ -638,6 +675,7 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
                     const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
                     const unsigned totalWork, const ddpeer::StripArgs strip)
 {
+    vt_pdl_trigger();  // the next kernel may set itself up while this one runs
     constexpr unsigned NT = 256;
     extern __shared__ float4 s_mem[];  // GRID_SMEM_BYTES, carved below (more than the 48 KB a static allocation may take)
     float4(*const s_sp)[GRID_V * GRID_V] = reinterpret_cast<float4(*)[GRID_V * GRID_V]>(s_mem);
@@ -658,6 +696,9 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     const float xpbd_bend = fp->xpbdBend;
     const float relaxation = fp->P.relaxationFactor;
     const float lrs = fp->P.longRangeStretchiness;
+    // everything above reads data that no kernel of the frame writes (cloth table, frame parameters); the predecessor's output
+    // (predIn, and the exchange state of a decomposed cloth) is first touched below
+    vt_pdl_wait();
     __syncthreads();
 
     // ---- one strip of a decomposed cloth (dd_peer.cuh): this rank owns the tile rows [tileRowBegin, tileRowEnd) of the single
@@ -938,6 +979,8 @@ __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restric
                                                          float* __restrict__ predictedOut,
                                                          const FrameParams* __restrict__ fp, unsigned n)
 {
+    vt_pdl_trigger();
+    vt_pdl_wait();
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
     const VtSimParams& P = fp->P;
@@ -968,6 +1011,8 @@ __global__ void __launch_bounds__(PB) normals_kernel(const float4* __restrict__ 
                                                      const unsigned* __restrict__ vtxTris, float* __restrict__ normalsOut,
                                                      unsigned n)
 {
+    vt_pdl_trigger();
+    vt_pdl_wait();
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
     pos4 += (size_t)blockIdx.y * n;  // instance (indices / CSR are per-instance local)
@@ -1019,14 +1064,14 @@ __global__ void __launch_bounds__(PB) pack_float4_kernel(const float* __restrict
 void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders, PreparedCollider* prepared,
                            const float* slotPositions, float* slotPositionsOut, unsigned numSlotFloats, const FrameParams* fp)
 {
-    prepare_inputs_kernel<<<1, 256, 0, L.stream>>>(colliders, prepared, slotPositions, slotPositionsOut, numSlotFloats, fp);
+    launch_pdl(prepare_inputs_kernel, dim3(1), dim3(256), 0, L.stream, colliders, prepared, slotPositions, slotPositionsOut, numSlotFloats, fp);
 }
 
 void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
                         float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders, const FrameParams* fp)
 {
-    begin_frame_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(positions, velocities, invMasses, pos4, vel4, pred,
-                                                                   colliders, fp, L.numParticles);
+    launch_pdl(begin_frame_kernel, dim3(pgrid(L.numParticles)), dim3(PB), 0, L.stream, positions, velocities, invMasses, pos4, vel4, pred,
+               colliders, fp, L.numParticles);
 }
 
 void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4,
@@ -1035,16 +1080,16 @@ void launch_collide(const FusedLaunch& L, const float4* predIn, float4* predOut,
 {
     const unsigned n = subset ? subsetCount : L.numParticles;
     if (!n) return;
-    collide_kernel<<<pgrid(n), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
-                                                  selfCollision ? 1 : 0, subset, subsetCount, 0u);
+    launch_pdl(collide_kernel, dim3(pgrid(n)), dim3(PB), 0, L.stream, predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
+               selfCollision ? 1 : 0, subset, subsetCount, 0u);
 }
 
 void launch_collide_range(const FusedLaunch& L, const float4* predIn, float4* predOut, const float4* pos4, const unsigned* neighbors,
                           const PreparedCollider* colliders, const FrameParams* fp, bool selfCollision, unsigned begin, unsigned count)
 {
     if (!count) return;
-    collide_kernel<<<pgrid(count), PB, 0, L.stream>>>(predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
-                                                      selfCollision ? 1 : 0, nullptr, count, begin);
+    launch_pdl(collide_kernel, dim3(pgrid(count)), dim3(PB), 0, L.stream, predIn, predOut, pos4, neighbors, colliders, fp, L.numParticles,
+               selfCollision ? 1 : 0, (const unsigned*)nullptr, count, begin);
 }
 
 size_t iterate_smem_bytes(const TilePlanDev& plan)
@@ -1068,7 +1113,7 @@ void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut,
     const size_t smem = iterate_smem_bytes(plan);
 #define VT_LAUNCH(LOG2T, NT)                                                                                               \
     if (plan.threads == (1u << LOG2T) && plan.ctaThreads == NT) {                                                          \
-        iterate_tile_kernel<LOG2T, NT><<<grid, NT, smem, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total); \
+        launch_pdl(iterate_tile_kernel<LOG2T, NT>, dim3(grid), dim3(NT), smem, L.stream, predIn, predOut, plan, attachSlotPositions, fp, inst, total); \
         return;                                                                                                            \
     }
     VT_ITERATE_VARIANTS(VT_LAUNCH)
@@ -1105,7 +1150,7 @@ void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* pre
     }
     if (!total) return;
     const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
-    iterate_grid_kernel<<<grid, 256, GRID_SMEM_BYTES, L.stream>>>(predIn, predOut, plan, attachSlotPositions, fp, inst, total, a);
+    launch_pdl(iterate_grid_kernel, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut, plan, attachSlotPositions, fp, inst, total, a);
 }
 
 unsigned configure_iterate_grid_kernel()
@@ -1122,15 +1167,15 @@ unsigned configure_iterate_grid_kernel()
 void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext, bool last,
                         float* positionsOut, float* velocitiesOut, float* predictedOut, const FrameParams* fp)
 {
-    end_substep_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(predIn, pos4, vel4, predNext, last ? 1 : 0, positionsOut,
-                                                                   velocitiesOut, predictedOut, fp, L.numParticles);
+    launch_pdl(end_substep_kernel, dim3(pgrid(L.numParticles)), dim3(PB), 0, L.stream, predIn, pos4, vel4, predNext, last ? 1 : 0, positionsOut,
+               velocitiesOut, predictedOut, fp, L.numParticles);
 }
 
 void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* indices, const unsigned* vtxTriOff,
                     const unsigned* vtxTris, float* normalsOut, Instancing inst)
 {
-    normals_kernel<<<dim3(pgrid(inst.particles), inst.count), PB, 0, L.stream>>>(pos4, indices, vtxTriOff, vtxTris, normalsOut,
-                                                                                   inst.particles);
+    launch_pdl(normals_kernel, dim3(pgrid(inst.particles), inst.count), dim3(PB), 0, L.stream, pos4, indices, vtxTriOff, vtxTris, normalsOut,
+               inst.particles);
 }
 
 #if !VT_FAST_MATH  // the spatial hash is integer work: one (exact) build only
