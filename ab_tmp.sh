@@ -1,19 +1,12 @@
-mkdir -p gpurun_out/r2h
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-run() { name=$1; res=$2; shift; shift
-  env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-sub-records --resolution $res > gpurun_out/r2h/bench_$name.json 2> gpurun_out/r2h/bench_$name.err
-  python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/r2h/bench_$name.json"))
-    print("$name", "ms/frame", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["ms_per_step"],4), "iter_us", round(d["roofline"]["launch_ms"]*1e3,2), "fast", round(d["other_math_mode"]["ms_per_step"],4))
-except Exception as e:
-    print("$name FAILED", e)
+mkdir -p gpurun_out/r2i
+timeout 900 python -m pytest tests/test_decomposed_gpu.py tests/test_solver_gpu.py -m gpu -x -q 2>&1 | tail -5
+python - <<'PY'
+import time, numpy as np
+import velvet_b200 as vb
+for R in (1023, 4095):
+    p = vb.default_params(); p.numSubsteps, p.numIterations = 5, 10
+    t0=time.perf_counter(); g = vb.build_scene(R, p); t1=time.perf_counter()
+    g.UpdateColliders(vb.sphere_plane_colliders()); g.Simulate(); t2=time.perf_counter()
+    print(R, "register %.3f s, first Simulate (plans + graph) %.3f s" % (t1-t0, t2-t1), "kernel", g.iterateKernel)
+    g.close()
 PY
-}
-run pdl_1m 1023 VELVET_PDL=1
-run nopdl_1m 1023 VELVET_PDL=0
-run pdl_256 255 VELVET_PDL=1
-run nopdl_256 255 VELVET_PDL=0
-run pdl_32 31 VELVET_PDL=1
-run nopdl_32 31 VELVET_PDL=0

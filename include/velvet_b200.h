@@ -306,8 +306,15 @@ VELVET_API int velvet_solver_add_cloth_instances(VelvetSolver* s, int resolution
                                                  const int* attachedIndices, int numAttached);
 
 /* ---- One large cloth decomposed over several GPUs (north_star mode 2).  Every rank (one process per GPU) registers the
- * same cloth on its own handle and calls velvet_solver_dd_setup(rank, world); rank r then owns a contiguous range of the
- * Morton-ordered Jacobi tiles.  A frame is driven step by step with velvet_solver_dd_step; the caller moves the bytes:
+ * same cloth on its own handle and calls velvet_solver_dd_setup(rank, world).
+ *
+ * Strip form (a single grid cloth, peer transport below): rank r owns a contiguous range of particle rows -- a contiguous
+ * index range, "decomposed by particle index range" -- and the Jacobi kernel exchanges the boundary rows itself; dd_info then
+ * reports tile ROWS in tileBegin / tileEnd / numTiles and no staging buffers.
+ *
+ * Tile form (any mesh; the stepped schedule): rank r owns a contiguous range of the Morton-ordered Jacobi tiles.  It is set
+ * up when first needed (velvet_solver_dd_prepare_stepped, dd_offsets or the first dd_step).  A frame is driven step by step
+ * with velvet_solver_dd_step; the caller moves the bytes:
  *   ITERATE_OWNED  -> send sendBuf[sendOffsets[q] .. sendOffsets[q+1]) to rank q, receive recvBuf[recvOffsets[q] ..) from q
  *   ITERATE_FINISH
  *   GATHER_PACK    -> all-gather gatherSend (maxOwnedCount float4 per rank) into gatherRecv -> GATHER_UNPACK
@@ -334,6 +341,8 @@ VELVET_API int velvet_solver_dd_setup(VelvetSolver* s, int rank, int world);
 VELVET_API int velvet_solver_dd_info(VelvetSolver* s, VelvetDDInfo* out);
 /* per-peer element offsets into sendBuf / recvBuf: arrays of world + 1 entries */
 VELVET_API int velvet_solver_dd_offsets(VelvetSolver* s, unsigned* sendOffsets, unsigned* recvOffsets);
+/* Sets up the tile form (exchange lists, staging buffers) if dd_setup chose the strip form; dd_info is valid for it afterwards. */
+VELVET_API int velvet_solver_dd_prepare_stepped(VelvetSolver* s);
 VELVET_API int velvet_solver_dd_step(VelvetSolver* s, int op, int arg, float farg);
 /* NVLink peer-memory transport (the fast path; velvet_b200/csrc/dd_peer.cuh).  After dd_setup every rank exports a blob of
  * CUDA IPC handles (its two predicted-position arrays + a flag array), the caller all-gathers the blobs (any transport:

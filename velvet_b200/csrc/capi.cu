@@ -400,6 +400,22 @@ int velvet_solver_dd_info(VelvetSolver* s, VelvetDDInfo* out)
 {
     VT_API_BEGIN
     VT_REQUIRE(s && out, "bad argument");
+    if (s->impl.ddIsStrip() && !s->impl.ddTilesReady()) {  // strip form only: no staging buffers, rows travel by peer stores
+        unsigned si[6];
+        s->impl.ddStripInfo(si);
+        const ExchangePlan& x = s->impl.ddPlan();
+        std::memset(out, 0, sizeof(*out));
+        out->rank = x.rank;
+        out->world = x.world;
+        out->tileBegin = si[0];
+        out->tileEnd = si[1];
+        out->numTiles = si[2];
+        out->ownedCount = si[3];
+        out->maxOwnedCount = si[4];
+        out->sendTotal = si[5];
+        out->recvTotal = si[5];
+        return VELVET_OK;
+    }
     const ExchangePlan& x = s->impl.ddPlan();
     const VtClothSolverGPU::DDBuffers b = s->impl.ddBuffers();
     out->rank = x.rank;
@@ -422,7 +438,7 @@ int velvet_solver_dd_offsets(VelvetSolver* s, unsigned* sendOffsets, unsigned* r
 {
     VT_API_BEGIN
     VT_REQUIRE(s && sendOffsets && recvOffsets, "bad argument");
-    s->impl.ddBuffers();  // throws unless set up
+    s->impl.ddBuffers();  // throws unless set up; brings the tile form (and its exchange lists) into being
     const ExchangePlan& x = s->impl.ddPlan();
     unsigned so = 0, ro = 0;
     for (int q = 0; q < x.world; q++) {
@@ -433,6 +449,14 @@ int velvet_solver_dd_offsets(VelvetSolver* s, unsigned* sendOffsets, unsigned* r
     }
     sendOffsets[x.world] = so;
     recvOffsets[x.world] = ro;
+    VT_API_END
+}
+
+int velvet_solver_dd_prepare_stepped(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.ddEnsureTiles();
     VT_API_END
 }
 

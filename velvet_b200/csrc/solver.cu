@@ -584,39 +584,11 @@ void VtClothSolverGPU::simulateSeam(float frameTime, Stage* t)
     m_lastLaunches = launches;
 }
 
-// ---- fused pipeline resources: SoA state, tile plan, vertex->triangle CSR (rebuilt when the topology changes)
-void VtClothSolverGPU::ensureFusedResources()
+// ---- the record-driven tile plan and its device copy (tile_plan.hpp); false + m_fallbackReason when the mesh cannot be tiled
+bool VtClothSolverGPU::buildTilePlan()
 {
-    if (!m_topologyDirty) {
-        if (m_initDirty && m_fusedUsable) {  // initialPositions were edited in place: refresh the float4 copy the hash filters with
-            exact_math::launch_pack_float4(FusedLaunch{m_stream, simParams.numParticles},
-                                           reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4,
-                                           simParams.numParticles);
-            m_initDirty = false;
-        }
-        return;
-    }
-    m_initDirty = false;  // the rebuild below packs the current initialPositions
-    Synchronize();
-    const uint N = simParams.numParticles;
-    if (!m_instanced) m_instancing = Instancing{1u, N, (uint)attachSlotPositions.size()};
-    const uint planN = m_instancing.particles;  // the tile plan / vertex CSR cover one instance
-    m_fusedUsable = false;
-    m_fallbackReason.clear();
-    if (m_graphExec) {
-        cudaGraphExecDestroy(m_graphExec);
-        m_graphExec = nullptr;
-    }
-    if (m_graph) {
-        cudaGraphDestroy(m_graph);
-        m_graph = nullptr;
-    }
-    m_topologyDirty = false;
-    if (N == 0) {
-        m_fallbackReason = "no particles";
-        return;
-    }
-
+    const uint planN = m_instancing.particles;
+    cudaStream_t st = m_stream;
     const int tileSize = m_tileSize ? m_tileSize : 256;  // power of two: the kernel is specialised on log2(tile)
     m_plan = build_tile_plan(planN, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), stretchIndices.data(),
                              stretchLengths.data(), stretchLengths.size(), bendIndices.data(), bendAngles.data(),
@@ -624,20 +596,8 @@ void VtClothSolverGPU::ensureFusedResources()
                              attachParticleIDs.size(), tileSize);
     if (!m_plan.valid) {
         m_fallbackReason = m_plan.whyInvalid;
-        return;
+        return false;
     }
-    for (size_t i = 0; i < attachSlotIDs.size(); i++)
-        if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= (size_t)m_instancing.slots) {
-            m_fallbackReason = "attach slot index out of range";
-            return;
-        }
-    for (size_t i = 0; i < indices.size(); i++)
-        if (indices[i] >= planN) {
-            m_fallbackReason = "triangle index out of range";
-            return;
-        }
-
-    cudaStream_t st = m_stream;
     m_dTiles.upload(m_plan.tiles, st);
     m_dOwned.upload(m_plan.ownedIds, st);
     m_dHalo.upload(m_plan.haloIds, st);
@@ -677,11 +637,72 @@ void VtClothSolverGPU::ensureFusedResources()
     const size_t smem = exact_math::iterate_smem_bytes(m_planDev);
     if (smem > 200 * 1024) {
         m_fallbackReason = "tile needs more than 200 KB of shared memory";
-        return;
+        return false;
     }
     m_planDev.residentCtas = std::min(exact_math::configure_iterate_kernel(smem, m_planDev.threads, m_planDev.ctaThreads),
                                       fast_math::configure_iterate_kernel(smem, m_planDev.threads, m_planDev.ctaThreads));
 
+    m_tilePlanBuilt = true;
+    return true;
+}
+
+void VtClothSolverGPU::ensureTilePlan()
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    ensureFusedResources();
+    if (!m_fusedUsable) throw Error(VELVET_ERR_UNSUPPORTED, "the fused pipeline is unavailable (" + m_fallbackReason + ")");
+    if (m_tilePlanBuilt) return;
+    Synchronize();
+    if (!buildTilePlan()) throw Error(VELVET_ERR_UNSUPPORTED, "the mesh cannot be tiled (" + m_fallbackReason + ")");
+    VT_CUDA(cudaStreamSynchronize(m_stream));
+}
+
+// ---- fused pipeline resources: SoA state, tile plan, vertex->triangle CSR (rebuilt when the topology changes)
+void VtClothSolverGPU::ensureFusedResources()
+{
+    if (!m_topologyDirty) {
+        if (m_initDirty && m_fusedUsable) {  // initialPositions were edited in place: refresh the float4 copy the hash filters with
+            exact_math::launch_pack_float4(FusedLaunch{m_stream, simParams.numParticles},
+                                           reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4,
+                                           simParams.numParticles);
+            m_initDirty = false;
+        }
+        return;
+    }
+    m_initDirty = false;  // the rebuild below packs the current initialPositions
+    Synchronize();
+    const uint N = simParams.numParticles;
+    if (!m_instanced) m_instancing = Instancing{1u, N, (uint)attachSlotPositions.size()};
+    const uint planN = m_instancing.particles;  // the tile plan / vertex CSR cover one instance
+    m_fusedUsable = false;
+    m_fallbackReason.clear();
+    if (m_graphExec) {
+        cudaGraphExecDestroy(m_graphExec);
+        m_graphExec = nullptr;
+    }
+    if (m_graph) {
+        cudaGraphDestroy(m_graph);
+        m_graph = nullptr;
+    }
+    m_topologyDirty = false;
+    if (N == 0) {
+        m_fallbackReason = "no particles";
+        return;
+    }
+
+    for (size_t i = 0; i < attachSlotIDs.size(); i++)
+        if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= (size_t)m_instancing.slots) {
+            m_fallbackReason = "attach slot index out of range";
+            return;
+        }
+    for (size_t i = 0; i < indices.size(); i++)
+        if (indices[i] >= planN) {
+            m_fallbackReason = "triangle index out of range";
+            return;
+        }
+
+    cudaStream_t st = m_stream;
+    m_tilePlanBuilt = false;
     // grid cloths carrying exactly the reference's constraint pattern get the implicit-grid kernel (grid_plan.hpp)
     m_gridUsable = false;
     m_gridPlan = GridPlan{};
@@ -722,6 +743,10 @@ void VtClothSolverGPU::ensureFusedResources()
             }
         }
     }
+
+    // the record-driven tile plan (0.35 s of host work per million particles) only when the grid kernel cannot run; the
+    // decomposed tile form and the plan accessors build it on demand (ensureTilePlan)
+    if (!m_gridUsable && !buildTilePlan()) return;
 
     // vertex -> incident triangles, ascending triangle id
     {
@@ -896,6 +921,43 @@ void VtClothSolverGPU::ddSetup(int rank, int world)
     if (simParams.numParticles == 0) throw Error(VELVET_ERR_STATE, "ddSetup: no cloth registered");
     ensureFusedResources();
     if (!m_fusedUsable) throw Error(VELVET_ERR_UNSUPPORTED, "ddSetup: the fused pipeline is unavailable (" + m_fallbackReason + ")");
+    const uint N = simParams.numParticles;
+    m_dd = ExchangePlan{};
+    m_dd.rank = rank;
+    m_dd.world = world;
+    m_ddTilesReady = false;
+    // A single grid cloth is decomposed into strips of tile rows for the peer-memory transport (contiguous particle ranges,
+    // the implicit-grid Jacobi kernel with the exchange fused in); the tile-plan decomposition (ddSetupTiles) serves the
+    // stepped / NCCL transport and every other mesh, and is set up only when one of those is used.
+    m_ddStrip = false;
+    {
+        const char* e = getenv("VELVET_DD");
+        const bool forceTiles = e && std::string(e) == "tiles";
+        if (!forceTiles && m_gridUsable && m_gridPlan.cloths.size() == 1 && (unsigned)world <= m_gridPlan.cloths[0].tilesY) {
+            const unsigned rows = m_gridPlan.cloths[0].tilesY, side = m_gridPlan.cloths[0].side;
+            m_ddTileRow.assign(world + 1, 0);
+            for (int r = 0; r < world; r++) m_ddTileRow[r + 1] = m_ddTileRow[r] + rows / world + ((unsigned)r < rows % world ? 1u : 0u);
+            const unsigned rowFirst = m_ddTileRow[rank] * GRID_TILE;
+            const unsigned rowEnd = std::min(m_ddTileRow[rank + 1] * GRID_TILE, side);
+            std::vector<unsigned char> mask(N, 0);
+            std::fill(mask.begin() + (size_t)rowFirst * side, mask.begin() + (size_t)rowEnd * side, (unsigned char)1);
+            m_ddStripMask.upload(mask, m_stream);
+            m_ddStrip = true;
+        }
+    }
+    if (!m_ddStrip) ddSetupTiles();
+    ddPeerClose();  // mappings of an earlier setup refer to buffers that may have moved
+    Synchronize();
+    m_ddReady = true;
+}
+
+// The tile-plan form: rank r owns a contiguous range of the Morton-ordered tiles of the record-driven plan.  Needed by the
+// stepped ABI (NCCL transport, LocalShards) and by every mesh that is not a single grid cloth; a strip-decomposed cloth sets
+// it up lazily, so that a 16.7 M-particle cloth over NVLink never builds the host-side tile plan at all.
+void VtClothSolverGPU::ddSetupTiles()
+{
+    ensureTilePlan();
+    const int rank = m_dd.rank, world = m_dd.world;
     if ((unsigned)world > m_plan.tiles.size()) throw Error(VELVET_ERR_INVALID_ARGUMENT, "ddSetup: more ranks than tiles");
     const uint N = simParams.numParticles;
     m_dd = build_exchange_plan(m_plan, N, rank, world);
@@ -935,35 +997,40 @@ void VtClothSolverGPU::ddSetup(int rank, int world)
             for (unsigned i = m_ddSendOff[q]; i < m_ddSendOff[q + 1]; i++) peerOf[i] = (unsigned char)q;
         m_ddSendPeer.upload(peerOf.empty() ? std::vector<unsigned char>(1, 0) : peerOf, m_stream);
     }
-    // A single grid cloth is decomposed into strips of tile rows for the peer-memory transport (contiguous particle ranges,
-    // the implicit-grid Jacobi kernel with the exchange fused in); the tile-plan decomposition above keeps serving the
-    // stepped / NCCL transport and every other mesh.
-    m_ddStrip = false;
-    {
-        const char* e = getenv("VELVET_DD");
-        const bool forceTiles = e && std::string(e) == "tiles";
-        if (!forceTiles && m_gridUsable && m_gridPlan.cloths.size() == 1 && (unsigned)world <= m_gridPlan.cloths[0].tilesY) {
-            const unsigned rows = m_gridPlan.cloths[0].tilesY, side = m_gridPlan.cloths[0].side;
-            m_ddTileRow.assign(world + 1, 0);
-            for (int r = 0; r < world; r++) m_ddTileRow[r + 1] = m_ddTileRow[r] + rows / world + ((unsigned)r < rows % world ? 1u : 0u);
-            const unsigned rowFirst = m_ddTileRow[rank] * GRID_TILE;
-            const unsigned rowEnd = std::min(m_ddTileRow[rank + 1] * GRID_TILE, side);
-            std::vector<unsigned char> mask(N, 0);
-            std::fill(mask.begin() + (size_t)rowFirst * side, mask.begin() + (size_t)rowEnd * side, (unsigned char)1);
-            m_ddStripMask.upload(mask, m_stream);
-            m_ddStrip = true;
-        }
-    }
-    ddPeerClose();  // mappings of an earlier setup refer to buffers that may have moved
     m_ddGatherSend.allocate(m_ddMaxOwned);
     m_ddGatherRecv.allocate((size_t)m_ddMaxOwned * world);
     Synchronize();
-    m_ddReady = true;
+    m_ddTilesReady = true;
 }
 
-VtClothSolverGPU::DDBuffers VtClothSolverGPU::ddBuffers() const
+void VtClothSolverGPU::ddStripInfo(unsigned out[6]) const
+{
+    if (!m_ddReady || !m_ddStrip) throw Error(VELVET_ERR_STATE, "no strip decomposition");
+    const unsigned side = m_gridPlan.cloths[0].side;
+    const int r = m_dd.rank, w = m_dd.world;
+    auto owned = [&](int q) { return (std::min(m_ddTileRow[q + 1] * GRID_TILE, side) - m_ddTileRow[q] * GRID_TILE) * side; };
+    unsigned most = 0;
+    for (int q = 0; q < w; q++) most = std::max(most, owned(q));
+    out[0] = m_ddTileRow[r];
+    out[1] = m_ddTileRow[r + 1];
+    out[2] = m_ddTileRow[w];
+    out[3] = owned(r);
+    out[4] = most;
+    out[5] = ((r > 0 ? 1u : 0u) + (r < w - 1 ? 1u : 0u)) * side;  // particles sent (= received) per iteration
+}
+
+void VtClothSolverGPU::ddEnsureTiles()
 {
     if (!m_ddReady) throw Error(VELVET_ERR_STATE, "ddSetup has not been called");
+    if (!m_ddTilesReady) {
+        VT_CUDA(cudaSetDevice(m_device));
+        ddSetupTiles();
+    }
+}
+
+VtClothSolverGPU::DDBuffers VtClothSolverGPU::ddBuffers()
+{
+    ddEnsureTiles();
     return DDBuffers{m_ddSendBuf.data(), m_ddRecvBuf.data(), m_ddGatherSend.data(), m_ddGatherRecv.data(),
                      m_ddSendOff[m_dd.world], m_ddRecvOff[m_dd.world], m_ddOwnedCount[m_dd.rank], m_ddMaxOwned};
 }
@@ -983,6 +1050,7 @@ void VtClothSolverGPU::ddValidateFrame() const
 void VtClothSolverGPU::ddFrameBegin(float frameTime)
 {
     ddValidateFrame();
+    ddEnsureTiles();  // the stepped schedule runs the tile form
     VT_CUDA(cudaSetDevice(m_device));
     FrameParams hp;
     hp.P = simParams;

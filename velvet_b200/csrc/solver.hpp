@@ -119,7 +119,13 @@ public:
     };
     void ddSetup(int rank, int world);
     const ExchangePlan& ddPlan() const { return m_dd; }
-    DDBuffers ddBuffers() const;
+    DDBuffers ddBuffers();      // (sets up the tile form if only the strip form exists so far)
+    void ddEnsureTiles();
+    // strip form of a single grid cloth (peer transport): true once ddSetup chose it; the tile form may not exist yet
+    bool ddIsStrip() const { return m_ddStrip; }
+    bool ddTilesReady() const { return m_ddTilesReady; }
+    // {first owned tile row, end tile row, tile rows of the cloth, owned particles, largest share, rows exchanged per iteration}
+    void ddStripInfo(unsigned out[6]) const;
     void ddFrameBegin(float frameTime);
     void ddSubstepBegin(int substep);  // hash (keys/sort replicated, lists of owned particles) + collide of owned particles + pack
     void ddIterateOwned();
@@ -183,7 +189,11 @@ public:
     cudaStream_t stream() const { return m_stream; }
     int device() const { return m_device; }
     int lastLaunchCount() const { return m_lastLaunches; }
-    const TilePlan& tilePlan() const { return m_plan; }
+    const TilePlan& tilePlan()  // builds the record-driven plan if the solver has been running the grid kernel only
+    {
+        ensureTilePlan();
+        return m_plan;
+    }
     const std::string& fusedFallbackReason() const { return m_fallbackReason; }
 
 private:
@@ -191,6 +201,9 @@ private:
     void simulateSeam(float frameTime, Stage* timing);
     void recordFusedFrame(Stage* timing);
     void ensureFusedResources();
+    bool buildTilePlan();
+    void ensureTilePlan();
+    bool m_tilePlanBuilt = false;
     void invalidate() { m_topologyDirty = true; }
     void clampNeighborBound(VtSimParams& P) const;
     void quiesce();  // drains an asynchronous frame before a registration call touches managed buffers
@@ -221,6 +234,8 @@ private:
     float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
     void recordDDFrame();
     void recordDDStripFrame();
+    void ddSetupTiles();
+    bool m_ddTilesReady = false;
     bool m_ddStrip = false;                 // single grid cloth: strips of tile rows, exchange fused into iterate_grid_kernel
     std::vector<unsigned> m_ddTileRow;      // [world + 1] tile rows of every rank
     DeviceBuffer<unsigned char> m_ddStripMask;

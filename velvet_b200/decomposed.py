@@ -69,24 +69,16 @@ class DecomposedCloth:
         check(self._L.velvet_solver_dd_setup(solver._h, self.rank, self.world))
         self.info = VelvetDDInfo()
         check(self._L.velvet_solver_dd_info(solver._h, C.byref(self.info)))
-        so = (C.c_uint * (self.world + 1))()
-        ro = (C.c_uint * (self.world + 1))()
-        check(self._L.velvet_solver_dd_offsets(solver._h, so, ro))
-        self.send_off, self.recv_off = list(so), list(ro)
-        dev = torch.device("cuda", device_index)
-        self.stream = torch.cuda.ExternalStream(solver.stream, device=dev)
-        alias = lambda ptr, n: torch.as_tensor(_DevicePtr(ptr, 4 * max(n, 1)), device=dev)
-        self.send = alias(self.info.sendBuf, self.info.sendTotal)
-        self.recv = alias(self.info.recvBuf, self.info.recvTotal)
-        self.gather_send = alias(self.info.gatherSend, self.info.maxOwnedCount)
-        self.gather_recv = alias(self.info.gatherRecv, self.info.maxOwnedCount * self.world)
+        self._dev = torch.device("cuda", device_index)
+        self.stream = torch.cuda.ExternalStream(solver.stream, device=self._dev)
+        self._stepped_ready = False
         self.halo_bytes_per_iteration = 16 * (self.info.sendTotal + self.info.recvTotal)
         if transport not in ("peer", "nccl"):
             raise ValueError("transport must be 'peer' or 'nccl'")
         self.transport = "nccl"
         self.peer_error = None
         if transport == "peer" and self.world > 1:
-            self._map_peers(dev)
+            self._map_peers(self._dev)
 
     def _map_peers(self, dev):
         """All-gather the IPC blobs and map the peers' arrays; every rank agrees on the outcome (peer, or nccl fallback)."""
@@ -115,6 +107,27 @@ class DecomposedCloth:
             self.transport = "peer"
         else:
             check(L.velvet_solver_dd_peer_close(self.solver._h))
+
+    def _ensure_stepped(self):
+        """Exchange lists and staging buffers of the tile form (a strip-decomposed cloth sets them up only when the stepped
+        schedule is really used), aliased as torch tensors for the NCCL calls."""
+        if self._stepped_ready:
+            return
+        torch = self.torch
+        self._L.velvet_solver_dd_prepare_stepped.argtypes = [C.c_void_p]
+        check(self._L.velvet_solver_dd_prepare_stepped(self.solver._h))
+        check(self._L.velvet_solver_dd_info(self.solver._h, C.byref(self.info)))
+        so = (C.c_uint * (self.world + 1))()
+        ro = (C.c_uint * (self.world + 1))()
+        check(self._L.velvet_solver_dd_offsets(self.solver._h, so, ro))
+        self.send_off, self.recv_off = list(so), list(ro)
+        alias = lambda ptr, n: torch.as_tensor(_DevicePtr(ptr, 4 * max(n, 1)), device=self._dev)
+        self.send = alias(self.info.sendBuf, self.info.sendTotal)
+        self.recv = alias(self.info.recvBuf, self.info.recvTotal)
+        self.gather_send = alias(self.info.gatherSend, self.info.maxOwnedCount)
+        self.gather_recv = alias(self.info.gatherRecv, self.info.maxOwnedCount * self.world)
+        self.halo_bytes_per_iteration = 16 * (self.info.sendTotal + self.info.recvTotal)
+        self._stepped_ready = True
 
     def close(self):
         """Unmap the peers (collective: every rank must call it before any rank destroys its solver)."""
@@ -149,6 +162,7 @@ class DecomposedCloth:
             return
         if self.transport == "closed":
             raise RuntimeError("DecomposedCloth.close() was called")
+        self._ensure_stepped()
         P = self.solver.simParams
         with self.torch.cuda.stream(self.stream):
             self._step(DD_FRAME_BEGIN, 0, dt)
@@ -191,8 +205,10 @@ class LocalShards:
         alias = lambda ptr, n: torch.as_tensor(_DevicePtr(ptr, 4 * max(n, 1)), device=dev)
         self.info, self.send_off, self.recv_off = [], [], []
         self.send, self.recv, self.gather_send, self.gather_recv = [], [], [], []
+        self._L.velvet_solver_dd_prepare_stepped.argtypes = [C.c_void_p]
         for r, s in enumerate(self.solvers):
             check(self._L.velvet_solver_dd_setup(s._h, r, self.world))
+            check(self._L.velvet_solver_dd_prepare_stepped(s._h))
             info = VelvetDDInfo()
             check(self._L.velvet_solver_dd_info(s._h, C.byref(info)))
             so = (C.c_uint * (self.world + 1))()
