@@ -268,6 +268,18 @@ VELVET_API int velvet_solver_buffer(VelvetSolver* s, int bufferId, void** devPtr
 /* Copy a public buffer to / from host memory (count elements of the buffer's type, synchronous). */
 VELVET_API int velvet_solver_download(VelvetSolver* s, int bufferId, void* host, size_t bytes);
 VELVET_API int velvet_solver_upload(VelvetSolver* s, int bufferId, const void* host, size_t bytes);
+/* Renderer hand-off, VtClothSolverGPU.hpp L107-110 (positions.sync(); normals.sync() into the cloths' GL vertex buffers,
+ * VtBuffer.hpp L122-236).  The caller registers, per cloth (in AddCloth order), device arrays it owns -- the pointers it got
+ * from cudaGraphicsResourceGetMappedPointer for that cloth's VBOs, or any device allocation of 3 floats per vertex;
+ * sync_render_targets mirrors the cloth's range of positions / normals into them on the solver stream.  NULL detaches. */
+VELVET_API int velvet_solver_set_render_targets(VelvetSolver* s, int clothIndex, float* positionsDev, float* normalsDev);
+VELVET_API int velvet_solver_sync_render_targets(VelvetSolver* s);
+/* The five SpatialHashGPU arrays in managed memory, host-indexable like the reference's VtBuffers (SpatialHashGPU.hpp
+ * L54-60), instead of plain device memory.  Call before velvet_solver_add_cloth. */
+VELVET_API int velvet_solver_set_hash_host_readable(VelvetSolver* s, int on);
+/* Debug guard (cf. VtClothSolverCPU::CheckNAN, VtClothSolverCPU.hpp L407-418): number of non-finite components in positions /
+ * velocities / predicted, and the first offending particle (numParticles when none).  Synchronous. */
+VELVET_API int velvet_solver_check_nan(VelvetSolver* s, unsigned* nonFiniteCount, unsigned* firstParticle);
 /* Asynchronous read-back of positions+normals on the solver stream into pinned host memory (headless
  * replacement of positions.sync()/normals.sync(), hpp L109-110). */
 VELVET_API int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals);

@@ -298,6 +298,39 @@ int velvet_solver_upload(VelvetSolver* s, int bufferId, const void* host, size_t
     VT_API_END
 }
 
+int velvet_solver_set_render_targets(VelvetSolver* s, int clothIndex, float* positionsDev, float* normalsDev)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.SetRenderTargets(clothIndex, positionsDev, normalsDev);
+    VT_API_END
+}
+
+int velvet_solver_sync_render_targets(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.SyncRenderTargets();
+    VT_API_END
+}
+
+int velvet_solver_set_hash_host_readable(VelvetSolver* s, int on)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    VT_REQUIRE(s->impl.simParams.numParticles == 0, "set_hash_host_readable must precede AddCloth");
+    s->impl.setHashHostReadable(on != 0);
+    VT_API_END
+}
+
+int velvet_solver_check_nan(VelvetSolver* s, unsigned* nonFiniteCount, unsigned* firstParticle)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && nonFiniteCount, "bad argument");
+    *nonFiniteCount = s->impl.CheckNaN(firstParticle);
+    VT_API_END
+}
+
 int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals)
 {
     VT_API_BEGIN

@@ -37,18 +37,20 @@ void default_sim_params(VtSimParams& p)
 
 // ------------------------------------------------------------------------------------------------ SpatialHashGPU
 
-SpatialHashGPU::SpatialHashGPU(float particleDiameter, int maxNumObjects, float hashCellSizeScalar, int maxNumNeighbors)
+SpatialHashGPU::SpatialHashGPU(float particleDiameter, int maxNumObjects, float hashCellSizeScalar, int maxNumNeighbors, bool hostReadable)
 {
     m_spacing = particleDiameter * hashCellSizeScalar;
     m_tableSize = 2 * maxNumObjects;
     m_maxNumNeighbors = maxNumNeighbors;
     // only kernels touch these five (the reference keeps them managed but never indexes them on the host): plain device
     // memory keeps 4.3 GB of neighbour slots per 16.7M particles out of the unified-memory pool
-    neighbors.setDeviceOnly();
-    particleHash.setDeviceOnly();
-    particleIndex.setDeviceOnly();
-    cellStart.setDeviceOnly();
-    cellEnd.setDeviceOnly();
+    if (!hostReadable) {
+        neighbors.setDeviceOnly();
+        particleHash.setDeviceOnly();
+        particleIndex.setDeviceOnly();
+        cellStart.setDeviceOnly();
+        cellEnd.setDeviceOnly();
+    }
     neighbors.resize((size_t)maxNumObjects * (size_t)maxNumNeighbors);
     particleHash.resize((size_t)maxNumObjects);
     particleIndex.resize((size_t)maxNumObjects);
@@ -217,6 +219,57 @@ void VtClothSolverGPU::HashFused()
     Synchronize();
 }
 
+void VtClothSolverGPU::SetRenderTargets(int clothIndex, float* positionsDev, float* normalsDev)
+{
+    if (clothIndex < 0 || (size_t)clothIndex >= positions.numRanges()) throw Error(VELVET_ERR_INVALID_ARGUMENT, "SetRenderTargets: no such cloth");
+    positions.attachRegistered((size_t)clothIndex, reinterpret_cast<vec3*>(positionsDev));
+    normals.attachRegistered((size_t)clothIndex, reinterpret_cast<vec3*>(normalsDev));
+}
+
+void VtClothSolverGPU::SyncRenderTargets()
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    positions.sync(m_stream);
+    normals.sync(m_stream);
+}
+
+namespace {
+__global__ void __launch_bounds__(256) count_nonfinite_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                              const float* __restrict__ c, unsigned n, unsigned* out)
+{
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    unsigned bad = 0;
+    for (int k = 0; k < 3; k++) {
+        bad += isfinite(a[3 * (size_t)id + k]) ? 0u : 1u;
+        bad += isfinite(b[3 * (size_t)id + k]) ? 0u : 1u;
+        bad += isfinite(c[3 * (size_t)id + k]) ? 0u : 1u;
+    }
+    if (bad) {
+        atomicAdd(out, bad);
+        atomicMin(out + 1, id);
+    }
+}
+}  // namespace
+
+unsigned VtClothSolverGPU::CheckNaN(unsigned* firstParticle)
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    const unsigned n = simParams.numParticles;
+    unsigned host[2] = {0u, n};
+    if (n) {
+        m_nanScratch.allocate(2);
+        VT_CUDA(cudaMemcpyAsync(m_nanScratch.data(), host, sizeof(host), cudaMemcpyHostToDevice, m_stream));
+        count_nonfinite_kernel<<<(n + 255) / 256, 256, 0, m_stream>>>(reinterpret_cast<const float*>(positions.data()),
+                                                                      reinterpret_cast<const float*>(velocities.data()),
+                                                                      reinterpret_cast<const float*>(predicted.data()), n, m_nanScratch.data());
+        VT_CUDA(cudaMemcpyAsync(host, m_nanScratch.data(), sizeof(host), cudaMemcpyDeviceToHost, m_stream));
+        Synchronize();
+    }
+    if (firstParticle) *firstParticle = host[1];
+    return host[0];
+}
+
 int VtClothSolverGPU::ReadbackPipelined(float* hostPositions, float* hostNormals)
 {
     if (!m_copyStream) {
@@ -359,7 +412,7 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
 
     // hash sized to the total particle count; snapshot taken after the transform, hpp L148-149
     m_spatialHash = std::make_shared<SpatialHashGPU>(particleDiameter, (int)simParams.numParticles,
-                                                     simParams.hashCellSizeScalar, simParams.maxNumNeighbors);
+                                                     simParams.hashCellSizeScalar, simParams.maxNumNeighbors, m_hashHostReadable);
     m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
     invalidate();
     return prevNumParticles;
@@ -418,7 +471,7 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
             for (int k = 0; k < numInstances; k++) invMasses[k * n + (size_t)g.attachPid[c]] = 0;
 
     m_spatialHash = std::make_shared<SpatialHashGPU>(g.particleDiameter, (int)total, simParams.hashCellSizeScalar,
-                                                     simParams.maxNumNeighbors);
+                                                     simParams.maxNumNeighbors, m_hashHostReadable);
     m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
     m_instancing = Instancing{(uint)numInstances, (uint)n, (uint)numAttached};
     m_clothRanges.assign(1, ClothRange{0u, (uint)n});  // one topology, shared by every instance

@@ -28,7 +28,9 @@ constexpr float kFixedDeltaTime = 1.0f / 60.0f;  // Timer.hpp L235
 class SpatialHashGPU {
 public:
     // SpatialHashGPU.hpp L18-28 (hashCellSizeScalar / maxNumNeighbors come from Global::simParams there)
-    SpatialHashGPU(float particleDiameter, int maxNumObjects, float hashCellSizeScalar, int maxNumNeighbors);
+    // hostReadable: the five hash arrays in managed memory like the reference's VtBuffers (SpatialHashGPU.hpp L54-60) instead
+    // of plain device memory (the default: 4.3 GB of neighbour slots per 16.7M particles stay out of the unified-memory pool)
+    SpatialHashGPU(float particleDiameter, int maxNumObjects, float hashCellSizeScalar, int maxNumNeighbors, bool hostReadable = false);
 
     // L32-39: snapshot of `count` packed float3 positions (device-accessible or host pointer)
     void SetInitialPositions(const float* positions, size_t count);
@@ -96,6 +98,16 @@ public:
     // buffers.  Simulate() runs exactly these kernels on its internal float4 state; this entry exists so that they can be
     // checked on arbitrary inputs (tests/test_hash_gpu.py).  Synchronous.
     void HashFused();
+    // Renderer hand-off (VtClothSolverGPU.hpp L107-110: positions.sync(); normals.sync()): device arrays owned by the caller
+    // -- the mapped pointers of the cloth's GL vertex buffers, or any device allocation of 3 floats per particle of that cloth
+    // -- registered per cloth; SyncRenderTargets() mirrors the cloth ranges into them in stream order.  NULL detaches.
+    void SetRenderTargets(int clothIndex, float* positionsDev, float* normalsDev);
+    void SyncRenderTargets();
+    // Debug guard (the reference's unused VtClothSolverCPU::CheckNAN, L407-418): counts non-finite components of positions,
+    // velocities and predicted on the device; returns the count and the first offending particle (or numParticles).
+    unsigned CheckNaN(unsigned* firstParticle);
+    // must be called before AddCloth: hash arrays host-readable (managed) like the reference's
+    void setHashHostReadable(bool on) { m_hashHostReadable = on; }
     int ReadbackPipelined(float* hostPositions, float* hostNormals);
     void ReadbackWait(int ticket);
 
@@ -221,6 +233,8 @@ private:
     int m_tileSize = 0;
     int m_mathMode = VELVET_MATH_EXACT;
     int m_iterateMode = VELVET_ITERATE_AUTO;
+    bool m_hashHostReadable = false;
+    DeviceBuffer<unsigned> m_nanScratch;
     std::vector<ClothRange> m_clothRanges;  // particle range of every AddCloth call
     Instancing m_instancing{1, 0, 0};
     // domain decomposition state

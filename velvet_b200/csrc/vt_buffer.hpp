@@ -11,6 +11,7 @@
 
 #include <cassert>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -99,6 +100,11 @@ public:
         m_deviceOnly = true;
     }
     bool deviceOnly() const { return m_deviceOnly; }
+    void setManaged()  // back to the reference's placement (host-indexable); only while empty
+    {
+        if (m_data) throw Error(-4, "VtBuffer::setManaged on an allocated buffer");
+        m_deviceOnly = false;
+    }
 
     void destroy()
     {
@@ -141,6 +147,58 @@ private:
     bool m_deviceOnly = false;
 };
 
+// VtRegisteredBuffer (reference: VtBuffer.hpp L122-186): a device array that somebody else owns -- in the reference a GL vertex
+// buffer registered with CUDA and mapped once (registerBuffer(GLuint), L167-179).  Headless, the owner hands over the mapped
+// device pointer itself (what cudaGraphicsResourceGetMappedPointer returned in the renderer, or any device allocation);
+// with VELVET_GL_INTEROP defined (and GL + cuda_gl_interop.h available to the includer) the GLuint form is compiled as well.
+template <class T>
+class VtRegisteredBuffer {
+public:
+    VtRegisteredBuffer() = default;
+    VtRegisteredBuffer(const VtRegisteredBuffer&) = delete;
+    VtRegisteredBuffer& operator=(const VtRegisteredBuffer&) = delete;
+    ~VtRegisteredBuffer() { destroy(); }
+
+    T* data() const { return m_buffer; }
+    operator T*() const { return m_buffer; }
+    size_t size() const { return m_count; }
+
+    void registerBuffer(T* mappedDevicePointer, size_t count)
+    {
+        destroy();
+        m_buffer = mappedDevicePointer;
+        m_count = count;
+        m_numBytes = count * sizeof(T);
+    }
+#ifdef VELVET_GL_INTEROP
+    void registerBuffer(GLuint vbo)  // VtBuffer.hpp L167-179, verbatim semantics: register, map once, read the pointer, unmap
+    {
+        destroy();
+        VT_CUDA(cudaGraphicsGLRegisterBuffer(&m_cudaVboResource, vbo, cudaGraphicsRegisterFlagsNone));
+        VT_CUDA(cudaGraphicsMapResources(1, &m_cudaVboResource, 0));
+        VT_CUDA(cudaGraphicsResourceGetMappedPointer((void**)&m_buffer, &m_numBytes, m_cudaVboResource));
+        m_count = m_numBytes / sizeof(T);
+        VT_CUDA(cudaGraphicsUnmapResources(1, &m_cudaVboResource, 0));
+    }
+#endif
+    void destroy()
+    {
+#ifdef VELVET_GL_INTEROP
+        if (m_cudaVboResource) cudaGraphicsUnregisterResource(m_cudaVboResource);
+        m_cudaVboResource = nullptr;
+#endif
+        m_buffer = nullptr;  // not ours to free
+        m_count = m_numBytes = 0;
+    }
+
+private:
+    size_t m_count = 0, m_numBytes = 0;
+    T* m_buffer = nullptr;
+#ifdef VELVET_GL_INTEROP
+    struct cudaGraphicsResource* m_cudaVboResource = nullptr;
+#endif
+};
+
 // Headless VtMergedBuffer: one managed array holding every cloth's range.  The reference mirrors each range
 // into a GL VBO (registerNewBuffer(GLuint) / sync(), VtBuffer.hpp L202-229); headless callers register host
 // data instead and read results back with cudaMemcpy (velvet_solver_download / readback_async).
@@ -167,12 +225,36 @@ public:
     size_t numRanges() const { return m_offsets.size(); }
     size_t rangeOffset(size_t i) const { return m_offsets[i]; }
     size_t rangeCount(size_t i) const { return m_counts[i]; }
-    void sync() {}  // GL mirrors only exist under VELVET_GL_INTEROP (not built headless)
+    // Attaches a registered (externally owned) device array to range i: sync() then mirrors the range into it, which is what
+    // the reference does for the renderer's VBOs (VtBuffer.hpp L202-229).  The array must hold rangeCount(i) elements.
+    void attachRegistered(size_t i, T* mappedDevicePointer)
+    {
+        if (i >= m_offsets.size()) throw Error(-1, "VtMergedBuffer::attachRegistered: no such range");
+        if (m_rbuffers.size() < m_offsets.size()) m_rbuffers.resize(m_offsets.size());
+        if (!m_rbuffers[i]) m_rbuffers[i] = std::make_shared<VtRegisteredBuffer<T>>();
+        if (mappedDevicePointer) m_rbuffers[i]->registerBuffer(mappedDevicePointer, m_counts[i]);
+        else m_rbuffers[i]->destroy();
+    }
+    // copy from the merged array to the registered ones (L222-229), in stream order
+    void sync(cudaStream_t stream = 0)
+    {
+        for (size_t i = 0; i < m_rbuffers.size(); i++)
+            if (m_rbuffers[i] && m_rbuffers[i]->data())
+                VT_CUDA(cudaMemcpyAsync(m_rbuffers[i]->data(), m_vbuffer.data() + m_offsets[i], m_counts[i] * sizeof(T),
+                                        cudaMemcpyDeviceToDevice, stream));
+    }
+    size_t numRegistered() const
+    {
+        size_t n = 0;
+        for (const auto& r : m_rbuffers) n += (r && r->data()) ? 1 : 0;
+        return n;
+    }
     void destroy()
     {
         m_vbuffer.destroy();
         m_offsets.clear();
         m_counts.clear();
+        m_rbuffers.clear();
     }
     operator T*() const { return m_vbuffer.data(); }
     T* data() const { return m_vbuffer.data(); }
@@ -181,6 +263,7 @@ public:
 
 private:
     std::vector<size_t> m_offsets, m_counts;
+    std::vector<std::shared_ptr<VtRegisteredBuffer<T>>> m_rbuffers;
     VtBuffer<T> m_vbuffer;
 };
 

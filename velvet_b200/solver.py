@@ -207,6 +207,27 @@ class VtClothSolverGPU:
         return self._L.velvet_solver_last_launch_count(self._h)
 
     # ---- buffers (VtClothSolverGPU.hpp L209-231, SpatialHashGPU.hpp L54-60)
+    def SetHashHostReadable(self, on: bool = True):
+        """Before AddCloth: the five hash arrays in managed memory, host-indexable like the reference's VtBuffers."""
+        self._L.velvet_solver_set_hash_host_readable.argtypes = [C.c_void_p, C.c_int]
+        check(self._L.velvet_solver_set_hash_host_readable(self._h, 1 if on else 0))
+
+    def SetRenderTargets(self, cloth_index: int, positions_dev: int, normals_dev: int):
+        """Device arrays (raw pointers) that SyncRenderTargets mirrors cloth `cloth_index`'s positions / normals into."""
+        self._L.velvet_solver_set_render_targets.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        check(self._L.velvet_solver_set_render_targets(self._h, cloth_index, C.c_void_p(positions_dev), C.c_void_p(normals_dev)))
+
+    def SyncRenderTargets(self):
+        self._L.velvet_solver_sync_render_targets.argtypes = [C.c_void_p]
+        check(self._L.velvet_solver_sync_render_targets(self._h))
+
+    def CheckNaN(self):
+        """(number of non-finite components in positions / velocities / predicted, first offending particle)."""
+        self._L.velvet_solver_check_nan.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        cnt, first = C.c_uint(), C.c_uint()
+        check(self._L.velvet_solver_check_nan(self._h, C.byref(cnt), C.byref(first)))
+        return cnt.value, first.value
+
     def buffer_ptr(self, name: str):
         p = C.c_void_p()
         n = C.c_size_t()
