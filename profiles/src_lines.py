@@ -5,7 +5,7 @@ import csv, io, subprocess, sys, collections
 
 rep = sys.argv[1]
 minpct = float(sys.argv[2]) if len(sys.argv) > 2 else 0.7
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + (["--kernel-name", sys.argv[3]] if len(sys.argv) > 3 else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur_file, hdr = None, None
 acc = collections.OrderedDict()
