@@ -1202,19 +1202,32 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
         neighbors, particleIndex, cellStart, cellEnd, PosFloat4{pred}, PosFloat4{init4}, hp);
 }
 
-bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
-                                   const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst,
-                                   const unsigned char* ownedMask)
+int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
+                                  const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
+                                  const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst,
+                                  const unsigned char* ownedMask, unsigned numOwned)
 {
-    if (hp.tableSize <= 0) return false;
+    if (hp.tableSize <= 0) return 0;
     const unsigned n = L.numParticles;
     SortedParticle* sorted = reinterpret_cast<SortedParticle*>(sortedScratch);
     reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n, hp.cellSpacing);
-    cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
-        neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, ownedMask);
-    return true;
+    if (!ownedMask) {
+        cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
+            neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, nullptr, n);
+        return 2;
+    }
+    // decomposed mode: compact the owned slots (scratch behind the sorted records: a counter + numOwned slot indices)
+    unsigned* counter = reinterpret_cast<unsigned*>(sorted + n);
+    unsigned* slots = counter + 4;
+    VT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), L.stream));
+    compact_owned_slots_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, ownedMask, n, slots, counter);
+    if (numOwned)
+        cache_neighbors_sorted_kernel<<<(numOwned + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
+            neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, slots, numOwned);
+    return 4;
 }
+
+size_t cache_neighbors_scratch_float4(size_t n) { return 2 * n + (n + 4 + 3) / 4 + 1; }  // sorted records + counter + owned slots
 
 // plain device-side copy (read-back staging): a kernel rather than cudaMemcpyAsync because the source is managed memory,
 // for which the driver's copy path is not stream-fast

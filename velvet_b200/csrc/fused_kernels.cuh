@@ -122,13 +122,15 @@ void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned*
 void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                             const unsigned* cellStart, const unsigned* cellEnd, const float4* pred, const float4* init4,
                             VtHashParams hp);
-// Restructured H4 (see hash_kernels.cuh): reorder pass + sorted-order candidate walk.  Returns false when it cannot
-// run (degenerate table); the caller then uses launch_cache_neighbors.
-bool launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
-                                   const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
-                                   const float4* init4, float4* sortedScratch /* 2 float4 per particle */, VtHashParams hp,
-                                   Instancing inst,  // hp.tableSize = rows per instance
-                                   const unsigned char* ownedMask = nullptr);  // decomposed mode: lists of owned particles only
+// Restructured H4 (see hash_kernels.cuh): reorder pass + sorted-order candidate walk.  Returns the number of launches
+// (kernels + memset nodes) it made, 0 when it cannot run (degenerate table); the caller then uses launch_cache_neighbors.
+int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
+                                  const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
+                                  const float4* init4, float4* sortedScratch /* cache_neighbors_scratch_float4(n) */, VtHashParams hp,
+                                  Instancing inst,  // hp.tableSize = rows per instance
+                                  const unsigned char* ownedMask = nullptr,  // decomposed mode: lists of the owned particles only ...
+                                  unsigned numOwned = 0);                    // ... exactly this many of them
+size_t cache_neighbors_scratch_float4(size_t numParticles);
 void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t words);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);
 void launch_unpack_float4(const FusedLaunch& L, const float4* in, float* packed3, unsigned n);  // xyz of n float4 -> packed float3

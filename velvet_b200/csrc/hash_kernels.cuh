@@ -197,16 +197,37 @@ constexpr int CN_THREADS = 256;
 // scattered 4-byte column stores neighbors[id + N*k] are absorbed by L2 (the touched part of the table is ~50 MB).
 // The walk is software-pipelined over buckets (the range of the next non-empty bucket is fetched while the candidates of
 // the current one are tested) and four candidates are in flight per trip.
+// Domain-decomposed mode: the sorted slots whose particle this rank owns, compacted (warp ballot + one atomic per warp), so
+// that the candidate walk below runs with full warps over numOwned threads.  Owned particles are scattered uniformly over
+// the sorted order (the hash is a hash): walking all slots and returning early for the others kept ~1/world of the lanes of
+// EVERY warp busy, and the walk barely got faster with more ranks (8 GPUs, 16.7M particles: the largest stage of the frame).
+// The order of the compacted list depends on warp arrival; every thread writes only its own particle's list, so the
+// neighbour table does not.
+static __global__ void __launch_bounds__(256) compact_owned_slots_kernel(const SortedParticle* __restrict__ sorted,
+                                                                         const unsigned char* __restrict__ ownedMask, unsigned n,
+                                                                         unsigned* __restrict__ slots, unsigned* __restrict__ counter)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool owned = false;
+    if (t < n) owned = __ldg(ownedMask + __float_as_uint(__ldg(&sorted[t].init.w))) != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, owned);
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(counter, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (owned) slots[base + __popc(ballot & ((1u << lane) - 1u))] = t;
+}
+
 static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
     unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
     const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles,
-    const unsigned char* __restrict__ ownedMask)
+    const unsigned* __restrict__ ownedSlots, const unsigned numThreads)
 {
-    const unsigned t = blockIdx.x * CN_THREADS + threadIdx.x;
-    if (t >= hp.numObjects) return;
+    const unsigned ti = blockIdx.x * CN_THREADS + threadIdx.x;
+    if (ti >= numThreads) return;
+    const unsigned t = ownedSlots ? __ldg(ownedSlots + ti) : ti;  // decomposed mode: only the slots of owned particles
     const float4 me = __ldg(&sorted[t].pos), me0 = __ldg(&sorted[t].init);
     const unsigned id = __float_as_uint(me0.w);
-    if (ownedMask && !__ldg(ownedMask + id)) return;  // domain-decomposed mode: another rank builds this particle's list
     const unsigned tableBase = (id / instanceParticles) * (unsigned)hp.tableSize;  // this instance's rows of the table
     const vec3 position = V3(me);
     const vec3 originalPos = V3(me0);

@@ -821,7 +821,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_predA.allocate(std::max<size_t>(N, 131072));
     m_predB.allocate(std::max<size_t>(N, 131072));
     m_init4.allocate(N);
-    m_sorted.allocate(2 * (size_t)N);
+    m_sorted.allocate(exact_math::cache_neighbors_scratch_float4(N));
     m_keysAlt.allocate(N);
     m_valsAlt.allocate(N);
     m_prepared.allocate(VT_MAX_COLLIDERS);
@@ -922,9 +922,9 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             STAGE_BEGIN(t, "Solver_HashCache");
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             hp.tableSize = H.tableSize() / (int)m_instancing.count;  // rows per instance
-            if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4,
-                                                          m_sorted, hp, m_instancing)) {
-                launches += 2;
+            if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur,
+                                                                         m_init4, m_sorted, hp, m_instancing)) {
+                launches += nl;
             } else {
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4, hp);
                 launches++;
@@ -1144,7 +1144,7 @@ void VtClothSolverGPU::ddSubstepBegin(int substep)
         VtHashParams hp = H.MakeParams(N, P.particleDiameter);
         // keys / sort / cell table are replicated; the expensive candidate walk only for the particles this rank owns
         if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4,
-                                                       m_sorted, hp, m_instancing, m_ddOwnedMask))
+                                                       m_sorted, hp, m_instancing, m_ddOwnedMask, m_ddOwnedCount[m_dd.rank]))
             exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4, hp);
     }
     // collide only the owned particles, then hand the boundary to the peers exactly like after an iteration
@@ -1369,9 +1369,9 @@ void VtClothSolverGPU::recordDDFrame()
             exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
             launches += 2 + m_sorter.lastLaunchCount();
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
-            if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, m_sorted,
-                                                          hp, m_instancing, m_ddOwnedMask)) {
-                launches += 2;
+            if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
+                                                                         m_init4, m_sorted, hp, m_instancing, m_ddOwnedMask, ownedCount)) {
+                launches += nl;
             } else {
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
                 launches++;
@@ -1474,9 +1474,9 @@ void VtClothSolverGPU::recordDDStripFrame()
             exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
             launches += 2 + m_sorter.lastLaunchCount();
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
-            if (exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, m_sorted,
-                                                          hp, m_instancing, m_ddStripMask)) {
-                launches += 2;
+            if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
+                                                                         m_init4, m_sorted, hp, m_instancing, m_ddStripMask, count)) {
+                launches += nl;
             } else {
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
                 launches++;
