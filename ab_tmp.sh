@@ -1,7 +1,13 @@
-mkdir -p gpurun_out/r2m
-timeout 900 python -m pytest tests/test_decomposed_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tests/_dd_gpu_worker.py gpurun_out/r2m 2047 2 10 peer > /dev/null 2>&1
-python -c "
-import json
-for r in (0,1):
-    d=json.load(open(f'gpurun_out/r2m/dd_gpu{r}.json')); print({k:d[k] for k in ('transport','bit_identical','launches_per_frame','single_gpu_ms','decomposed_ms','owned') if k in d})"
+timeout 900 python -m pytest tests/test_hash_gpu.py tests/test_ref_cuda_gpu.py "tests/test_solver_gpu.py::test_headline_1m_one_frame_against_the_oracle" -m gpu -x -q 2>&1 | tail -4
+python - <<'PY'
+import velvet_b200 as vb
+for R in (1023, 4095):
+    p = vb.default_params(); p.numSubsteps, p.numIterations = 5, 10
+    g = vb.build_scene(R, p); g.UpdateColliders(vb.sphere_plane_colliders())
+    for _ in range(8): g.Simulate()
+    acc={}
+    for _ in range(3):
+        for k,v in g.SimulateTimed().items(): acc[k]=acc.get(k,0)+v/3
+    print(R, {k:round(v,3) for k,v in acc.items() if k in ("Solver_Total","Solver_HashCache","Solver_Iterate","Solver_CollideParticles","Solver_HashSort")})
+    g.close()
+PY

@@ -378,6 +378,15 @@ VELVET_API int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* nu
  * withAttach != 0).  The plan is built by worker threads (VELVET_PLAN_THREADS, default: the hardware concurrency); the digest
  * must not depend on their number (tests/test_capi_cpu.py). */
 VELVET_API int velvet_plan_grid_digest(int resolution, int tileSize, int withAttach, unsigned long long* digest);
+/* Host-only: the grid-cloth recognition the solver runs before choosing its Jacobi kernel (grid_plan.hpp).  clothCounts =
+ * particles of every AddCloth call, in order.  *recognised = 1 when the stretch / bending lists are exactly the pattern
+ * VtClothObjectGPU generates for square grids of those sizes (VtClothObjectGPU.hpp L75-132); then *numTiles = tiles of the
+ * implicit-grid kernel and rest4 (may be NULL; 4 floats per particle) receives, per vertex, the rest lengths of the
+ * (vertical, horizontal, diagonal, anti-diagonal) stretch constraints generated there.  whyNot (may be NULL, 128 bytes)
+ * receives the reason otherwise. */
+VELVET_API int velvet_grid_plan_check(const unsigned* clothCounts, int numCloths, const int* stretchIndices, const float* stretchLengths,
+                                      size_t numStretch, const unsigned* bendIndices, const float* bendAngles, size_t numBend,
+                                      int* recognised, unsigned* numTiles, float* rest4, char* whyNot);
 /* Host-only: shared-memory wavefronts per Jacobi iteration of the constraint threads' 16-byte accesses (position loads and
  * slot stores) for the tile plan of a grid cloth: out3 = {minimum, with records in constraint-id order, with the emitted
  * bank-conflict-avoiding order}. */

@@ -94,3 +94,72 @@ def test_tile_plan_does_not_depend_on_the_number_of_builder_threads():
     for R, tile, attach in ((255, 256, 0), (255, 128, 1), (300, 256, 1), (511, 256, 0)):
         one = digest(R, tile, attach, 1)
         assert digest(R, tile, attach, 3) == one and digest(R, tile, attach, 8) == one and digest(R, tile, attach, None) == one
+
+
+def _grid_check(counts, si, sl, bi, ba, want_rest=True):
+    import ctypes as C
+    import numpy as np
+    L = vb.load()
+    L.velvet_grid_plan_check.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_uint), C.c_void_p, C.c_char_p]
+    counts = np.ascontiguousarray(counts, np.uint32)
+    si, sl = np.ascontiguousarray(si, np.int32), np.ascontiguousarray(sl, np.float32)
+    bi, ba = np.ascontiguousarray(bi, np.uint32), np.ascontiguousarray(ba, np.float32)
+    ok, tiles = C.c_int(), C.c_uint()
+    rest = np.zeros(4 * int(counts.sum()), np.float32)
+    why = C.create_string_buffer(128)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.velvet_grid_plan_check(p(counts), len(counts), p(si), p(sl), len(sl), p(bi), p(ba), len(ba), C.byref(ok), C.byref(tiles),
+                                    p(rest) if want_rest else None, why) == 0
+    return bool(ok.value), tiles.value, rest.reshape(-1, 4), why.value.decode()
+
+
+def test_grid_cloths_are_recognised_from_their_constraint_pattern():
+    """Host logic of the Jacobi-kernel choice (grid_plan.cpp), no GPU: the lists VtClothObjectGPU generates (here: by the O1
+    oracle's restatement of VtClothObjectGPU.hpp L75-132) are recognised, with the rest lengths filed per generating vertex;
+    any deviation -- a swapped pair, an extra or missing constraint, another triangulation -- is not."""
+    import numpy as np
+    from oracle import o1
+
+    def lists(R, off=0):
+        s = o1.O1Solver(o1.default_params())
+        v, idx = o1.generate_cloth_mesh(R)
+        s.cloth_object_start(R, v, idx, o1.transform_matrix((0.1, 1.5, 1.0), (70, 10, 0), (1, 1, 1)), [])
+        return (s.buffer("stretchIndices").copy() + off, s.buffer("stretchLengths").copy(),
+                s.buffer("bendIndices").copy() + off, s.buffer("bendAngles").copy())
+
+    R = 20
+    n = (R + 1) ** 2
+    si, sl, bi, ba = lists(R)
+    ok, tiles, rest, why = _grid_check([n], si, sl, bi, ba)
+    assert ok and tiles == ((R + 1 + 14) // 15) ** 2, why
+    # rest lengths per generating vertex: (x,y)-(x,y+1), (x,y)-(x+1,y), (x,y)-(x+1,y+1), (x,y+1)-(x+1,y); 0 where absent
+    pairs = si.reshape(-1, 2)
+    side = R + 1
+    expect = np.zeros((n, 4), np.float32)
+    for (a, b), length in zip(pairs, sl):
+        lo = min(a, b)
+        d = (b - a)
+        kind = {1: 0, side: 1, side + 1: 2}.get(d)
+        if kind is None:  # anti-diagonal (x,y+1)-(x+1,y): generated at vertex (x,y) = a - 1
+            assert d == side - 1
+            expect[a - 1, 3] = length
+        else:
+            expect[lo, kind] = length
+    assert np.array_equal(rest, expect)
+    assert (rest[:, 0] > 0).sum() == R * (R + 1) and (rest[:, 3] > 0).sum() == R * R
+
+    bad = si.copy(); bad[[6, 7]] = bad[[7, 6]]  # one pair reversed
+    assert not _grid_check([n], bad, sl, bi, ba)[0]
+    assert not _grid_check([n], si[:-2], sl[:-1], bi, ba)[0]  # one constraint missing
+    assert not _grid_check([n], np.r_[si, [0, 5]], np.r_[sl, [0.3]], bi, ba)[0]  # one extra
+    other = bi.reshape(-1, 4)[:, [1, 0, 2, 3]].reshape(-1)  # another quad orientation
+    assert not _grid_check([n], si, sl, other, ba)[0]
+    assert not _grid_check([n - 1], si, sl, bi, ba)[0]  # not a square grid
+
+    # two cloths of different size registered one after the other
+    R2 = 7
+    s2 = lists(R2, off=n)
+    ok, tiles, rest, why = _grid_check([n, (R2 + 1) ** 2], np.r_[si, s2[0]], np.r_[sl, s2[1]], np.r_[bi, s2[2].astype(np.uint32)], np.r_[ba, s2[3]])
+    assert ok and tiles == 4 + 1, why
+    assert np.array_equal(rest[:n], expect)

@@ -613,6 +613,30 @@ int velvet_plan_grid_tiles(int resolution, int tileSize, unsigned* numTiles, uns
     VT_API_END
 }
 
+int velvet_grid_plan_check(const unsigned* clothCounts, int numCloths, const int* stretchIndices, const float* stretchLengths,
+                           size_t numStretch, const unsigned* bendIndices, const float* bendAngles, size_t numBend, int* recognised,
+                           unsigned* numTiles, float* rest4, char* whyNot)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(clothCounts && numCloths > 0 && recognised, "grid_plan_check: bad argument");
+    std::vector<ClothRange> ranges;
+    unsigned total = 0;
+    for (int c = 0; c < numCloths; c++) {
+        ranges.push_back(ClothRange{total, clothCounts[c]});
+        total += clothCounts[c];
+    }
+    const GridPlan g = build_grid_plan(total, ranges, stretchIndices, stretchLengths, numStretch, bendIndices, bendAngles, numBend,
+                                       nullptr, nullptr, nullptr, 0);
+    *recognised = g.valid ? 1 : 0;
+    if (numTiles) *numTiles = g.valid ? g.numTiles : 0u;
+    if (g.valid && rest4) std::memcpy(rest4, g.rest4.data(), sizeof(float) * g.rest4.size());
+    if (whyNot) {
+        std::memset(whyNot, 0, 128);
+        std::strncpy(whyNot, g.why.c_str(), 127);
+    }
+    VT_API_END
+}
+
 int velvet_plan_grid_digest(int resolution, int tileSize, int withAttach, unsigned long long* digest)
 {
     VT_API_BEGIN

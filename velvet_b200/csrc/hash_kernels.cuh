@@ -114,16 +114,19 @@ __global__ void __launch_bounds__(256) cache_neighbors_kernel(unsigned* __restri
 struct FastMod {
     unsigned long long M;  // ceil(2^64 / d)
     unsigned d;
+    unsigned pow2Mask;     // d - 1 when d is a power of two (tableSize = 2 * maxNumObjects: every power-of-two cloth), else 0
 };
 inline FastMod make_fastmod(unsigned d)
 {
     FastMod f;
     f.d = d;
     f.M = 0xFFFFFFFFFFFFFFFFull / d + 1;
+    f.pow2Mask = (d & (d - 1)) == 0 ? d - 1 : 0u;
     return f;
 }
 __device__ __forceinline__ unsigned fastmod_u32(unsigned a, const FastMod f)
 {
+    if (f.pow2Mask) return a & f.pow2Mask;  // uniform branch: one AND instead of two 64-bit multiplies
     const unsigned long long low = f.M * a;
     return (unsigned)__umul64hi(low, (unsigned long long)f.d);
 }
@@ -137,32 +140,31 @@ __device__ __forceinline__ unsigned hash_key_fast(int hx, int hy, int hz, const 
 // One 32-byte record per sorted slot: {predicted xyz, cell tag} {registration-time xyz, particle id}.  Both distance tests
 // of a candidate read the same 32-byte sector; the second half is only fetched for candidates that pass the first test.
 //
-// Cell tag: the candidate's integer cell coordinates, each biased by 256 and clamped to [0, 507], in three 10-bit fields.
+// Cell tag: the candidate's integer cell coordinates, each reduced mod 256, in three 10-bit fields.
 // A bucket of the reference's table mixes particles of unrelated cells (tableSize is a power of two: 207 936 occupied cells
 // fold into 138 605 buckets on a flat 1024^2 sheet), so ~60 % of the candidates a particle meets cannot be neighbours at
-// all.  tag + (514 - own coordinate) per field lands in [512, 519] exactly when the candidate's cell is within -2 .. +5
-// cells of the particle's on that axis: ONE add and ONE masked compare reject every candidate whose cell is three or more
-// cells away on some axis, i.e. at least 2 cell widths apart, which the reference's `distance^2 < cellSpacing^2` test rejects
-// as well.  The filter is a superset test (clamping only shrinks differences), the float tests still decide, so the lists
-// stay bit-identical; it only removes the float work and the second half of the predicate for the foreign candidates.
+// all.  tag + (258 - own coordinate mod 256) per field has its low eight bits in [0, 7] exactly when the candidate's cell is
+// -2 .. +5 cells from the particle's on that axis (mod 256): ONE add and ONE masked compare reject every candidate whose
+// cell is three or more cells away on some axis, i.e. at least 2 cell widths apart, which the reference's
+// `distance^2 < cellSpacing^2` test rejects as well.  The filter is a superset test (a cell a multiple of 256 cells away
+// passes too and is then rejected by the float test), so the lists stay bit-identical; it only removes the float work and
+// the second half of the predicate for the foreign candidates.
+// (Round 1 clamped the coordinates to +-256 cells instead of wrapping them: correct, but on a cloth wider than 512 cells --
+// 4096^2 spans 1 820 -- most tags were clamped and the filter let nearly everything through.)
 struct __align__(32) SortedParticle {
     float4 pos;   // w = cell tag bits
     float4 init;  // w = particle id bits
 };
-constexpr unsigned CN_TAG_FIELD = 10, CN_TAG_BIAS = 256, CN_TAG_MAX = 507, CN_TAG_K = 514;
-constexpr unsigned CN_TAG_MASK = 0x3F8u | (0x3F8u << 10) | (0x3F8u << 20);
-constexpr unsigned CN_TAG_WANT = 0x200u | (0x200u << 10) | (0x200u << 20);
+constexpr unsigned CN_TAG_FIELD = 10, CN_TAG_K = 258;
+constexpr unsigned CN_TAG_MASK = 0xF8u | (0xF8u << 10) | (0xF8u << 20);
+constexpr unsigned CN_TAG_WANT = 0u;
 
-__device__ __forceinline__ unsigned cn_tag_coord(int i)
-{
-    const int b = i + (int)CN_TAG_BIAS;
-    return (unsigned)(b < 0 ? 0 : (b > (int)CN_TAG_MAX ? (int)CN_TAG_MAX : b));
-}
+__device__ __forceinline__ unsigned cn_tag_coord(int i) { return (unsigned)i & 255u; }  // two's complement: i mod 256
 __device__ __forceinline__ unsigned cn_cell_tag(int ix, int iy, int iz)
 {
     return cn_tag_coord(ix) | (cn_tag_coord(iy) << CN_TAG_FIELD) | (cn_tag_coord(iz) << (2 * CN_TAG_FIELD));
 }
-// what a particle adds to a candidate's tag
+// what a particle adds to a candidate's tag: per field in [3, 258], so tag + probe <= 513 never carries into the next field
 __device__ __forceinline__ unsigned cn_cell_probe(int ix, int iy, int iz)
 {
     return (CN_TAG_K - cn_tag_coord(ix)) | ((CN_TAG_K - cn_tag_coord(iy)) << CN_TAG_FIELD) |

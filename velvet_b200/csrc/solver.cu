@@ -1319,7 +1319,7 @@ void VtClothSolverGPU::recordDDFrame()
     const VtSimParams& P = simParams;
     const uint N = P.numParticles;
     if (m_ddStrip) {
-        recordDDStripFrame();
+        recordDDStripFrame(nullptr);
         return;
     }
     const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
@@ -1418,7 +1418,7 @@ void VtClothSolverGPU::recordDDFrame()
 //   all-gather of the owned range (peer stores), then Finalize + Predict on every rank for every particle, which keeps
 //   pos4 / vel4 / the public buffers identical everywhere (collide reads pos4 of arbitrary neighbours).
 // The signal / wait pairs are the "I have stopped reading the buffer you are about to write" handshakes.
-void VtClothSolverGPU::recordDDStripFrame()
+void VtClothSolverGPU::recordDDStripFrame(Stage* t)
 {
     const VtSimParams& P = simParams;
     const uint N = P.numParticles;
@@ -1455,16 +1455,21 @@ void VtClothSolverGPU::recordDDStripFrame()
         launches++;
     };
 
+    STAGE_BEGIN(t, "DD_BeginFrame(replicated)");
     ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()), m_slotsDev,
                        (uint)(3 * attachSlotPositions.size()), fp);
     ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
                     m_pos4, m_vel4, buf[cur], m_prepared, fp);
     launches += 2;
+    STAGE_END(t);
     const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
     const bool odd = RadixSorter::numPasses(maxBit) & 1;
     for (int substep = 0; substep < P.numSubsteps; substep++) {
+        STAGE_BEGIN(t, "DD_Sync");
         signal();  // begin_frame / end_substep are done with `other` (and with `cur` as an output): the neighbours may write rows
+        STAGE_END(t);
         if (P.enableSelfCollision && substep % P.interleavedHash == 0) {
+            STAGE_BEGIN(t, "DD_HashKeysSortCells(replicated)");
             uint* k0 = odd ? m_keysAlt.data() : H.particleHash.data();
             uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
             uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
@@ -1473,6 +1478,8 @@ void VtClothSolverGPU::recordDDStripFrame()
             m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
             exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
             launches += 2 + m_sorter.lastLaunchCount();
+            STAGE_END(t);
+            STAGE_BEGIN(t, "DD_NeighborCache(reorder replicated, walk owned)");
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
                                                                          m_init4, m_sorted, hp, m_instancing, m_ddStripMask, count)) {
@@ -1481,14 +1488,20 @@ void VtClothSolverGPU::recordDDStripFrame()
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
                 launches++;
             }
+            STAGE_END(t);
         }
+        STAGE_BEGIN(t, "DD_Collide(owned)");
         ops.collide_range(L, buf[cur], buf[other], m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0, begin, count);
         launches++;
+        STAGE_END(t);
+        STAGE_BEGIN(t, "DD_Sync");
         wait_all();  // every peer is past its end_substep: its `other` may take rows
         A.which = other;
         ddpeer::launch_strip_push_rows(m_stream, A, buf[other], side);
         launches++;
+        STAGE_END(t);
         std::swap(cur, other);
+        STAGE_BEGIN(t, "DD_Iterate(owned, exchange fused)");
         for (int iteration = 0; iteration < P.numIterations; iteration++) {
             A.which = other;
             // The last iteration stores every result into every peer: the per-substep all-gather overlaps the Jacobi math.
@@ -1500,6 +1513,8 @@ void VtClothSolverGPU::recordDDStripFrame()
             std::swap(cur, other);
         }
         A.gatherAll = 0;
+        STAGE_END(t);
+        STAGE_BEGIN(t, "DD_Sync");
         if (P.numIterations <= 0) {  // nothing to ride on: gather the collide output with a launch of its own
             signal();
             wait_all();
@@ -1509,14 +1524,19 @@ void VtClothSolverGPU::recordDDStripFrame()
             signal();  // stream order: the whole last iteration, all its peer stores included, is behind this
         }
         wait_all();
+        STAGE_END(t);
+        STAGE_BEGIN(t, "DD_Finalize(replicated)");
         const bool last = substep == P.numSubsteps - 1;
         ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
                         reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
         launches++;
+        STAGE_END(t);
         if (!last) std::swap(cur, other);
     }
+    STAGE_BEGIN(t, "DD_Normals(replicated)");
     ops.normals(L, m_pos4, indices, m_vtxTriOff, m_vtxTris, reinterpret_cast<float*>(normals.data()), m_instancing);
     launches++;
+    STAGE_END(t);
     VT_CUDA(cudaGetLastError());
     m_ddGraphLaunches = launches;
 }
@@ -1534,6 +1554,18 @@ void VtClothSolverGPU::ddSimulate(float frameTime)
     hp.xpbdBend = simParams.bendCompliance / hp.substepTime / hp.substepTime;
     hp.numColliders = (uint)sdfColliders.size();
     VT_CUDA(cudaMemcpyAsync(m_frameParams.data(), &hp, sizeof(hp), cudaMemcpyHostToDevice, m_stream));
+    if (m_ddStrip && getenv("VELVET_DD_TIMING")) {  // diagnostic: the frame un-graphed with an event pair per stage (every rank alike)
+        Stage timing(m_stream);
+        recordDDStripFrame(&timing);
+        const StageTiming r = timing.collect();
+        if (m_dd.rank == 0) {
+            std::string line = "[velvet dd timing, rank 0, ms]";
+            for (size_t i = 0; i < r.labels.size(); i++) line += " " + r.labels[i] + "=" + std::to_string(r.ms[i]);
+            fprintf(stderr, "%s\n", line.c_str());
+        }
+        m_lastLaunches = m_ddGraphLaunches;
+        return;
+    }
     const unsigned long long key = topologyKey() | 1ull;
     if (!m_ddGraphExec || key != m_ddGraphKey) {
         if (m_ddGraphExec) cudaGraphExecDestroy(m_ddGraphExec);

@@ -247,7 +247,7 @@ private:
     DeviceBuffer<float4> m_ddSendBuf, m_ddRecvBuf, m_ddGatherSend, m_ddGatherRecv;
     float4 *m_ddCur = nullptr, *m_ddOther = nullptr;
     void recordDDFrame();
-    void recordDDStripFrame();
+    void recordDDStripFrame(Stage* timing);
     void ddSetupTiles();
     bool m_ddTilesReady = false;
     bool m_ddStrip = false;                 // single grid cloth: strips of tile rows, exchange fused into iterate_grid_kernel
