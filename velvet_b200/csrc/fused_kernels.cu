@@ -846,23 +846,23 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
 #else
         {
             // the bend first (it needs the most registers; its three far-corner corrections leave for their slots at once),
-            // then the four stretches.  p0 p1 p2 p3 = c00 c11 c01 c10: e = p3 - p2 = -dA, p2 - p0 = -dV, p3 - p0 = -dH
+            // then the four stretches.  p0 p1 p2 p3 = c00 c11 c01 c10: e = p3 - p2 = -dA, p2 - p0 = -dV, p3 - p0 = -dH.
+            // ONE rarely taken branch per bundle redoes whatever left the fast-path windows (degenerate or non-finite geometry).
             bool okLenA = true;
-            const float lenA = vt_sqrt_u(dot(dA, dA), okLenA);
+            const float lenA = vt_sqrt_dist_u(dot(dA, dA), okLenA);
             bool okB = okLenA;
             const bool aB = bend_eval_dv_u(-dA, lenA, -dV, -dH, V3(c10) - V3(c11), V3(c01) - V3(c11), c00.w, c11.w, c01.w, c10.w,
                                            restAngle, xpbd_bend, oB.c0, oB.c1, oB.c2, oB.c3, okB) && vQ;
             if (!aB) oB.c0 = oB.c1 = oB.c2 = oB.c3 = V3(0, 0, 0);
             oB.flag = aB ? 1.0f : 0.0f;
-            if (vQ && !okB) oB = grid_bend_slow(c00, c11, c01, c10, restAngle, xpbd_bend);
             s_slots[5][tid] = F4(oB.c1, oB.flag);  // bending p1 -> c11
             s_slots[6][tid] = F4(oB.c3, oB.flag);  // bending p3 -> c10
             s_slots[7][tid] = F4(oB.c2, oB.flag);  // bending p2 -> c01
 
             bool okV = true, okH = true, okD = true, okA = okLenA;
-            StretchHalf hV = stretch_begin_len(dV, vt_sqrt_u(dot(dV, dV), okV), c00.w, c01.w, rest.x);
-            StretchHalf hH = stretch_begin_len(dH, vt_sqrt_u(dot(dH, dH), okH), c00.w, c10.w, rest.y);
-            StretchHalf hD = stretch_begin_len(dD, vt_sqrt_u(dot(dD, dD), okD), c00.w, c11.w, rest.z);
+            StretchHalf hV = stretch_begin_len(dV, vt_sqrt_dist_u(dot(dV, dV), okV), c00.w, c01.w, rest.x);
+            StretchHalf hH = stretch_begin_len(dH, vt_sqrt_dist_u(dot(dH, dH), okH), c00.w, c10.w, rest.y);
+            StretchHalf hD = stretch_begin_len(dD, vt_sqrt_dist_u(dot(dD, dD), okD), c00.w, c11.w, rest.z);
             StretchHalf hA = stretch_begin_len(dA, lenA, c01.w, c10.w, rest.w);
             hV.active = hV.active && vV;
             hH.active = hH.active && vH;
@@ -870,22 +870,32 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             hA.active = hA.active && vQ;
             oV.c1 = oV.c2 = oH.c1 = oH.c2 = oD.c1 = oD.c2 = oA.c1 = oA.c2 = V3(0, 0, 0);
             if (hV.active || hH.active || hD.active || hA.active) {  // a freely falling, undeformed cloth keeps every distance at rest: no divisions then
-                // an inactive constraint (or one whose vertices lie outside the cloth: the staged values there are stale but
-                // finite) gets lambda = 0, hence corrections of +-0
-                stretch_finish_masked_u(hV, c00.w, c01.w, rest.x, oV.c1, oV.c2, okV);
-                stretch_finish_masked_u(hH, c00.w, c10.w, rest.y, oH.c1, oH.c2, okH);
-                stretch_finish_masked_u(hD, c00.w, c11.w, rest.z, oD.c1, oD.c2, okD);
-                stretch_finish_masked_u(hA, c01.w, c10.w, rest.w, oA.c1, oA.c2, okA);
+                // (distance - rest) / (w1 + w2): the four denominators are powers of two for unit inverse masses, a division by
+                // which is an exact multiplication -- tested once for the bundle
+                float sV, sH, sD, sA;
+                const bool pV = vt_pow2_rcp(hV.denom, sV), pH = vt_pow2_rcp(hH.denom, sH), pD = vt_pow2_rcp(hD.denom, sD),
+                           pA = vt_pow2_rcp(hA.denom, sA);
+                const bool pow2 = pV && pH && pD && pA;
+                stretch_finish_grid_u(hV, c00.w, c01.w, rest.x, pow2, sV, oV.c1, oV.c2, okV);
+                stretch_finish_grid_u(hH, c00.w, c10.w, rest.y, pow2, sH, oH.c1, oH.c2, okH);
+                stretch_finish_grid_u(hD, c00.w, c11.w, rest.z, pow2, sD, oD.c1, oD.c2, okD);
+                stretch_finish_grid_u(hA, c01.w, c10.w, rest.w, pow2, sA, oA.c1, oA.c2, okA);
             }
             oV.flag = hV.active ? 1.0f : 0.0f;
             oH.flag = hH.active ? 1.0f : 0.0f;
             oD.flag = hD.active ? 1.0f : 0.0f;
             oA.flag = hA.active ? 1.0f : 0.0f;
-            if ((vV && !okV) || (vH && !okH) || (vQ && !(okD && okA))) {  // rare: degenerate or non-finite geometry
+            if ((vV && !okV) || (vH && !okH) || (vQ && !(okD && okA && okB))) {
                 if (vV && !okV) oV = grid_stretch_slow(c00, c01, rest.x);
                 if (vH && !okH) oH = grid_stretch_slow(c00, c10, rest.y);
                 if (vQ && !okD) oD = grid_stretch_slow(c00, c11, rest.z);
                 if (vQ && !okA) oA = grid_stretch_slow(c01, c10, rest.w);
+                if (vQ && !okB) {
+                    oB = grid_bend_slow(c00, c11, c01, c10, restAngle, xpbd_bend);
+                    s_slots[5][tid] = F4(oB.c1, oB.flag);
+                    s_slots[6][tid] = F4(oB.c3, oB.flag);
+                    s_slots[7][tid] = F4(oB.c2, oB.flag);
+                }
             }
         }
 #endif
