@@ -6,12 +6,30 @@
 // one cudaGraphLaunch on the solver's own stream; the graph is re-captured only when the topology changes
 // (particle/constraint counts, substeps, iterations, hash interleave, buffer reallocation).
 #include "solver.hpp"
+#include "setup_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <chrono>
+#include <cstdio>
 
 namespace velvet {
+
+// VELVET_SETUP_TIMING=1: wall time of the phases of registration and of the first Simulate, on stderr (diagnostic)
+struct SetupClock {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    SetupClock() : on(getenv("VELVET_SETUP_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[velvet setup] %-44s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 void default_sim_params(VtSimParams& p)
 {
@@ -383,6 +401,7 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
         throw Error(VELVET_ERR_INVALID_ARGUMENT, "AddCloth: at most 2^30 - 1 particles (the hash table has 2 * numParticles int rows)");
     VT_CUDA(cudaSetDevice(m_device));
     Synchronize();
+    SetupClock clk;
     const int prevNumParticles = (int)simParams.numParticles;
     const int newParticles = numVertices;
     m_clothRanges.push_back(ClothRange{(uint)prevNumParticles, (uint)newParticles});
@@ -393,27 +412,57 @@ int VtClothSolverGPU::AddCloth(const float* vertices, int numVertices, const uin
     simParams.deltaTime = kFixedDeltaTime;
     simParams.maxSpeed = 2 * particleDiameter / kFixedDeltaTime * simParams.numSubsteps;
 
-    positions.registerNewBuffer(reinterpret_cast<const vec3*>(vertices), (size_t)newParticles);
-    normals.registerNewBuffer(nullptr, (size_t)newParticles);
+    if (deviceRegistration()) {
+        // every per-particle array is filled on the device, in pages created there (VtBuffer::extendOnDevice)
+        const size_t n = (size_t)newParticles;
+        cudaStream_t st = m_stream;
+        vec3* pos = positions.registerNewBufferOnDevice(n, m_device, st);
+        VT_CUDA(cudaMemcpyAsync(pos, vertices, n * sizeof(vec3), cudaMemcpyHostToDevice, st));
+        VT_CUDA(cudaMemsetAsync(normals.registerNewBufferOnDevice(n, m_device, st), 0, n * sizeof(vec3), st));
+        clk.lap("AddCloth: positions + normals buffers");
+        uint* idx = indices.extendOnDevice((size_t)numIndices, m_device, st);
+        if (numIndices) {
+            VT_CUDA(cudaMemcpyAsync(idx, meshIndices, (size_t)numIndices * sizeof(uint), cudaMemcpyHostToDevice, st));
+            if (prevNumParticles) setup::offset_indices(idx, idx, (size_t)numIndices, (uint)prevNumParticles, st);
+        }
+        clk.lap("AddCloth: mesh indices");
+        VT_CUDA(cudaMemsetAsync(velocities.extendOnDevice(n, m_device, st), 0, n * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(predicted.extendOnDevice(n, m_device, st), 0, n * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(deltas.extendOnDevice(n, m_device, st), 0, n * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(deltaCounts.extendOnDevice(n, m_device, st), 0, n * sizeof(int), st));
+        const float one = 1.0f;
+        uint oneBits;
+        std::memcpy(&oneBits, &one, 4);
+        setup::fill_words(invMasses.extendOnDevice(n, m_device, st), n, oneBits, st);
+        clk.lap("AddCloth: velocity/predicted/delta/mass buffers");
+    } else {
+        positions.registerNewBuffer(reinterpret_cast<const vec3*>(vertices), (size_t)newParticles);
+        normals.registerNewBuffer(nullptr, (size_t)newParticles);
+        clk.lap("AddCloth: positions + normals buffers");
 
-    std::vector<uint> shifted((size_t)numIndices);
-    for (int i = 0; i < numIndices; i++) shifted[i] = meshIndices[i] + (uint)prevNumParticles;
-    indices.push_back(shifted);
+        std::vector<uint> shifted((size_t)numIndices);
+        for (int i = 0; i < numIndices; i++) shifted[i] = meshIndices[i] + (uint)prevNumParticles;
+        indices.push_back(shifted);
+        clk.lap("AddCloth: mesh indices");
 
-    velocities.push_back((size_t)newParticles, V3(0, 0, 0));
-    predicted.push_back((size_t)newParticles, V3(0, 0, 0));
-    deltas.push_back((size_t)newParticles, V3(0, 0, 0));
-    deltaCounts.push_back((size_t)newParticles, 0);
-    invMasses.push_back((size_t)newParticles, 1.0f);
+        velocities.push_back((size_t)newParticles, V3(0, 0, 0));
+        predicted.push_back((size_t)newParticles, V3(0, 0, 0));
+        deltas.push_back((size_t)newParticles, V3(0, 0, 0));
+        deltaCounts.push_back((size_t)newParticles, 0);
+        invMasses.push_back((size_t)newParticles, 1.0f);
+        clk.lap("AddCloth: velocity/predicted/delta/mass buffers");
+    }
 
     // world transform on the device, hpp L143-145
     seam::InitializePositions(reinterpret_cast<float*>(positions.data()), prevNumParticles, newParticles, modelMatrix16, m_stream);
     Synchronize();
+    clk.lap("AddCloth: world transform");
 
     // hash sized to the total particle count; snapshot taken after the transform, hpp L148-149
     m_spatialHash = std::make_shared<SpatialHashGPU>(particleDiameter, (int)simParams.numParticles,
                                                      simParams.hashCellSizeScalar, simParams.maxNumNeighbors, m_hashHostReadable);
     m_spatialHash->SetInitialPositions(reinterpret_cast<const float*>(positions.data()), positions.size());
+    clk.lap("AddCloth: spatial hash");
     invalidate();
     return prevNumParticles;
 }
@@ -477,6 +526,119 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
     m_clothRanges.assign(1, ClothRange{0u, (uint)n});  // one topology, shared by every instance
     m_instanced = true;
     invalidate();
+}
+
+bool VtClothSolverGPU::deviceRegistration()
+{
+    const char* e = getenv("VELVET_HOST_GENERATE");
+    return !(e && *e && std::strcmp(e, "0") != 0);
+}
+
+void VtClothSolverGPU::GenerateGridClothOnDevice(int R, int base, const float* vertices, const float* M,
+                                                 const std::vector<int>& attachedIndices)
+{
+    if (R <= 0 || base < 0 || !vertices || !M) throw Error(VELVET_ERR_INVALID_ARGUMENT, "GenerateGridClothOnDevice: bad argument");
+    const size_t nv = (size_t)(R + 1) * (R + 1);
+    if ((size_t)base + nv > positions.size() || indices.size() < (size_t)6 * R * R)
+        throw Error(VELVET_ERR_STATE, "GenerateGridClothOnDevice: the cloth is not registered (AddCloth first)");
+    quiesce();
+    SetupClock clk;
+    cudaStream_t st = m_stream;
+    const float* world = reinterpret_cast<const float*>(positions.data());  // AddCloth has applied the model matrix
+    GeneratedCloth g;
+    g.base = (uint)base;
+    g.R = R;
+    g.stretchBegin = stretchLengths.size();
+    g.bendBegin = bendAngles.size();
+    g.attachBegin = attachParticleIDs.size();
+    g.numSlots = (uint)attachedIndices.size();
+    g.firstSlot = (uint)attachSlotPositions.size();
+
+    // GenerateStretch, VtClothObjectGPU.hpp L75-116
+    const size_t numStretch = 4 * (size_t)R * R + 2 * (size_t)R;
+    int* sIdx = stretchIndices.extendOnDevice(2 * numStretch, m_device, st);
+    float* sLen = stretchLengths.extendOnDevice(numStretch, m_device, st);
+    setup::generate_stretch(sIdx, sLen, world, (uint)base, R, st);
+
+    // GenerateAttach, L134-148: AddAttachSlot, then that slot's constraint for every particle, slot by slot
+    for (size_t slot = 0; slot < attachedIndices.size(); slot++) {
+        const int a = attachedIndices[slot];
+        if (a < 0 || (size_t)a >= nv) throw Error(VELVET_ERR_INVALID_ARGUMENT, "attached index out of range");
+        const vec3 slotPos = mul_point(M, load3(vertices, (size_t)a), 1.0f);  // the bits the device transform produced
+        attachSlotPositions.push_back(slotPos);
+        int* pid = attachParticleIDs.extendOnDevice(nv, m_device, st);
+        int* sid = attachSlotIDs.extendOnDevice(nv, m_device, st);
+        float* dist = attachDistances.extendOnDevice(nv, m_device, st);
+        setup::generate_attach(pid, sid, dist, world, invMasses.data(), (uint)base, (uint)nv, (int)(g.firstSlot + slot), slotPos, st);
+    }
+
+    // GenerateBending, L118-132: the triangles' own indices (i, i+5, i+2, i+1), rest angle 0
+    const size_t numQuads = (size_t)R * R;
+    const size_t meshBegin = indices.size() - 6 * numQuads;  // this cloth's (shifted) triangles: the last AddCloth's
+    uint* bIdx = bendIndices.extendOnDevice(4 * numQuads, m_device, st);
+    float* bAng = bendAngles.extendOnDevice(numQuads, m_device, st);
+    setup::generate_bend(bIdx, bAng, indices.data() + meshBegin, numQuads, st);
+    m_generated.push_back(g);
+    invalidate();
+    VT_CUDA(cudaStreamSynchronize(st));  // the lists are public: the host may index them as soon as Start returns
+    clk.lap("Start: constraint lists (device)");
+}
+
+bool VtClothSolverGPU::generatedListsIntact() const
+{
+    if (m_instanced || m_generated.size() != m_clothRanges.size() || m_generated.empty()) return false;
+    size_t s = 0, b = 0, a = 0;
+    uint slots = 0;
+    for (size_t k = 0; k < m_generated.size(); k++) {
+        const GeneratedCloth& g = m_generated[k];
+        const size_t nv = (size_t)(g.R + 1) * (g.R + 1);
+        if (g.base != m_clothRanges[k].base || nv != m_clothRanges[k].count) return false;
+        if (g.stretchBegin != s || g.bendBegin != b || g.attachBegin != a || g.firstSlot != slots) return false;
+        s += 4 * (size_t)g.R * g.R + 2 * (size_t)g.R;
+        b += (size_t)g.R * g.R;
+        a += nv * g.numSlots;
+        slots += g.numSlots;
+    }
+    return s == stretchLengths.size() && b == bendAngles.size() && a == attachParticleIDs.size() &&
+           slots == attachSlotPositions.size();
+}
+
+// The implicit-grid plan of generated cloths, on the device (grid_plan.cpp is the host builder for everything else).
+// Leaves m_setupFlags[1] != 0 when the mesh was not triangulated like the reference's grid.
+bool VtClothSolverGPU::buildGridPlanOnDevice(uint planN, cudaStream_t st)
+{
+    if (m_generated.size() > GRID_MAX_CLOTHS) return false;
+    GridPlan plan;
+    uint tiles = 0;
+    for (const GeneratedCloth& g : m_generated) {
+        GridCloth gc;
+        gc.base = g.base;
+        gc.side = (uint)g.R + 1;
+        gc.tilesY = (gc.side + GRID_TILE - 1) / GRID_TILE;
+        gc.firstTile = tiles;
+        tiles += gc.tilesY * gc.tilesY;
+        plan.cloths.push_back(gc);
+    }
+    plan.numTiles = tiles;
+    plan.valid = true;
+    const size_t numAttach = attachParticleIDs.size();
+    m_gCloths.upload(plan.cloths, st);
+    m_gRest4.allocate(planN);
+    m_gAngle.release();  // every generated quad rests flat: the kernel takes the angle as a scalar
+    m_gAttOff.allocate((size_t)planN + 1);
+    m_gAttachRec.allocate(numAttach + 1);
+    uint attBase = 0;
+    for (const GeneratedCloth& g : m_generated) {
+        const uint nv = (uint)((g.R + 1) * (g.R + 1));
+        setup::grid_plan_from_lists(m_gRest4, stretchLengths.data() + g.stretchBegin, bendIndices.data() + 4 * g.bendBegin, g.base, g.R,
+                                    m_setupFlags.data() + 1, st);
+        setup::grid_attach_records(m_gAttOff, m_gAttachRec, attachDistances.data() + g.attachBegin, g.base, nv, g.numSlots, g.firstSlot,
+                                   attBase, st);
+        attBase += nv * g.numSlots;
+    }
+    setup::fill_words(m_gAttOff.data() + planN, 1, attBase, st);
+    m_gridPlan = std::move(plan);
+    return true;
 }
 
 void VtClothSolverGPU::AddStretch(int idx1, int idx2, float distance)
@@ -724,6 +886,7 @@ void VtClothSolverGPU::ensureFusedResources()
     }
     m_initDirty = false;  // the rebuild below packs the current initialPositions
     Synchronize();
+    SetupClock clk;
     const uint N = simParams.numParticles;
     if (!m_instanced) m_instancing = Instancing{1u, N, (uint)attachSlotPositions.size()};
     const uint planN = m_instancing.particles;  // the tile plan / vertex CSR cover one instance
@@ -743,27 +906,55 @@ void VtClothSolverGPU::ensureFusedResources()
         return;
     }
 
-    for (size_t i = 0; i < attachSlotIDs.size(); i++)
-        if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= (size_t)m_instancing.slots) {
-            m_fallbackReason = "attach slot index out of range";
-            return;
-        }
-    for (size_t i = 0; i < indices.size(); i++)
-        if (indices[i] >= planN) {
-            m_fallbackReason = "triangle index out of range";
-            return;
-        }
-
     cudaStream_t st = m_stream;
+    // lists that are exactly what GenerateGridClothOnDevice wrote stay on the device: the checks below run there too
+    const bool generated = generatedListsIntact();
+    if (!generated)
+        for (size_t i = 0; i < attachSlotIDs.size(); i++)
+            if (attachSlotIDs[i] < 0 || (size_t)attachSlotIDs[i] >= (size_t)m_instancing.slots) {
+                m_fallbackReason = "attach slot index out of range";
+                return;
+            }
+
+    // vertex -> incident triangles (ascending triangle id) and the mesh index range check, on the device
+    m_setupFlags.allocate(2);
+    VT_CUDA(cudaMemsetAsync(m_setupFlags.data(), 0, 2 * sizeof(int), st));
+    {
+        const size_t numIdx = indices.size() - indices.size() % 3;
+        m_vtxTriOff.allocate((size_t)planN + 1);
+        m_vtxTris.allocate(std::max<size_t>(numIdx, 1));
+        DeviceBuffer<uint> cursor;
+        cursor.allocate(planN);
+        clk.lap("  vtx-tri: allocations");
+        setup::vertex_triangles(indices.data(), numIdx, planN, m_vtxTriOff, m_vtxTris, cursor, m_setupFlags.data(), st);
+        clk.lap("  vtx-tri: launches");
+        VT_CUDA(cudaStreamSynchronize(st));  // `cursor` goes out of scope
+        clk.lap("  vtx-tri: sync");
+    }
+    clk.lap("resources: vertex -> triangle lists (device)");
+
     m_tilePlanBuilt = false;
     // grid cloths carrying exactly the reference's constraint pattern get the implicit-grid kernel (grid_plan.hpp)
     m_gridUsable = false;
     m_gridPlan = GridPlan{};
-    {
-        int mode = m_iterateMode;
-        if (const char* e = getenv("VELVET_ITERATE"))
-            if (std::string(e) == "tiles") mode = VELVET_ITERATE_TILES;
-        if (mode == VELVET_ITERATE_AUTO) {
+    int mode = m_iterateMode;
+    if (const char* e = getenv("VELVET_ITERATE"))
+        if (std::string(e) == "tiles") mode = VELVET_ITERATE_TILES;
+    bool planOnDevice = false;
+    if (mode == VELVET_ITERATE_AUTO && generated) planOnDevice = buildGridPlanOnDevice(planN, st);
+    int flags[2] = {0, 0};
+    VT_CUDA(cudaMemcpyAsync(flags, m_setupFlags.data(), sizeof(flags), cudaMemcpyDeviceToHost, st));
+    VT_CUDA(cudaStreamSynchronize(st));
+    if (flags[0]) {
+        m_fallbackReason = "triangle index out of range";
+        return;
+    }
+    if (planOnDevice && flags[1]) {  // a mesh triangulated differently: the host builder below says why and the tile plan takes over
+        planOnDevice = false;
+        m_gridPlan = GridPlan{};
+    }
+    if (mode == VELVET_ITERATE_AUTO) {
+        if (!planOnDevice) {
             m_gridPlan = build_grid_plan(planN, m_clothRanges, stretchIndices.data(), stretchLengths.data(), stretchLengths.size(),
                                          bendIndices.data(), bendAngles.data(), bendAngles.size(), attachParticleIDs.data(),
                                          attachSlotIDs.data(), attachDistances.data(), attachParticleIDs.size());
@@ -773,48 +964,41 @@ void VtClothSolverGPU::ensureFusedResources()
                 m_gAngle.upload(m_gridPlan.restAngle, st);
                 m_gAttOff.upload(m_gridPlan.attOff, st);
                 m_gAttachRec.upload(reinterpret_cast<const uint2*>(m_gridPlan.attachRec.data()), m_gridPlan.attachRec.size() / 2, st);
-                m_gridDev.cloths = m_gCloths;
-                m_gridDev.rest4 = m_gRest4;
-                m_gridDev.restAngle = m_gAngle;
-                m_gridDev.uniformAngle = 0.0f;
-                {  // one rest angle for every quad (what the reference registers): the kernel takes it as a scalar
-                    bool uniform = true;
-                    for (size_t i = 1; i < bendAngles.size() && uniform; i++) uniform = bendAngles[i] == bendAngles[0];
-                    if (uniform && bendAngles.size()) {
-                        m_gridDev.restAngle = nullptr;
-                        m_gridDev.uniformAngle = bendAngles[0];
-                    }
-                }
-                m_gridDev.attOff = m_gAttOff;
-                m_gridDev.attachRec = m_gAttachRec;
-                m_gridDev.numCloths = (uint)m_gridPlan.cloths.size();
-                m_gridDev.numTiles = m_gridPlan.numTiles;
-                m_gridDev.tilesY0 = m_gridPlan.cloths[0].tilesY;
-                m_gridDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
-                m_gridDev.residentCtas = std::min(exact_math::configure_iterate_grid_kernel(), fast_math::configure_iterate_grid_kernel());
-                m_gridUsable = true;
             }
         }
+        if (m_gridPlan.valid) {
+            m_gridDev.cloths = m_gCloths;
+            m_gridDev.rest4 = m_gRest4;
+            m_gridDev.restAngle = m_gAngle;
+            m_gridDev.uniformAngle = 0.0f;
+            if (planOnDevice) {
+                m_gridDev.restAngle = nullptr;  // generated quads rest flat
+            } else {  // one rest angle for every quad (what the reference registers): the kernel takes it as a scalar
+                bool uniform = true;
+                for (size_t i = 1; i < bendAngles.size() && uniform; i++) uniform = bendAngles[i] == bendAngles[0];
+                if (uniform && bendAngles.size()) {
+                    m_gridDev.restAngle = nullptr;
+                    m_gridDev.uniformAngle = bendAngles[0];
+                }
+            }
+            m_gridDev.attOff = m_gAttOff;
+            m_gridDev.attachRec = m_gAttachRec;
+            m_gridDev.numCloths = (uint)m_gridPlan.cloths.size();
+            m_gridDev.numTiles = m_gridPlan.numTiles;
+            m_gridDev.tilesY0 = m_gridPlan.cloths[0].tilesY;
+            m_gridDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
+            m_gridDev.residentCtas = std::min(exact_math::configure_iterate_grid_kernel(), fast_math::configure_iterate_grid_kernel());
+            m_gridUsable = true;
+        }
     }
+    clk.lap(planOnDevice ? "resources: grid plan (device)" : "resources: grid plan (host) + upload");
 
     // the record-driven tile plan (0.35 s of host work per million particles) only when the grid kernel cannot run; the
     // decomposed tile form and the plan accessors build it on demand (ensureTilePlan)
     if (!m_gridUsable && !buildTilePlan()) return;
+    clk.lap("resources: tile plan");
 
-    // vertex -> incident triangles, ascending triangle id
-    {
-        const size_t T = indices.size() / 3;
-        std::vector<uint> off((size_t)planN + 1, 0), tris(3 * T);
-        for (size_t i = 0; i < 3 * T; i++) off[indices[i] + 1]++;
-        for (uint v = 0; v < planN; v++) off[v + 1] += off[v];
-        std::vector<uint> cur(off.begin(), off.end() - 1);
-        for (size_t tIdx = 0; tIdx < T; tIdx++)
-            for (int k = 0; k < 3; k++) tris[cur[indices[3 * tIdx + k]]++] = (uint)tIdx;
-        if (tris.empty()) tris.push_back(0);
-        m_vtxTriOff.upload(off, st);
-        m_vtxTris.upload(tris, st);
-    }
-
+    clk.lap("  (before allocations)");
     m_pos4.allocate(N);
     m_vel4.allocate(N);
     // at least 2 MB each: the decomposed mode exports them over CUDA IPC and must not share a driver slab with other arrays
@@ -827,9 +1011,12 @@ void VtClothSolverGPU::ensureFusedResources()
     m_prepared.allocate(VT_MAX_COLLIDERS);
     m_frameParams.allocate(1);
     m_slotsDev.allocate(std::max<size_t>(3 * attachSlotPositions.size(), 3));
+    clk.lap("  allocations: cudaMalloc x 11");
     m_sorter.reserve(N);
+    clk.lap("  allocations: sorter");
     FusedLaunch L{st, N};
     exact_math::launch_pack_float4(L, reinterpret_cast<const float*>(m_spatialHash->initialPositions.data()), m_init4, N);
+    clk.lap("resources: device allocations");
 
     // the big public buffers live in managed memory (reference contract): make them device-resident now
     auto prefetch = [&](const void* p, size_t bytes) {
@@ -843,6 +1030,7 @@ void VtClothSolverGPU::ensureFusedResources()
     prefetch(indices.data(), indices.size() * sizeof(uint));
     (void)cudaGetLastError();  // prefetch is best effort
     VT_CUDA(cudaStreamSynchronize(st));
+    clk.lap("resources: prefetch + sync");
     m_fusedUsable = true;
 }
 
@@ -1634,6 +1822,7 @@ void VtClothSolverGPU::Simulate(float frameTime)
             cudaGraphDestroy(m_graph);
             m_graph = nullptr;
         }
+        SetupClock clk;
         VT_CUDA(cudaStreamBeginCapture(m_stream, cudaStreamCaptureModeThreadLocal));
         try {
             recordFusedFrame(nullptr);
@@ -1646,6 +1835,7 @@ void VtClothSolverGPU::Simulate(float frameTime)
         VT_CUDA(cudaStreamEndCapture(m_stream, &m_graph));
         VT_CUDA(cudaGraphInstantiate(&m_graphExec, m_graph, 0));
         m_graphKey = key;
+        clk.lap("Simulate: graph capture + instantiate");
     }
     VT_CUDA(cudaGraphLaunch(m_graphExec, m_stream));
     m_mayBeBusy = true;
@@ -1896,8 +2086,14 @@ void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, con
     const size_t ni = (size_t)6 * R * R;
     m_particleDiameter = length_plain(load3(vertices, 0) - load3(vertices, 1)) * m_solver->simParams.particleDiameterScalar;  // L49
     m_indexOffset = m_solver->AddCloth(vertices, (int)nv, meshIndices, (int)ni, M, m_particleDiameter);
+    if (VtClothSolverGPU::deviceRegistration()) {
+        m_solver->GenerateGridClothOnDevice(R, m_indexOffset, vertices, M, m_attachedIndices);
+        return;
+    }
+    SetupClock clk;
     const GridConstraints g = GenerateGridConstraints(R, vertices, meshIndices, M, m_attachedIndices,
                                                       m_solver->simParams.particleDiameterScalar, m_indexOffset);
+    clk.lap("Start: GenerateGridConstraints (host)");
     m_solver->AddStretchBulk(g.stretchIdx.data(), g.stretchLen.data(), g.stretchLen.size());
     // AddAttachSlot then that slot's AddAttach calls, slot by slot (L134-148)
     for (size_t slot = 0; slot < m_attachedIndices.size(); slot++) {
@@ -1905,6 +2101,7 @@ void VtClothObjectGPU::Start(const float* vertices, const uint* meshIndices, con
         m_solver->AddAttachBulk(&g.attachPid[slot * nv], &g.attachSlot[slot * nv], &g.attachDist[slot * nv], nv);
     }
     m_solver->AddBendBulk(g.bendIdx.data(), g.bendAngle.data(), g.bendAngle.size());
+    clk.lap("Start: bulk registration");
 }
 
 }  // namespace velvet

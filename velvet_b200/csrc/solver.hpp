@@ -155,6 +155,13 @@ public:
     void ddSimulate(float frameTime);
     bool ddPeerError();  // true when a wait kernel timed out (peer missing); synchronises the stream
 
+    // VtClothObjectGPU::Start for a grid cloth whose particles AddCloth just registered at `base`: the stretch / attach /
+    // bending lists are written by kernels (setup_kernels.cuh), bit-identical to GenerateGridConstraints' and in its order.
+    void GenerateGridClothOnDevice(int resolution, int base, const float* vertices, const float* modelMatrix16,
+                                   const std::vector<int>& attachedIndices);
+    // false when VELVET_HOST_GENERATE is set (the host loops of round 1: kept for A/B tests of the lists)
+    static bool deviceRegistration();
+
     // bulk variants (one memcpy instead of a managed-memory push_back per element)
     void AddStretchBulk(const int* idxPairs, const float* distances, size_t n);
     void AddBendBulk(const uint* idxQuads, const float* angles, size_t n);
@@ -236,6 +243,18 @@ private:
     bool m_hashHostReadable = false;
     DeviceBuffer<unsigned> m_nanScratch;
     std::vector<ClothRange> m_clothRanges;  // particle range of every AddCloth call
+    // what GenerateGridClothOnDevice appended for each cloth: while the lists consist of exactly these ranges, the grid plan
+    // follows from the generator (no entry-by-entry check on the host, which would fault the lists back out of the device)
+    struct GeneratedCloth {
+        uint base;
+        int R;
+        size_t stretchBegin, bendBegin, attachBegin;
+        uint numSlots, firstSlot;
+    };
+    std::vector<GeneratedCloth> m_generated;
+    bool generatedListsIntact() const;
+    bool buildGridPlanOnDevice(uint planN, cudaStream_t st);
+    DeviceBuffer<int> m_setupFlags;  // [0] mesh index out of range, [1] bending quads differ from the grid pattern
     Instancing m_instancing{1, 0, 0};
     // domain decomposition state
     ExchangePlan m_dd;

@@ -74,6 +74,22 @@ public:
         m_count += n;
     }
 
+    // Appends `n` elements that the DEVICE is going to write (a generation kernel, an async copy): returns the first one.
+    // For managed memory the pages of the new range are created on `device` right away, so that neither the writing kernel
+    // nor the host faults on them (a host-side push_back of a million elements is a million first-touch stores into managed
+    // pages that a prefetch then has to move: the whole cost of registering a cloth).
+    T* extendOnDevice(size_t n, int device, cudaStream_t stream)
+    {
+        reserve(m_count + n);
+        T* first = m_data + m_count;
+        if (!m_deviceOnly && n) {
+            cudaMemPrefetchAsync(first, n * sizeof(T), device, stream);
+            (void)cudaGetLastError();  // best effort: without it the first kernel touching the range pays the faults
+        }
+        m_count += n;
+        return first;
+    }
+
     void reserve(size_t minCapacity)
     {
         if (minCapacity <= m_capacity) return;
@@ -220,6 +236,13 @@ public:
         if (src) std::memcpy(m_vbuffer.data() + offset, src, count * sizeof(T));
         else std::memset((void*)(m_vbuffer.data() + offset), 0, count * sizeof(T));
         return offset;
+    }
+    // Same bookkeeping, contents left to the device (see VtBuffer::extendOnDevice): returns the range's first element.
+    T* registerNewBufferOnDevice(size_t count, int device, cudaStream_t stream)
+    {
+        m_offsets.push_back(m_vbuffer.size());
+        m_counts.push_back(count);
+        return m_vbuffer.extendOnDevice(count, device, stream);
     }
     size_t size() const { return m_vbuffer.size(); }
     size_t numRanges() const { return m_offsets.size(); }
