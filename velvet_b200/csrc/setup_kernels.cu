@@ -27,6 +27,23 @@ __global__ void __launch_bounds__(PB) offset_indices_kernel(unsigned* __restrict
     if (i < n) dst[i] = src[i] + offset;
 }
 
+__global__ void __launch_bounds__(PB) instance_positions_kernel(float* __restrict__ positions, const float* __restrict__ vertices,
+                                                                const float* __restrict__ models, unsigned n)
+{
+    const unsigned i = blockIdx.x * PB + threadIdx.x;
+    if (i >= n) return;
+    const size_t k = blockIdx.y;
+    store3(positions, k * n + i, mul_point(models + 16 * k, load3(vertices, i), 1.0f));
+}
+
+__global__ void __launch_bounds__(PB) instance_pin_kernel(float* __restrict__ invMasses, const int* __restrict__ pinned, unsigned numPinned,
+                                                          unsigned n, unsigned numInstances)
+{
+    const size_t t = (size_t)blockIdx.x * PB + threadIdx.x;
+    if (t >= (size_t)numPinned * numInstances) return;
+    invMasses[(t / numPinned) * n + (size_t)pinned[t % numPinned]] = 0.0f;
+}
+
 // where the constraints generated at vertex (x, y) start in the cloth's stretch list
 __device__ __forceinline__ size_t stretch_slot(int x, int y, int R)
 {
@@ -162,6 +179,20 @@ void offset_indices(unsigned* dst, const unsigned* src, size_t n, unsigned offse
 {
     if (!n) return;
     offset_indices_kernel<<<blocks_for(n), PB, 0, st>>>(dst, src, n, offset);
+    VT_CUDA(cudaGetLastError());
+}
+
+void instance_positions(float* positions, const float* vertices, const float* models16, unsigned n, unsigned numInstances, cudaStream_t st)
+{
+    if (!n || !numInstances) return;
+    instance_positions_kernel<<<dim3(blocks_for(n), numInstances), PB, 0, st>>>(positions, vertices, models16, n);
+    VT_CUDA(cudaGetLastError());
+}
+
+void instance_pin(float* invMasses, const int* pinned, unsigned numPinned, unsigned n, unsigned numInstances, cudaStream_t st)
+{
+    if (!numPinned || !numInstances) return;
+    instance_pin_kernel<<<blocks_for((size_t)numPinned * numInstances), PB, 0, st>>>(invMasses, pinned, numPinned, n, numInstances);
     VT_CUDA(cudaGetLastError());
 }
 

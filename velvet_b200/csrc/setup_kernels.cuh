@@ -27,6 +27,11 @@ void fill_words(void* dst, size_t words, unsigned value, cudaStream_t st);
 // dst[i] = src[i] + offset (mesh indices of a cloth shifted to its place in the particle arrays)
 void offset_indices(unsigned* dst, const unsigned* src, size_t n, unsigned offset, cudaStream_t st);
 
+// Batched instances: positions[k * n + i] = model_k * vertices[i] for instance k (models: 16 floats per instance, device),
+// and invMasses[k * n + pinned[j]] = 0 for the particles an attach constraint pins
+void instance_positions(float* positions, const float* vertices, const float* models16, unsigned n, unsigned numInstances, cudaStream_t st);
+void instance_pin(float* invMasses, const int* pinned, unsigned numPinned, unsigned n, unsigned numInstances, cudaStream_t st);
+
 // GenerateStretch (L75-116): 4R^2 + 2R constraints of the cloth whose particles start at `base` (global index), emitted
 // vertex by vertex in (x, y) order: structural y, structural x, the two shear diagonals.
 void generate_stretch(int* idxPairs, float* lengths, const float* worldPositions, unsigned base, int R, cudaStream_t st);

@@ -491,19 +491,47 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
     simParams.maxSpeed = 2 * g.particleDiameter / kFixedDeltaTime * simParams.numSubsteps;
 
     // state for every instance; mesh indices / constraints once (per-instance local indices)
-    for (int k = 0; k < numInstances; k++) {
-        positions.registerNewBuffer(reinterpret_cast<const vec3*>(vertices), n);
-        normals.registerNewBuffer(nullptr, n);
+    const bool onDevice = deviceRegistration();
+    if (onDevice) {
+        // per-particle arrays of all instances written on the device, in pages created there (VtBuffer::extendOnDevice)
+        cudaStream_t st = m_stream;
+        DeviceBuffer<float> vtx, mdl;
+        vtx.upload(vertices, 3 * n, st);
+        mdl.upload(models, 16 * (size_t)numInstances, st);
+        vec3* pos = positions.registerNewBuffersOnDevice(n, (size_t)numInstances, m_device, st);
+        setup::instance_positions(reinterpret_cast<float*>(pos), vtx, mdl, (uint)n, (uint)numInstances, st);
+        VT_CUDA(cudaMemsetAsync(normals.registerNewBuffersOnDevice(n, (size_t)numInstances, m_device, st), 0, total * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(velocities.extendOnDevice(total, m_device, st), 0, total * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(predicted.extendOnDevice(total, m_device, st), 0, total * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(deltas.extendOnDevice(total, m_device, st), 0, total * sizeof(vec3), st));
+        VT_CUDA(cudaMemsetAsync(deltaCounts.extendOnDevice(total, m_device, st), 0, total * sizeof(int), st));
+        const float one = 1.0f;
+        uint oneBits;
+        std::memcpy(&oneBits, &one, 4);
+        float* w = invMasses.extendOnDevice(total, m_device, st);
+        setup::fill_words(w, total, oneBits, st);
+        std::vector<int> pinned;  // hpp L172, in every instance
+        for (size_t c = 0; c < g.attachDist.size(); c++)
+            if (g.attachDist[c] == 0) pinned.push_back(g.attachPid[c]);
+        DeviceBuffer<int> pinnedDev;
+        pinnedDev.upload(pinned, st);
+        setup::instance_pin(w, pinnedDev, (uint)pinned.size(), (uint)n, (uint)numInstances, st);
+        Synchronize();  // the staging arrays go out of scope
+    } else {
+        for (int k = 0; k < numInstances; k++) {
+            positions.registerNewBuffer(reinterpret_cast<const vec3*>(vertices), n);
+            normals.registerNewBuffer(nullptr, n);
+        }
+        velocities.push_back(total, V3(0, 0, 0));
+        predicted.push_back(total, V3(0, 0, 0));
+        deltas.push_back(total, V3(0, 0, 0));
+        deltaCounts.push_back(total, 0);
+        invMasses.push_back(total, 1.0f);
+        for (int k = 0; k < numInstances; k++)
+            seam::InitializePositions(reinterpret_cast<float*>(positions.data()), (int)(k * n), (int)n, models + 16 * (size_t)k, m_stream);
+        Synchronize();
     }
     indices.append(meshIndices, ni);
-    velocities.push_back(total, V3(0, 0, 0));
-    predicted.push_back(total, V3(0, 0, 0));
-    deltas.push_back(total, V3(0, 0, 0));
-    deltaCounts.push_back(total, 0);
-    invMasses.push_back(total, 1.0f);
-    for (int k = 0; k < numInstances; k++)
-        seam::InitializePositions(reinterpret_cast<float*>(positions.data()), (int)(k * n), (int)n, models + 16 * (size_t)k, m_stream);
-    Synchronize();
 
     stretchIndices.append(g.stretchIdx.data(), g.stretchIdx.size());
     stretchLengths.append(g.stretchLen.data(), g.stretchLen.size());
@@ -513,11 +541,13 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
     attachSlotIDs.append(g.attachSlot.data(), g.attachSlot.size());
     attachDistances.append(g.attachDist.data(), g.attachDist.size());
     // slot positions of every instance: the world position of the attached vertex under that instance's matrix
+    // (computed here with the function the device transform applies: indexing positions[] would fault device pages back)
     for (int k = 0; k < numInstances; k++)
-        for (int a : attached) attachSlotPositions.push_back(positions[k * n + (size_t)a]);
-    for (size_t c = 0; c < g.attachDist.size(); c++)
-        if (g.attachDist[c] == 0)  // hpp L172, in every instance
-            for (int k = 0; k < numInstances; k++) invMasses[k * n + (size_t)g.attachPid[c]] = 0;
+        for (int a : attached) attachSlotPositions.push_back(mul_point(models + 16 * (size_t)k, load3(vertices, (size_t)a), 1.0f));
+    if (!onDevice)
+        for (size_t c = 0; c < g.attachDist.size(); c++)
+            if (g.attachDist[c] == 0)  // hpp L172, in every instance
+                for (int k = 0; k < numInstances; k++) invMasses[k * n + (size_t)g.attachPid[c]] = 0;
 
     m_spatialHash = std::make_shared<SpatialHashGPU>(g.particleDiameter, (int)total, simParams.hashCellSizeScalar,
                                                      simParams.maxNumNeighbors, m_hashHostReadable);

@@ -244,6 +244,15 @@ public:
         m_counts.push_back(count);
         return m_vbuffer.extendOnDevice(count, device, stream);
     }
+    // `numRanges` equal ranges of `count` elements each in one go (batched instances): returns the first range's first element.
+    T* registerNewBuffersOnDevice(size_t count, size_t numRanges, int device, cudaStream_t stream)
+    {
+        for (size_t k = 0; k < numRanges; k++) {
+            m_offsets.push_back(m_vbuffer.size() + k * count);
+            m_counts.push_back(count);
+        }
+        return m_vbuffer.extendOnDevice(count * numRanges, device, stream);
+    }
     size_t size() const { return m_vbuffer.size(); }
     size_t numRanges() const { return m_offsets.size(); }
     size_t rangeOffset(size_t i) const { return m_offsets[i]; }
