@@ -280,6 +280,17 @@ VELVET_API int velvet_solver_set_hash_host_readable(VelvetSolver* s, int on);
 /* Debug guard (cf. VtClothSolverCPU::CheckNAN, VtClothSolverCPU.hpp L407-418): number of non-finite components in positions /
  * velocities / predicted, and the first offending particle (numParticles when none).  Synchronous. */
 VELVET_API int velvet_solver_check_nan(VelvetSolver* s, unsigned* nonFiniteCount, unsigned* firstParticle);
+/* MouseGrabber (MouseGrabber.hpp L31-110) on the device.  The reference walks every position on the HOST to find the vertex
+ * under the mouse ray and edits positions / velocities / invMass through managed memory; these three calls do the same work
+ * in kernels on the solver stream (the camera math that turns a mouse position into a ray, L112-130, stays with the caller).
+ *   grab:    FindClosestVertexToRay (L92-110) + pin (L46-52): *grabbedIndex = picked particle or -1, *distanceToOrigin its
+ *            distance along the ray (FLT_MAX when none); the particle's inverse mass becomes 0.  Synchronous (returns the pick).
+ *   drag:    UpdateGrappedVertex (L66-79) for the ray of this frame; no-op when nothing is grabbed.  Asynchronous.
+ *   release: mouse-up branch (L57-62): the inverse mass is restored.  Asynchronous. */
+VELVET_API int velvet_solver_grab(VelvetSolver* s, const float* rayOrigin3, const float* rayDirection3, int* grabbedIndex,
+                                  float* distanceToOrigin);
+VELVET_API int velvet_solver_drag(VelvetSolver* s, const float* rayOrigin3, const float* rayDirection3);
+VELVET_API int velvet_solver_release(VelvetSolver* s);
 /* Asynchronous read-back of positions+normals on the solver stream into pinned host memory (headless
  * replacement of positions.sync()/normals.sync(), hpp L109-110). */
 VELVET_API int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals);

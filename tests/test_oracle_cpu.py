@@ -339,3 +339,24 @@ def test_oracle_positions_within_tolerance_of_reference_kernel_golden_cube25():
             worst[f + 1] = float(np.max(np.abs(s.buffer("positions") - g[f"positions_{f + 1}"])))
     print("O1 vs reference CUDA kernels, 25x25 cloth on a turning cube, max |dx| per frame:", worst)
     assert worst[1] <= 1e-4 * 2.0 and worst[5] <= 1e-3 * 2.0 and worst[10] <= 1e-3 * 2.0, worst
+
+
+def test_grabber_restatement_known_answers():
+    """oracle/grabber.py (MouseGrabber.hpp L31-110): a ray through a chosen vertex picks it at its distance, the nearest of
+    several wins, ties go to the first index, a miss leaves -1 / FLT_MAX, drag moves 20 % of the way to the mouse point."""
+    from oracle.grabber import FLT_MAX, MouseGrabber, find_closest_vertex_to_ray
+    pos = np.array([[0, 0, 5], [0, 0, 3], [0.001, 0, 3], [0, 0, 9], [5, 5, 5]], np.float32)
+    o, d = np.zeros(3, np.float32), np.array([0, 0, 1], np.float32)
+    assert find_closest_vertex_to_ray(pos, o, d, 0.1) == (1, 3.0)
+    assert find_closest_vertex_to_ray(pos[[0, 3, 4]], o, d, 0.1) == (0, 5.0)
+    assert find_closest_vertex_to_ray(pos, o, np.array([0, 1, 0], np.float32), 0.1) == (-1, FLT_MAX)
+    # exactly one diameter away is NOT within reach (strict <)
+    assert find_closest_vertex_to_ray(np.array([[0.1, 0, 1]], np.float32), o, d, np.float32(0.1))[0] == -1
+    vel, inv = np.zeros((5, 3), np.float32), np.ones(5, np.float32)
+    m = MouseGrabber(pos, vel, inv, 0.1)
+    assert m.grab(o, d) == (1, 3.0) and inv[1] == 0 and m.grabbing
+    m.drag(np.array([1, 0, 0], np.float32), d)            # mouse point (1, 0, 3): the vertex moves 20 % of the way
+    assert np.allclose(pos[1], (0.2, 0, 3), atol=1e-6)
+    assert np.allclose(vel[1], (0.2 * 60, 0, 0), rtol=1e-5)
+    m.release()
+    assert inv[1] == 1 and not m.grabbing

@@ -64,7 +64,7 @@ EXPORTED_SYMBOLS = [
     "velvet_solver_add_attach_slot", "velvet_solver_add_attach", "velvet_solver_add_bend",
     "velvet_solver_update_colliders", "velvet_make_collider", "velvet_solver_simulate", "velvet_solver_simulate_dt",
     "velvet_solver_synchronize", "velvet_solver_hash", "velvet_solver_hash_fused", "velvet_solver_buffer", "velvet_solver_download",
-    "velvet_solver_upload", "velvet_solver_set_render_targets", "velvet_solver_sync_render_targets", "velvet_solver_set_hash_host_readable", "velvet_solver_check_nan", "velvet_solver_readback_async", "velvet_solver_readback_pipelined", "velvet_solver_readback_wait", "velvet_solver_stream",
+    "velvet_solver_upload", "velvet_solver_set_render_targets", "velvet_solver_sync_render_targets", "velvet_solver_set_hash_host_readable", "velvet_solver_check_nan", "velvet_solver_grab", "velvet_solver_drag", "velvet_solver_release", "velvet_solver_readback_async", "velvet_solver_readback_pipelined", "velvet_solver_readback_wait", "velvet_solver_stream",
     "velvet_solver_last_launch_count", "velvet_solver_simulate_timed", "velvet_generate_cloth_mesh",
     "velvet_transform_matrix", "velvet_cloth_object_start", "velvet_solver_add_cloth_instances", "velvet_solver_dd_setup", "velvet_solver_dd_info",
     "velvet_solver_dd_offsets", "velvet_solver_dd_prepare_stepped", "velvet_solver_dd_step", "velvet_dd_plan_grid", "velvet_plan_grid_tiles", "velvet_plan_grid_smem_wavefronts", "velvet_plan_grid_digest", "velvet_grid_plan_check", "velvet_dd_peer_blob_bytes",

@@ -22,7 +22,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libvelvet_b200.so")
 INCLUDE = os.path.normpath(os.path.join(HERE, "..", "include"))
 
-SOURCES = ["radix_sort.cu", "seam_kernels.cu", "fused_kernels.cu", "setup_kernels.cu", "dd_peer.cu", "tile_plan.cpp", "grid_plan.cpp", "solver.cu", "capi.cu"]
+SOURCES = ["radix_sort.cu", "seam_kernels.cu", "fused_kernels.cu", "setup_kernels.cu", "input_kernels.cu", "dd_peer.cu", "tile_plan.cpp", "grid_plan.cpp", "solver.cu", "capi.cu"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # Experiments only (never the default, never used by tests): VELVET_VARIANT=fast builds a second library with FMA

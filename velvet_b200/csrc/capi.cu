@@ -331,6 +331,32 @@ int velvet_solver_check_nan(VelvetSolver* s, unsigned* nonFiniteCount, unsigned*
     VT_API_END
 }
 
+int velvet_solver_grab(VelvetSolver* s, const float* rayOrigin3, const float* rayDirection3, int* grabbedIndex, float* distanceToOrigin)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && rayOrigin3 && rayDirection3, "grab: bad argument");
+    const VtClothSolverGPU::GrabResult r = s->impl.Grab(rayOrigin3, rayDirection3);
+    if (grabbedIndex) *grabbedIndex = r.index;
+    if (distanceToOrigin) *distanceToOrigin = r.distanceToOrigin;
+    VT_API_END
+}
+
+int velvet_solver_drag(VelvetSolver* s, const float* rayOrigin3, const float* rayDirection3)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s && rayOrigin3 && rayDirection3, "drag: bad argument");
+    s->impl.Drag(rayOrigin3, rayDirection3);
+    VT_API_END
+}
+
+int velvet_solver_release(VelvetSolver* s)
+{
+    VT_API_BEGIN
+    VT_REQUIRE(s, "solver is NULL");
+    s->impl.Release();
+    VT_API_END
+}
+
 int velvet_solver_readback_async(VelvetSolver* s, float* hostPositions, float* hostNormals)
 {
     VT_API_BEGIN

@@ -270,6 +270,39 @@ __global__ void __launch_bounds__(256) count_nonfinite_kernel(const float* __res
 }
 }  // namespace
 
+VtClothSolverGPU::GrabResult VtClothSolverGPU::Grab(const float* o, const float* d)
+{
+    VT_CUDA(cudaSetDevice(m_device));
+    if (!m_grab.data()) {
+        m_grab.allocate(1);
+        const input::GrabState none{~0ull, -1, 0.0f, 0.0f, 0};
+        VT_CUDA(cudaMemcpyAsync(m_grab.data(), &none, sizeof(none), cudaMemcpyHostToDevice, m_stream));
+    }
+    input::grab(m_grab, reinterpret_cast<const float*>(positions.data()), invMasses.data(), simParams.numParticles, V3(o[0], o[1], o[2]),
+                V3(d[0], d[1], d[2]), simParams.particleDiameter, m_stream);
+    input::GrabState st;
+    VT_CUDA(cudaMemcpyAsync(&st, m_grab.data(), sizeof(st), cudaMemcpyDeviceToHost, m_stream));
+    VT_CUDA(cudaStreamSynchronize(m_stream));
+    return GrabResult{st.index, st.distanceToOrigin};
+}
+
+void VtClothSolverGPU::Drag(const float* o, const float* d)
+{
+    if (!m_grab.data()) return;  // nothing was ever grabbed
+    VT_CUDA(cudaSetDevice(m_device));
+    input::drag(m_grab, reinterpret_cast<float*>(positions.data()), reinterpret_cast<float*>(velocities.data()), V3(o[0], o[1], o[2]),
+                V3(d[0], d[1], d[2]), kFixedDeltaTime, m_stream);
+    m_mayBeBusy = true;
+}
+
+void VtClothSolverGPU::Release()
+{
+    if (!m_grab.data()) return;
+    VT_CUDA(cudaSetDevice(m_device));
+    input::release(m_grab, invMasses.data(), m_stream);
+    m_mayBeBusy = true;
+}
+
 unsigned VtClothSolverGPU::CheckNaN(unsigned* firstParticle)
 {
     VT_CUDA(cudaSetDevice(m_device));

@@ -13,6 +13,7 @@
 #include "dd_peer.cuh"
 #include "fused_kernels.cuh"
 #include "grid_plan.hpp"
+#include "input_kernels.cuh"
 #include "radix_sort.cuh"
 #include "seam.hpp"
 #include "tile_plan.hpp"
@@ -106,6 +107,14 @@ public:
     // Debug guard (the reference's unused VtClothSolverCPU::CheckNAN, L407-418): counts non-finite components of positions,
     // velocities and predicted on the device; returns the count and the first offending particle (or numParticles).
     unsigned CheckNaN(unsigned* firstParticle);
+    // MouseGrabber.hpp L31-110 as device operations (input_kernels.cuh); Grab synchronises to return the pick
+    struct GrabResult {
+        int index;
+        float distanceToOrigin;
+    };
+    GrabResult Grab(const float* rayOrigin3, const float* rayDirection3);
+    void Drag(const float* rayOrigin3, const float* rayDirection3);
+    void Release();
     // must be called before AddCloth: hash arrays host-readable (managed) like the reference's
     void setHashHostReadable(bool on) { m_hashHostReadable = on; }
     int ReadbackPipelined(float* hostPositions, float* hostNormals);
@@ -254,6 +263,7 @@ private:
     std::vector<GeneratedCloth> m_generated;
     bool generatedListsIntact() const;
     bool buildGridPlanOnDevice(uint planN, cudaStream_t st);
+    DeviceBuffer<input::GrabState> m_grab;
     DeviceBuffer<int> m_setupFlags;  // [0] mesh index out of range, [1] bending quads differ from the grid pattern
     Instancing m_instancing{1, 0, 0};
     // domain decomposition state

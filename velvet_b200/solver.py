@@ -228,6 +228,28 @@ class VtClothSolverGPU:
         check(self._L.velvet_solver_check_nan(self._h, C.byref(cnt), C.byref(first)))
         return cnt.value, first.value
 
+    def Grab(self, rayOrigin, rayDirection):
+        """MouseGrabber::HandleMouseInteraction, mouse-down branch (MouseGrabber.hpp L40-55), on the device: returns
+        (index of the picked particle or -1, its distance along the ray)."""
+        o = np.ascontiguousarray(rayOrigin, np.float32)
+        d = np.ascontiguousarray(rayDirection, np.float32)
+        idx, dist = C.c_int(-1), C.c_float(0)
+        self._L.velvet_solver_grab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        check(self._L.velvet_solver_grab(self._h, _ptr(o), _ptr(d), C.byref(idx), C.byref(dist)))
+        return idx.value, np.float32(dist.value)
+
+    def Drag(self, rayOrigin, rayDirection):
+        """MouseGrabber::UpdateGrappedVertex (L66-79) for this frame's ray."""
+        o = np.ascontiguousarray(rayOrigin, np.float32)
+        d = np.ascontiguousarray(rayDirection, np.float32)
+        self._L.velvet_solver_drag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        check(self._L.velvet_solver_drag(self._h, _ptr(o), _ptr(d)))
+
+    def Release(self):
+        """Mouse-up branch (L57-62)."""
+        self._L.velvet_solver_release.argtypes = [C.c_void_p]
+        check(self._L.velvet_solver_release(self._h))
+
     def buffer_ptr(self, name: str):
         p = C.c_void_p()
         n = C.c_size_t()
