@@ -606,3 +606,30 @@ def test_uploading_constraint_or_initial_position_buffers_takes_effect_in_the_fu
         o.simulate()
     assert_fused_parity(g, o, TOL_1)
     assert np.array_equal(valid_prefix_table(g.download("neighbors"), 1024, 64), valid_prefix_table(o.buffer("neighbors"), 1024, 64))
+
+
+def test_nonzero_rest_angles_uploaded_after_registration(iterate_kernel_param):
+    """SURVEY section 8 row f4 (the reference leaves `// TODO: calculate angle`, VtClothObjectGPU.hpp L128-129): per-quad rest
+    angles written into the public bendAngles buffer after the cloth was generated.  The grid kernel then takes its rest
+    angles from the per-vertex array instead of the scalar 0; both iterate kernels against the oracle."""
+    p = gpu_params(numSubsteps=3, numIterations=6)
+    g, o = make_pair(26, p)
+    set_colliders(g, o, vb.sphere_plane_colliders())
+    rng = np.random.default_rng(11)
+    angles = rng.uniform(0.0, 0.6, len(o.buffer("bendAngles"))).astype(np.float32)
+    o.buffer("bendAngles")[:] = angles
+    g.upload("bendAngles", angles)
+    for _ in range(6):
+        g.Simulate()
+        o.simulate()
+    assert_fused_parity(g, o, TOL_60)
+    # and one shared non-zero angle (the scalar path of the grid kernel)
+    g2, o2 = make_pair(26, p)
+    set_colliders(g2, o2, vb.sphere_plane_colliders())
+    same = np.full(len(o2.buffer("bendAngles")), 0.25, np.float32)
+    o2.buffer("bendAngles")[:] = same
+    g2.upload("bendAngles", same)
+    for _ in range(6):
+        g2.Simulate()
+        o2.simulate()
+    assert_fused_parity(g2, o2, TOL_60)

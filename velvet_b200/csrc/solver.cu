@@ -198,6 +198,9 @@ void VtClothSolverGPU::NotifyBufferEdited(int bufferId)
     case VELVET_BUF_ATTACHPARTICLEIDS:
     case VELVET_BUF_ATTACHSLOTIDS:
     case VELVET_BUF_ATTACHDISTANCES:
+        // the lists are no longer what the device generator wrote (rest angles, say, may now differ from 0): the plan is
+        // derived from the lists themselves again (grid_plan.cpp), whatever they now hold
+        m_generated.clear();
         invalidate();
         break;
     case VELVET_BUF_INITIALPOSITIONS:
