@@ -670,6 +670,8 @@ __device__ __noinline__ GridBendOut grid_bend_slow(float4 p0, float4 p1, float4 
 #ifndef VT_GRID_BLOCKS
 #define VT_GRID_BLOCKS 3  // resident CTAs per SM the register budget is sized for (80 registers; at 4 x 64 the kernel spills: 41.0 vs 39.2 us)
 #endif
+// BX x BY bundles per tile = (BX - 1) x (BY - 1) owned particles: 16 x 16, or 15 x 17 (grid_plan.hpp: the cloth side decides)
+template <int BX, int BY>
 __global__ void __launch_bounds__(256, VT_GRID_BLOCKS)
 iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const GridPlanDev plan,
                     const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
@@ -677,6 +679,9 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
 {
     vt_pdl_trigger();  // the next kernel may set itself up while this one runs
     constexpr unsigned NT = 256;
+    constexpr int TX = BX - 1, TY = BY - 1;  // owned particles per tile along x (slow index) and y
+    constexpr int VY = BY + 1;               // staged vertices per tile row
+    static_assert(BX * BY <= (int)NT && (BX + 1) * (BY + 1) <= GRID_V * GRID_V, "tile shape exceeds the CTA or its staging buffers");
     extern __shared__ float4 s_mem[];  // GRID_SMEM_BYTES, carved below (more than the 48 KB a static allocation may take)
     float4(*const s_sp)[GRID_V * GRID_V] = reinterpret_cast<float4(*)[GRID_V * GRID_V]>(s_mem);
     float4(*const s_rest)[NT] = reinterpret_cast<float4(*)[NT]>(s_mem + 2 * GRID_V * GRID_V);
@@ -686,7 +691,8 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     GridCloth* const s_cloth = reinterpret_cast<GridCloth*>(s_tile + 3);
 
     const unsigned tid = threadIdx.x;
-    const int by = (int)(tid & 15u), bx = (int)(tid >> 4);
+    const bool live = BX * BY == (int)NT || tid < (unsigned)(BX * BY);  // 15 x 17 leaves the last thread without a bundle
+    const int by = live ? (int)(tid % (unsigned)BY) : 0, bx = live ? (int)(tid / (unsigned)BY) : 0;
     const unsigned stride = gridDim.x;
     unsigned w = blockIdx.x;
     if (w >= totalWork) return;
@@ -738,8 +744,8 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             t.planBase = g.base;
             t.instance = 0;
             t.side = (int)g.side;
-            t.x0 = (int)row * GRID_TILE;
-            t.y0 = (int)c * GRID_TILE;
+            t.x0 = (int)row * TX;  // (strips are cut in rows of 15: launched with the square shape only)
+            t.y0 = (int)c * TY;
             return t;
         }
         unsigned tile = item, in = 0;
@@ -756,20 +762,20 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         t.planBase = g.base;  // attach CSR, rest lengths and angles cover one instance
         t.instance = in;
         t.side = (int)g.side;
-        t.x0 = (int)tx * GRID_TILE;
-        t.y0 = (int)(lt - tx * g.tilesY) * GRID_TILE;
+        t.x0 = (int)tx * TX;
+        t.y0 = (int)(lt - tx * g.tilesY) * TY;
         return t;
     };
     // stage the 17 x 17 vertices around the tile, the bundle's rest lengths and rest angle (vertices outside the cloth are skipped)
-    const unsigned spAddr = (unsigned)__cvta_generic_to_shared(&s_sp[0][bx * GRID_V + by]);
+    const unsigned spAddr = (unsigned)__cvta_generic_to_shared(&s_sp[0][bx * VY + by]);
     const unsigned restAddr = (unsigned)__cvta_generic_to_shared(&s_rest[0][tid]);
     const unsigned angleAddr = (unsigned)__cvta_generic_to_shared(&s_angle[0][tid]);
-    constexpr unsigned SP_BYTES = GRID_V * GRID_V * 16, V16 = GRID_V * 16;
+    constexpr unsigned SP_BYTES = GRID_V * GRID_V * 16, V16 = VY * 16;
     auto cp16 = [](unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
     auto cp4 = [](unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src)); };
     auto issue_tile = [&](unsigned buf, const GridTileCoord& t) {
         const int gx = t.x0 - 1 + bx, gy = t.y0 - 1 + by;
-        const bool inX = (unsigned)gx < (unsigned)t.side, inY = (unsigned)gy < (unsigned)t.side;
+        const bool inX = live && (unsigned)gx < (unsigned)t.side, inY = (unsigned)gy < (unsigned)t.side;
         const bool inX1 = (unsigned)(gx + 1) < (unsigned)t.side, inY1 = (unsigned)(gy + 1) < (unsigned)t.side;
         const int idx = gx * t.side + gy;
         const float4* src = predInAll + t.base + idx;
@@ -779,10 +785,10 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
             cp16(restAddr + buf * (NT * 16), plan.rest4 + t.planBase + idx);
             if (plan.restAngle) cp4(angleAddr + buf * (NT * 4), plan.restAngle + t.planBase + idx);
         }
-        if (by == GRID_B - 1 && inX && inY1) cp16(dst + 16, src + 1);
-        if (bx == GRID_B - 1) {
+        if (by == BY - 1 && inX && inY1) cp16(dst + 16, src + 1);
+        if (bx == BX - 1 && live) {
             if (inX1 && inY) cp16(dst + V16, src + t.side);
-            if (by == GRID_B - 1 && inX1 && inY1) cp16(dst + V16 + 16, src + t.side + 1);
+            if (by == BY - 1 && inX1 && inY1) cp16(dst + V16 + 16, src + t.side + 1);
         }
     };
 
@@ -809,13 +815,13 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
 
         // ---- which constraints of this bundle exist (cloth border, partially filled tiles)
         const int gx = x0Cur - 1 + bx, gy = y0Cur - 1 + by;
-        const bool inGrid = (unsigned)gx < (unsigned)sideCur && (unsigned)gy < (unsigned)sideCur;
+        const bool inGrid = live && (unsigned)gx < (unsigned)sideCur && (unsigned)gy < (unsigned)sideCur;
         const bool vV = inGrid && gy + 1 < sideCur;  // (x,y)-(x,y+1)
         const bool vH = inGrid && gx + 1 < sideCur;  // (x,y)-(x+1,y)
         const bool vQ = vV && vH;                    // both diagonals and the bending constraint of the quad
 
-        const float4* sp = &s_sp[buf][bx * GRID_V + by];
-        const float4 c00 = sp[0], c01 = sp[1], c10 = sp[GRID_V], c11 = sp[GRID_V + 1];
+        const float4* sp = &s_sp[buf][bx * VY + by];
+        const float4 c00 = sp[0], c01 = sp[1], c10 = sp[VY], c11 = sp[VY + 1];
         const float4 rest = s_rest[buf][tid];
         const float restAngle = plan.restAngle ? s_angle[buf][tid] : plan.uniformAngle;
 
@@ -923,9 +929,9 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
                 delta.z += v.z;
                 count += v.w;
             };
-            add(s_slots[0][tid - GRID_B - 1]);
-            add(s_slots[1][tid - GRID_B]);
-            add(s_slots[2][tid - GRID_B]);
+            add(s_slots[0][tid - BY - 1]);
+            add(s_slots[1][tid - BY]);
+            add(s_slots[2][tid - BY]);
             add(s_slots[3][tid - 1]);
             add(s_slots[4][tid - 1]);
             add(F4(oV.c1, oV.flag));
@@ -945,8 +951,8 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
                     }
                 }
             }
-            add(s_slots[5][tid - GRID_B - 1]);
-            add(s_slots[6][tid - GRID_B]);
+            add(s_slots[5][tid - BY - 1]);
+            add(s_slots[6][tid - BY]);
             add(s_slots[7][tid - 1]);
             add(F4(oB.c0, oB.flag));
             vec3 p = V3(c00);
@@ -1160,7 +1166,14 @@ void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* pre
     }
     if (!total) return;
     const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
-    launch_pdl(iterate_grid_kernel, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut, plan, attachSlotPositions, fp, inst, total, a);
+    if (plan.tileX == (unsigned)GRID_TILE_RX && plan.tileY == (unsigned)GRID_TILE_RY && !strip)
+        launch_pdl(iterate_grid_kernel<GRID_TILE_RX + 1, GRID_TILE_RY + 1>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut,
+                   plan, attachSlotPositions, fp, inst, total, a);
+    else if (plan.tileX == (unsigned)GRID_TILE && plan.tileY == (unsigned)GRID_TILE)
+        launch_pdl(iterate_grid_kernel<GRID_B, GRID_B>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut, plan,
+                   attachSlotPositions, fp, inst, total, a);
+    else
+        throw Error(VELVET_ERR_STATE, "iterate_grid: no kernel for this tile shape");
 }
 
 unsigned configure_iterate_grid_kernel()
@@ -1168,8 +1181,14 @@ unsigned configure_iterate_grid_kernel()
     int dev = 0, sms = 0, perSm = 0;
     VT_CUDA(cudaGetDevice(&dev));
     VT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    VT_CUDA(cudaFuncSetAttribute(iterate_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM_BYTES));
-    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_grid_kernel, 256, GRID_SMEM_BYTES));
+    int perSmRect = 0;
+    VT_CUDA(cudaFuncSetAttribute(iterate_grid_kernel<GRID_B, GRID_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM_BYTES));
+    VT_CUDA(cudaFuncSetAttribute(iterate_grid_kernel<GRID_TILE_RX + 1, GRID_TILE_RY + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)GRID_SMEM_BYTES));
+    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, iterate_grid_kernel<GRID_B, GRID_B>, 256, GRID_SMEM_BYTES));
+    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmRect, iterate_grid_kernel<GRID_TILE_RX + 1, GRID_TILE_RY + 1>, 256,
+                                                          GRID_SMEM_BYTES));
+    if (perSmRect < perSm) perSm = perSmRect;
     if (perSm < 1) throw Error(VELVET_ERR_UNSUPPORTED, "the grid Jacobi kernel does not fit on an SM");
     return (unsigned)(sms * perSm);
 }

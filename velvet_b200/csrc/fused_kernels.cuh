@@ -46,6 +46,7 @@ struct GridPlanDev {
     unsigned numCloths, numTiles, hasAttach;
     unsigned residentCtas;
     unsigned tilesY0;  // tiles along one side of cloth 0 (strip decomposition of a single cloth)
+    unsigned tileX, tileY;  // owned particles per tile (grid_plan.hpp): 15 x 15, or 14 x 16
 };
 
 constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)

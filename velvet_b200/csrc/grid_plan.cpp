@@ -6,10 +6,37 @@
 
 namespace velvet {
 
+void choose_grid_tile_shape(const std::vector<unsigned>& sides, bool squareOnly, unsigned& tileX, unsigned& tileY)
+{
+    auto tiles = [&](unsigned tx, unsigned ty) {
+        unsigned long long n = 0;
+        for (unsigned s : sides) n += (unsigned long long)((s + tx - 1) / tx) * ((s + ty - 1) / ty);
+        return n;
+    };
+    tileX = tileY = GRID_TILE;
+    if (squareOnly) return;
+    const unsigned long long square = tiles(GRID_TILE, GRID_TILE), rect = tiles(GRID_TILE_RX, GRID_TILE_RY);
+    if (rect * 100 <= square * 95) {
+        tileX = GRID_TILE_RX;
+        tileY = GRID_TILE_RY;
+    }
+}
+
+unsigned lay_out_grid_tiles(std::vector<GridCloth>& cloths, unsigned tileX, unsigned tileY)
+{
+    unsigned tiles = 0;
+    for (GridCloth& gc : cloths) {
+        gc.tilesY = (gc.side + tileY - 1) / tileY;
+        gc.firstTile = tiles;
+        tiles += ((gc.side + tileX - 1) / tileX) * gc.tilesY;
+    }
+    return tiles;
+}
+
 GridPlan build_grid_plan(unsigned numParticles, const std::vector<ClothRange>& cloths, const int* stretchIndices,
                          const float* stretchLengths, size_t numStretch, const unsigned* bendIndices, const float* bendAngles,
                          size_t numBend, const int* attachParticleIDs, const int* attachSlotIDs, const float* attachDistances,
-                         size_t numAttach)
+                         size_t numAttach, bool squareTilesOnly)
 {
     GridPlan g;
     auto fail = [&](const char* why) {
@@ -35,7 +62,6 @@ GridPlan build_grid_plan(unsigned numParticles, const std::vector<ClothRange>& c
     g.rest4.assign(4 * (size_t)numParticles, 0.0f);
     g.restAngle.assign(numParticles, 0.0f);
     size_t s = 0, b = 0;
-    unsigned tiles = 0;
     for (const ClothRange& c : cloths) {
         const unsigned side = (unsigned)std::lround(std::sqrt((double)c.count));
         const int R = (int)side - 1, off = (int)c.base;
@@ -67,12 +93,15 @@ GridPlan build_grid_plan(unsigned numParticles, const std::vector<ClothRange>& c
         GridCloth gc;
         gc.base = c.base;
         gc.side = side;
-        gc.tilesY = (side + GRID_TILE - 1) / GRID_TILE;
-        gc.firstTile = tiles;
-        tiles += gc.tilesY * gc.tilesY;
+        gc.tilesY = gc.firstTile = 0;
         g.cloths.push_back(gc);
     }
-    g.numTiles = tiles;
+    {
+        std::vector<unsigned> sides;
+        for (const GridCloth& gc : g.cloths) sides.push_back(gc.side);
+        choose_grid_tile_shape(sides, squareTilesOnly, g.tileX, g.tileY);
+        g.numTiles = lay_out_grid_tiles(g.cloths, g.tileX, g.tileY);
+    }
 
     // attach constraints by particle, ascending constraint id inside a particle (counting sort)
     g.attOff.assign((size_t)numParticles + 1, 0u);

@@ -675,17 +675,17 @@ bool VtClothSolverGPU::buildGridPlanOnDevice(uint planN, cudaStream_t st)
 {
     if (m_generated.size() > GRID_MAX_CLOTHS) return false;
     GridPlan plan;
-    uint tiles = 0;
+    std::vector<uint> sides;
     for (const GeneratedCloth& g : m_generated) {
         GridCloth gc;
         gc.base = g.base;
         gc.side = (uint)g.R + 1;
-        gc.tilesY = (gc.side + GRID_TILE - 1) / GRID_TILE;
-        gc.firstTile = tiles;
-        tiles += gc.tilesY * gc.tilesY;
+        gc.tilesY = gc.firstTile = 0;
         plan.cloths.push_back(gc);
+        sides.push_back(gc.side);
     }
-    plan.numTiles = tiles;
+    choose_grid_tile_shape(sides, m_squareTilesOnly, plan.tileX, plan.tileY);
+    plan.numTiles = lay_out_grid_tiles(plan.cloths, plan.tileX, plan.tileY);
     plan.valid = true;
     const size_t numAttach = attachParticleIDs.size();
     m_gCloths.upload(plan.cloths, st);
@@ -1023,7 +1023,7 @@ void VtClothSolverGPU::ensureFusedResources()
         if (!planOnDevice) {
             m_gridPlan = build_grid_plan(planN, m_clothRanges, stretchIndices.data(), stretchLengths.data(), stretchLengths.size(),
                                          bendIndices.data(), bendAngles.data(), bendAngles.size(), attachParticleIDs.data(),
-                                         attachSlotIDs.data(), attachDistances.data(), attachParticleIDs.size());
+                                         attachSlotIDs.data(), attachDistances.data(), attachParticleIDs.size(), m_squareTilesOnly);
             if (m_gridPlan.valid) {
                 m_gCloths.upload(m_gridPlan.cloths, st);
                 m_gRest4.upload(reinterpret_cast<const float4*>(m_gridPlan.rest4.data()), planN, st);
@@ -1052,6 +1052,8 @@ void VtClothSolverGPU::ensureFusedResources()
             m_gridDev.numCloths = (uint)m_gridPlan.cloths.size();
             m_gridDev.numTiles = m_gridPlan.numTiles;
             m_gridDev.tilesY0 = m_gridPlan.cloths[0].tilesY;
+            m_gridDev.tileX = m_gridPlan.tileX;
+            m_gridDev.tileY = m_gridPlan.tileY;
             m_gridDev.hasAttach = attachParticleIDs.size() ? 1u : 0u;
             m_gridDev.residentCtas = std::min(exact_math::configure_iterate_grid_kernel(), fast_math::configure_iterate_grid_kernel());
             m_gridUsable = true;
@@ -1226,6 +1228,10 @@ void VtClothSolverGPU::ddSetup(int rank, int world)
     if (m_instanced) throw Error(VELVET_ERR_UNSUPPORTED, "ddSetup: batched instances are sharded, not decomposed");
     VT_CUDA(cudaSetDevice(m_device));
     if (simParams.numParticles == 0) throw Error(VELVET_ERR_STATE, "ddSetup: no cloth registered");
+    if (!m_squareTilesOnly) {  // strips are cut in rows of 15-particle tiles
+        m_squareTilesOnly = true;
+        invalidate();
+    }
     ensureFusedResources();
     if (!m_fusedUsable) throw Error(VELVET_ERR_UNSUPPORTED, "ddSetup: the fused pipeline is unavailable (" + m_fallbackReason + ")");
     const uint N = simParams.numParticles;

@@ -326,6 +326,7 @@ private:
     GridPlan m_gridPlan;
     GridPlanDev m_gridDev{};
     bool m_gridUsable = false;
+    bool m_squareTilesOnly = false;  // set by the strip decomposition, which counts the cloth in 15-row tiles
     DeviceBuffer<GridCloth> m_gCloths;
     DeviceBuffer<float4> m_gRest4;
     DeviceBuffer<float> m_gAngle;
