@@ -263,41 +263,46 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     const float cs2 = hp.cellSpacing2, pd2 = hp.particleDiameter2;
     unsigned* out = neighbors + id;
     unsigned k = 0;
-    unsigned cur = 0, end = 0;
-    if (mask) {
-        const unsigned key = key_of(__ffs(mask) - 1);
-        mask &= mask - 1;
-        cur = __ldg(cellStart + key);
-        end = __ldg(cellEnd + key);
-    }
-    while (cur < end) {  // a listed bucket is never empty
-        if (cur + K < end) end = cur + K;
-        unsigned nextCur = 0, nextEnd = 0;
-        if (mask) {  // range of the next bucket: in flight while this one is tested
+    // ONE flat loop over the candidates of all buckets: a lane that finishes a bucket moves on to its next one inside the loop
+    // body.  (With a loop over buckets around a loop over candidates, a warp -- whose lanes sit in ~4 different cells, each
+    // with its own sequence of bucket lengths -- ran every bucket for as long as its slowest lane: 15.6 of 32 lanes busy.)
+    // The range of the bucket after the current one is always in flight while the current one is tested.
+    auto fetch_range = [&](unsigned& first, unsigned& last) {
+        first = last = 0;
+        if (mask) {
             const unsigned key = key_of(__ffs(mask) - 1);
             mask &= mask - 1;
-            nextCur = __ldg(cellStart + key);
-            nextEnd = __ldg(cellEnd + key);
+            first = __ldg(cellStart + key);
+            last = __ldg(cellEnd + key);
         }
-        for (; cur < end; cur += 4) {
-            float4 q[4];
+    };
+    unsigned cur, end, nextCur, nextEnd;
+    fetch_range(cur, end);  // a listed bucket is never empty
+    if (cur + K < end) end = cur + K;
+    fetch_range(nextCur, nextEnd);
+    while (cur < end) {
+        float4 q[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) q[j] = __ldg(&sorted[cur + j < end ? cur + j : cur].pos);
+        for (int j = 0; j < 4; j++) q[j] = __ldg(&sorted[cur + j < end ? cur + j : cur].pos);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (cur + j >= end) break;
-                if (((__float_as_uint(q[j].w) + probe) & CN_TAG_MASK) != CN_TAG_WANT) continue;  // cell >= 3 cells away
-                if (!(length2(position - V3(q[j])) < cs2)) continue;
-                const float4 o = __ldg(&sorted[cur + j].init);  // same 32-byte sector as q[j]: an L1 hit
-                const unsigned nb = __float_as_uint(o.w);
-                if (nb != id && length2(originalPos - V3(o)) > pd2) {
-                    out[(size_t)k * N] = nb;
-                    if (++k >= K) return;
-                }
+        for (int j = 0; j < 4; j++) {
+            if (cur + j >= end) break;
+            if (((__float_as_uint(q[j].w) + probe) & CN_TAG_MASK) != CN_TAG_WANT) continue;  // cell >= 3 cells away
+            if (!(length2(position - V3(q[j])) < cs2)) continue;
+            const float4 o = __ldg(&sorted[cur + j].init);  // same 32-byte sector as q[j]: an L1 hit
+            const unsigned nb = __float_as_uint(o.w);
+            if (nb != id && length2(originalPos - V3(o)) > pd2) {
+                out[(size_t)k * N] = nb;
+                if (++k >= K) return;
             }
         }
-        cur = nextCur;
-        end = nextEnd;
+        cur += 4;
+        if (cur >= end) {  // on to the next bucket (its range has arrived by now), and ask for the one after it
+            cur = nextCur;
+            end = nextEnd;
+            if (cur + K < end) end = cur + K;
+            fetch_range(nextCur, nextEnd);
+        }
     }
     if (k < K) out[(size_t)k * N] = 0xffffffffu;
 }
