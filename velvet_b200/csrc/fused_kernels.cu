@@ -94,14 +94,6 @@ __global__ void prepare_inputs_kernel(const VtSDFCollider* __restrict__ collider
     for (unsigned k = i; k < numSlotFloats; k += blockDim.x) slotPositionsOut[k] = slotPositions[k];
 }
 
-#if !VT_FAST_MATH  // integer helpers exist in the exact build only
-__global__ void __launch_bounds__(PB) fill_kernel(unsigned* __restrict__ dst, unsigned value, unsigned n)
-{
-    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id < n) dst[id] = value;
-}
-#endif
-
 __global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict__ positions,
                                                          const float* __restrict__ velocities,
                                                          const float* __restrict__ invMasses, float4* __restrict__ pos4,
@@ -1209,17 +1201,16 @@ void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* in
 
 #if !VT_FAST_MATH  // the spatial hash is integer work: one (exact) build only
 void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
-                           int tableSizePerInstance, Instancing inst)
+                           int tableSizePerInstance, Instancing inst, unsigned* cellStart, int tableSize)
 {
     hash_particles_kernel<PosFloat4><<<pgrid(L.numParticles), PB, 0, L.stream>>>(keys, vals, PosFloat4{pred}, L.numParticles,
-                                                                                 cellSpacing, tableSizePerInstance, inst.particles);
+                                                                                 cellSpacing, tableSizePerInstance, inst.particles,
+                                                                                 cellStart, (unsigned)tableSize);
 }
 
-void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash,
-                            int tableSize)
+// cellStart was filled with 0xffffffff by launch_hash_particles of the same rebuild
+void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash)
 {
-    // a fill kernel rather than cudaMemsetAsync: cellStart is managed memory and this runs under graph capture
-    fill_kernel<<<pgrid((unsigned)tableSize), PB, 0, L.stream>>>(cellStart, 0xffffffffu, (unsigned)tableSize);
     find_cell_start_kernel<<<pgrid(L.numParticles), PB, 0, L.stream>>>(cellStart, cellEnd, particleHash, L.numParticles);
 }
 

@@ -116,10 +116,10 @@ void launch_normals(const FusedLaunch& L, const float4* pos4, const unsigned* in
                     const unsigned* vtxTris, float* normalsOut, Instancing inst);
 
 // spatial hash on float4 positions (keys/vals may be the alternate sort buffers)
+// (also clears the cell table of the rebuild: cellStart[0, tableSize) = empty)
 void launch_hash_particles(const FusedLaunch& L, unsigned* keys, unsigned* vals, const float4* pred, float cellSpacing,
-                           int tableSizePerInstance, Instancing inst);
-void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash,
-                            int tableSize);
+                           int tableSizePerInstance, Instancing inst, unsigned* cellStart, int tableSize);
+void launch_find_cell_start(const FusedLaunch& L, unsigned* cellStart, unsigned* cellEnd, const unsigned* particleHash);
 void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                             const unsigned* cellStart, const unsigned* cellEnd, const float4* pred, const float4* init4,
                             VtHashParams hp);

@@ -24,13 +24,17 @@ template <class Pos>
 __global__ void __launch_bounds__(256) hash_particles_kernel(unsigned* __restrict__ particleHash,
                                                              unsigned* __restrict__ particleIndex, Pos positions,
                                                              unsigned n, float cellSpacing, int tableSize,
-                                                             unsigned instanceParticles)
+                                                             unsigned instanceParticles, unsigned* __restrict__ emptyTable = nullptr,
+                                                             unsigned emptyCount = 0)
 {
     // Batched independent cloths: instance i = id / instanceParticles owns table rows [i*tableSize, (i+1)*tableSize), so
     // one global sort orders every instance separately and instances never see each other's particles.  A single cloth
     // (or several interacting cloths, the reference's case) is instance 0 with instanceParticles == n.
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
+    // fused pipeline: the cell table of this rebuild is cleared here (cellStart = "empty" for every bucket; FindCellStart runs
+    // after the sort and nothing reads the table in between), which saves the fill launch in front of find_cell_start_kernel
+    for (unsigned j = id; j < emptyCount; j += n) emptyTable[j] = 0xffffffffu;
     const vec3 p = positions(id);
     particleHash[id] = (unsigned)hash_coords(int_coord(p.x, cellSpacing), int_coord(p.y, cellSpacing),
                                              int_coord(p.z, cellSpacing), tableSize) +

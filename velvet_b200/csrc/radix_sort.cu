@@ -55,23 +55,13 @@ __device__ inline unsigned block_exclusive_scan_256(unsigned v, unsigned* s_warp
     return warpBase + incl - v;
 }
 
-// In-place exclusive scan of each pass's 256-bin histogram: hist[p][d] -> first output slot of digit d.
-__global__ void __launch_bounds__(RS_THREADS) rs_scan_kernel(unsigned* hist, int passes)
-{
-    __shared__ unsigned s_warp[RS_WARPS];
-    for (int p = 0; p < passes; p++) {
-        unsigned v = hist[p * RS_RADIX + threadIdx.x];
-        unsigned ex = block_exclusive_scan_256(v, s_warp);
-        hist[p * RS_RADIX + threadIdx.x] = ex;
-    }
-}
-
 // One digit pass.  Tile order is claimed dynamically so that look-back only ever waits on running tiles.
 template <int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_kernel(const unsigned* __restrict__ keysIn, const unsigned* __restrict__ valsIn,
                    unsigned* __restrict__ keysOut, unsigned* __restrict__ valsOut, unsigned n, int shift,
-                   unsigned mask, const unsigned* __restrict__ base, unsigned* lookback, unsigned* tileCounter)
+                   unsigned mask, const unsigned* __restrict__ hist /* digit counts of this pass */, unsigned* lookback,
+                   unsigned* tileCounter)
 {
     constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ unsigned s_tile;
@@ -141,8 +131,11 @@ rs_onesweep_kernel(const unsigned* __restrict__ keysIn, const unsigned* __restri
         lb[tile * RS_RADIX + tid] = (excl + tcount) | RS_FLAG_INCL;
     }
     const unsigned tbase = block_exclusive_scan_256(tcount, s_warp);
+    // first output slot of digit `tid` in this pass: exclusive scan of the pass's histogram (every tile redoes this 256-bin
+    // scan instead of a one-block kernel in front of the passes: one launch less per sort)
+    const unsigned digitBase = block_exclusive_scan_256(hist[tid], s_warp);
     s_tbase[tid] = tbase;
-    s_goff[tid] = base[tid] + excl - tbase;
+    s_goff[tid] = digitBase + excl - tbase;
     __syncthreads();
 
 #pragma unroll
@@ -199,8 +192,7 @@ int RadixSorter::sort(unsigned* keysA, unsigned* valsA, unsigned* keysB, unsigne
     unsigned histBlocks = (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
     if (histBlocks > 148u * 8u) histBlocks = 148u * 8u;
     rs_histogram_kernel<<<histBlocks, RS_THREADS, 0, stream>>>(keysA, n, endBit, passes, hist);
-    rs_scan_kernel<<<1, RS_THREADS, 0, stream>>>(hist, passes);
-    m_lastLaunches += 2;
+    m_lastLaunches += 1;
 
     unsigned *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
     for (int p = 0; p < passes; p++) {

@@ -228,9 +228,9 @@ void VtClothSolverGPU::HashFused()
     uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
     uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
     uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
-    exact_math::launch_hash_particles(L, k0, v0, m_predA, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing);
+    exact_math::launch_hash_particles(L, k0, v0, m_predA, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing, H.cellStart, H.tableSize());
     m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-    exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+    exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
     VtHashParams hp = H.MakeParams(N, simParams.particleDiameter);
     hp.tableSize = H.tableSize() / (int)m_instancing.count;
     if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_predA, m_init4, m_sorted, hp,
@@ -1164,7 +1164,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
             STAGE_BEGIN(t, "Solver_HashParticle");
-            exact_math::launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing);
+            exact_math::launch_hash_particles(L, k0, v0, cur, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing, H.cellStart, H.tableSize());
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashSort");
@@ -1172,7 +1172,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             launches += m_sorter.lastLaunchCount();
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashBuildCell");
-            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
             launches++;
             STAGE_END(t);
             STAGE_BEGIN(t, "Solver_HashCache");
@@ -1398,9 +1398,9 @@ void VtClothSolverGPU::ddSubstepBegin(int substep)
         uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
         uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
         uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
-        exact_math::launch_hash_particles(L, k0, v0, m_ddCur, H.spacing(), H.tableSize(), m_instancing);
+        exact_math::launch_hash_particles(L, k0, v0, m_ddCur, H.spacing(), H.tableSize(), m_instancing, H.cellStart, H.tableSize());
         m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-        exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+        exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
         VtHashParams hp = H.MakeParams(N, P.particleDiameter);
         // keys / sort / cell table are replicated; the expensive candidate walk only for the particles this rank owns
         if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4,
@@ -1624,9 +1624,9 @@ void VtClothSolverGPU::recordDDFrame()
             uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
             uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
-            exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing);
+            exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing, H.cellStart, H.tableSize());
             m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
             launches += 2 + m_sorter.lastLaunchCount();
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
@@ -1734,9 +1734,9 @@ void VtClothSolverGPU::recordDDStripFrame(Stage* t)
             uint* v0 = odd ? m_valsAlt.data() : H.particleIndex.data();
             uint* k1 = odd ? H.particleHash.data() : m_keysAlt.data();
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
-            exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing);
+            exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing, H.cellStart, H.tableSize());
             m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash, H.tableSize());
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
             launches += 2 + m_sorter.lastLaunchCount();
             STAGE_END(t);
             STAGE_BEGIN(t, "DD_NeighborCache(reorder replicated, walk owned)");
