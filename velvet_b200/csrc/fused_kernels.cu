@@ -1225,12 +1225,14 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                   const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
                                   const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst,
-                                  const unsigned char* ownedMask, unsigned numOwned)
+                                  const unsigned char* ownedMask, unsigned numOwned, const unsigned* sortedHashForCells)
 {
     if (hp.tableSize <= 0) return 0;
     const unsigned n = L.numParticles;
     SortedParticle* sorted = reinterpret_cast<SortedParticle*>(sortedScratch);
-    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n, hp.cellSpacing);
+    // (with sortedHashForCells the cell table is built in the same launch: cellStart was cleared by launch_hash_particles)
+    reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n, hp.cellSpacing,
+                                                         const_cast<unsigned*>(cellStart), const_cast<unsigned*>(cellEnd), sortedHashForCells);
     if (!ownedMask) {
         cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
             neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, nullptr, n);

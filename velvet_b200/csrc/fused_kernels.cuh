@@ -130,7 +130,8 @@ int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, con
                                   const float4* init4, float4* sortedScratch /* cache_neighbors_scratch_float4(n) */, VtHashParams hp,
                                   Instancing inst,  // hp.tableSize = rows per instance
                                   const unsigned char* ownedMask = nullptr,  // decomposed mode: lists of the owned particles only ...
-                                  unsigned numOwned = 0);                    // ... exactly this many of them
+                                  unsigned numOwned = 0,                     // ... exactly this many of them
+                                  const unsigned* sortedHashForCells = nullptr);  // also run FindCellStart (no launch_find_cell_start then)
 size_t cache_neighbors_scratch_float4(size_t numParticles);
 void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t words);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);

@@ -179,10 +179,25 @@ static __global__ void __launch_bounds__(256) reorder_sorted_kernel(SortedPartic
                                                                     const unsigned* __restrict__ particleIndex,
                                                                     const float4* __restrict__ pred,
                                                                     const float4* __restrict__ init4, unsigned n,
-                                                                    float cellSpacing)
+                                                                    float cellSpacing, unsigned* __restrict__ cellStart,
+                                                                    unsigned* __restrict__ cellEnd,
+                                                                    const unsigned* __restrict__ particleHash)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (particleHash) {  // FindCellStart_Kernel (H3, find_cell_start_kernel above) for sorted slot i, in the same launch
+        const unsigned hash = particleHash[i];
+        if (i == 0) {
+            cellStart[hash] = 0;
+        } else {
+            const unsigned prev = particleHash[i - 1];
+            if (hash != prev) {
+                cellStart[hash] = i;
+                cellEnd[prev] = i;
+            }
+        }
+        if (i == n - 1) cellEnd[hash] = i + 1;
+    }
     const unsigned id = particleIndex[i];
     float4 p = __ldg(pred + id);
     float4 o = __ldg(init4 + id);

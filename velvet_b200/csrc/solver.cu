@@ -230,12 +230,13 @@ void VtClothSolverGPU::HashFused()
     uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
     exact_math::launch_hash_particles(L, k0, v0, m_predA, H.spacing(), H.tableSize() / (int)m_instancing.count, m_instancing, H.cellStart, H.tableSize());
     m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-    exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
     VtHashParams hp = H.MakeParams(N, simParams.particleDiameter);
     hp.tableSize = H.tableSize() / (int)m_instancing.count;
     if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_predA, m_init4, m_sorted, hp,
-                                                   m_instancing))
+                                                   m_instancing, nullptr, 0, H.particleHash)) {
+        exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
         exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_predA, m_init4, hp);
+    }
     VT_CUDA(cudaGetLastError());
     Synchronize();
 }
@@ -1171,19 +1172,16 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
             launches += m_sorter.lastLaunchCount();
             STAGE_END(t);
-            STAGE_BEGIN(t, "Solver_HashBuildCell");
-            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
-            launches++;
-            STAGE_END(t);
-            STAGE_BEGIN(t, "Solver_HashCache");
+            STAGE_BEGIN(t, "Solver_HashCache");  // + HashBuildCell: the cell table is built by the reorder launch
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             hp.tableSize = H.tableSize() / (int)m_instancing.count;  // rows per instance
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur,
-                                                                         m_init4, m_sorted, hp, m_instancing)) {
+                                                                         m_init4, m_sorted, hp, m_instancing, nullptr, 0, H.particleHash)) {
                 launches += nl;
             } else {
+                exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur, m_init4, hp);
-                launches++;
+                launches += 2;
             }
             STAGE_END(t);
         }
@@ -1400,12 +1398,13 @@ void VtClothSolverGPU::ddSubstepBegin(int substep)
         uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
         exact_math::launch_hash_particles(L, k0, v0, m_ddCur, H.spacing(), H.tableSize(), m_instancing, H.cellStart, H.tableSize());
         m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-        exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
         VtHashParams hp = H.MakeParams(N, P.particleDiameter);
         // keys / sort / cell table are replicated; the expensive candidate walk only for the particles this rank owns
         if (!exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4,
-                                                       m_sorted, hp, m_instancing, m_ddOwnedMask, m_ddOwnedCount[m_dd.rank]))
+                                                       m_sorted, hp, m_instancing, m_ddOwnedMask, m_ddOwnedCount[m_dd.rank], H.particleHash)) {
+            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
             exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, m_ddCur, m_init4, hp);
+        }
     }
     // collide only the owned particles, then hand the boundary to the peers exactly like after an iteration
     ops.collide(L, m_ddCur, m_ddOther, m_pos4, H.neighbors, m_prepared, m_frameParams, P.enableSelfCollision != 0,
@@ -1626,15 +1625,16 @@ void VtClothSolverGPU::recordDDFrame()
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
             exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing, H.cellStart, H.tableSize());
             m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
-            launches += 2 + m_sorter.lastLaunchCount();
+            launches += 1 + m_sorter.lastLaunchCount();
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
-                                                                         m_init4, m_sorted, hp, m_instancing, m_ddOwnedMask, ownedCount)) {
+                                                                         m_init4, m_sorted, hp, m_instancing, m_ddOwnedMask, ownedCount,
+                                                                         H.particleHash)) {
                 launches += nl;
             } else {
+                exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
-                launches++;
+                launches += 2;
             }
         }
         ops.collide(L, buf[cur], buf[other], m_pos4, H.neighbors, m_prepared, fp, P.enableSelfCollision != 0, ownedIds, ownedCount);
@@ -1736,17 +1736,18 @@ void VtClothSolverGPU::recordDDStripFrame(Stage* t)
             uint* v1 = odd ? H.particleIndex.data() : m_valsAlt.data();
             exact_math::launch_hash_particles(L, k0, v0, buf[cur], H.spacing(), H.tableSize(), m_instancing, H.cellStart, H.tableSize());
             m_sorter.sort(k0, v0, k1, v1, N, maxBit, m_stream);
-            exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
-            launches += 2 + m_sorter.lastLaunchCount();
+            launches += 1 + m_sorter.lastLaunchCount();
             STAGE_END(t);
             STAGE_BEGIN(t, "DD_NeighborCache(reorder replicated, walk owned)");
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
-                                                                         m_init4, m_sorted, hp, m_instancing, m_ddStripMask, count)) {
+                                                                         m_init4, m_sorted, hp, m_instancing, m_ddStripMask, count,
+                                                                         H.particleHash)) {
                 launches += nl;
             } else {
+                exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
                 exact_math::launch_cache_neighbors(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur], m_init4, hp);
-                launches++;
+                launches += 2;
             }
             STAGE_END(t);
         }
