@@ -84,22 +84,73 @@ def workload_config(R, world, interleaved_hash=3):
 
 # ---------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in a thread of this process (one sample every
+    2 ms: a 60 ms timed region still gets ~30; `nvidia-smi -lms` needs longer than that just to start on an 8-GPU box), with
+    nvidia-smi as the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake_slowdown", 0x80))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, torch=None):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p = self.f = None
+        self.nvml = self.handle = self.thread = None
+        self.samples, self.masks, self.running = [], [], False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            if torch is not None:  # the device this rank computes on, whatever CUDA_VISIBLE_DEVICES did to the numbering
+                try:
+                    pr = torch.cuda.get_device_properties(gpu_index)
+                    bus = "%08X:%02X:%02X.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+                    handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+                except Exception:
+                    handle = None
+            self.handle = handle if handle is not None else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while self.running:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.masks.append(int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.running = False
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvml"}
+            sm = sorted(self.samples)
+            mask = 0
+            for m in self.masks:
+                mask |= m
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "reasons": sorted(n for n, bit in self.REASONS if mask & bit),
+                    "samples": len(sm), "sm_min_mhz": sm[0], "source": "nvml, one sample per 2 ms inside the timed region"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -123,9 +174,9 @@ class ClockSampler:
             except Exception:
                 continue
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvidia-smi"}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
@@ -353,7 +404,7 @@ def velvet_main(args, rank, world, local_rank):
     restart(W)
 
     # ---- timed region 1: device-resident (value)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, torch)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
