@@ -180,7 +180,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
-def run_cpu_reference(resolution, frames, warm_frames=0):
+def run_cpu_reference(resolution, frames, warm_frames=0, budget_s=None):
     """Times O2 = the reference's CPU solver (VtClothSolverCPU, single-thread Gauss-Seidel) restated in oracle/ on this
     box's host cores.  Returns (particle_substeps_per_s, seconds_per_frame, n)."""
     from oracle import o1, o2
@@ -188,12 +188,32 @@ def run_cpu_reference(resolution, frames, warm_frames=0):
     p.numSubsteps, p.numIterations = SUBSTEPS, ITERATIONS
     s = o2.O2Solver(p, resolution, o1.transform_matrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1)))
     s.set_colliders([1, 0], [[0, 0, 0], [0, 0.6, 0]], [1.0, 0.6])
-    for _ in range(warm_frames):
+    # budget_s bounds the whole run (a 1024x1024 frame takes ~12 s on one core and cannot be split: the reference hashes once
+    # per frame): the first frame is timed, then as many warm-up / timed frames as fit, at least one timed.  Throughput
+    # (particle-substeps/s) does not depend on how many frames are averaged.
+    done_warm = 0
+    if budget_s is not None and warm_frames > 0:
+        t0 = time.perf_counter()
+        s.simulate()
+        first = time.perf_counter() - t0
+        done_warm = 1
+        can = max(1, int(budget_s / max(first, 1e-9)) - 1)  # frames that still fit
+        if warm_frames - 1 + frames > can:
+            warm_frames = 1
+            frames = max(1, min(frames, can))
+    elif budget_s is not None:
+        t0 = time.perf_counter()
+        s.simulate()  # an untimed probe frame to size the run
+        first = time.perf_counter() - t0
+        frames = max(1, min(frames, int(budget_s / max(first, 1e-9)) - 1))
+    for _ in range(warm_frames - done_warm):
         s.simulate()
     t0 = time.perf_counter()
     for _ in range(frames):
         s.simulate()
     dt = time.perf_counter() - t0
+    if budget_s is not None:
+        return s.n * SUBSTEPS * frames / dt, dt / frames, s.n, frames, max(warm_frames, 1)
     return s.n * SUBSTEPS * frames / dt, dt / frames, s.n
 
 
@@ -204,8 +224,9 @@ def reference_main(args, rank, world):
     # workload as the velvet arm: the same 1024x1024 drape, W warm-up frames, K timed frames (~12 s each on one host core --
     # the algorithm is sequential, so one core is all it can use).  Under torchrun this is one of the N identical cloths.
     res = args.cpu_resolution if args.cpu_resolution is not None else args.resolution
-    steps, warm = max(1, args.steps), max(0, args.warmup)
-    value, sec_per_frame, n = run_cpu_reference(res, steps, warm)
+    asked_steps, asked_warm = max(1, args.steps), max(0, args.warmup)
+    budget = float(os.environ.get("VELVET_REF_BUDGET_S", "150"))
+    value, sec_per_frame, n, steps, warm = run_cpu_reference(res, asked_steps, asked_warm, budget_s=budget)
     same = res == args.resolution
     cfg = workload_config(args.resolution, world)
     line = {
@@ -214,7 +235,10 @@ def reference_main(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg, "same_config": same,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": (f"{steps} timed + {warm} warm-up frame(s) of "
+                         "sample": ((f"--steps {asked_steps} --warmup {asked_warm} bounded to " if (steps, warm) != (asked_steps, asked_warm) else "")
+                                    + f"{steps} timed + {warm} warm-up frame(s) "
+                                    + (f"(a frame takes {sec_per_frame:.1f} s and cannot be split; budget {budget:.0f} s, VELVET_REF_BUDGET_S) "
+                                       if (steps, warm) != (asked_steps, asked_warm) else "") + "of "
                                     + ("the same workload (one cloth)" if same else f"a {res + 1}x{res + 1} sample of the workload")
                                     + "; VtClothSolverCPU restated (oracle/ref_gs_cpu.c), single thread like the reference "
                                       f"(Gauss-Seidel is sequential); host has {os.cpu_count()} cores")},
