@@ -97,7 +97,7 @@ __global__ void prepare_inputs_kernel(const VtSDFCollider* __restrict__ collider
 __global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict__ positions,
                                                          const float* __restrict__ velocities,
                                                          const float* __restrict__ invMasses, float4* __restrict__ pos4,
-                                                         float4* __restrict__ vel4, float4* __restrict__ pred,
+                                                         float4* __restrict__ pred,
                                                          const PreparedCollider* __restrict__ colliders,
                                                          const FrameParams* __restrict__ fp, unsigned n)
 {
@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(PB) begin_frame_kernel(const float* __restrict
     const float dt = fp->substepTime;
     const vec3 vel = load3(velocities, id) + V3(P.gravity[0], P.gravity[1], P.gravity[2]) * dt;
     pos4[id] = F4(pos, w);
-    vel4[id] = F4(vel, 0.0f);
     pred[id] = F4(pos + vel * dt, w);
 }
 
@@ -981,7 +980,7 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
 }
 
 __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restrict__ predIn, float4* __restrict__ pos4,
-                                                         float4* __restrict__ vel4, float4* __restrict__ predNext,
+                                                         float4* __restrict__ predNext,
                                                          int last, float* __restrict__ positionsOut,
                                                          float* __restrict__ velocitiesOut,
                                                          float* __restrict__ predictedOut,
@@ -999,7 +998,6 @@ __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restric
     finalize_point(V3(pr), V3(po), dt, P.maxSpeed, P.damping, newPos, vel);  // Finalize_Kernel, .cu L396-406
     pos4[id] = F4(newPos, po.w);
     if (last) {
-        vel4[id] = F4(vel, 0.0f);
         store3(positionsOut, id, newPos);
         store3(velocitiesOut, id, vel);
         store3(predictedOut, id, V3(pr));
@@ -1007,7 +1005,6 @@ __global__ void __launch_bounds__(PB) end_substep_kernel(const float4* __restric
     } else {
         // PredictPositions of the next substep, .cu L51-52
         vel = vel + V3(P.gravity[0], P.gravity[1], P.gravity[2]) * dt;
-        vel4[id] = F4(vel, 0.0f);
         predNext[id] = F4(newPos + vel * dt, po.w);
     }
 }
@@ -1076,9 +1073,9 @@ void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders,
 }
 
 void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
-                        float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders, const FrameParams* fp)
+                        float4* pos4, float4* pred, const PreparedCollider* colliders, const FrameParams* fp)
 {
-    launch_pdl(begin_frame_kernel, dim3(pgrid(L.numParticles)), dim3(PB), 0, L.stream, positions, velocities, invMasses, pos4, vel4, pred,
+    launch_pdl(begin_frame_kernel, dim3(pgrid(L.numParticles)), dim3(PB), 0, L.stream, positions, velocities, invMasses, pos4, pred,
                colliders, fp, L.numParticles);
 }
 
@@ -1185,10 +1182,10 @@ unsigned configure_iterate_grid_kernel()
     return (unsigned)(sms * perSm);
 }
 
-void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext, bool last,
+void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* predNext, bool last,
                         float* positionsOut, float* velocitiesOut, float* predictedOut, const FrameParams* fp)
 {
-    launch_pdl(end_substep_kernel, dim3(pgrid(L.numParticles)), dim3(PB), 0, L.stream, predIn, pos4, vel4, predNext, last ? 1 : 0, positionsOut,
+    launch_pdl(end_substep_kernel, dim3(pgrid(L.numParticles)), dim3(PB), 0, L.stream, predIn, pos4, predNext, last ? 1 : 0, positionsOut,
                velocitiesOut, predictedOut, fp, L.numParticles);
 }
 

@@ -83,7 +83,7 @@ void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders,
 
 // AoS import + pre-stabilisation SDF pass (frame dt) + PredictPositions of substep 0.
 void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
-                        float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders,
+                        float4* pos4, float4* pred, const PreparedCollider* colliders,
                         const FrameParams* fp);
 
 // CollideParticles + ApplyDeltas + CollideSDF (substep dt): predIn -> predOut.
@@ -107,7 +107,7 @@ unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned c
 
 // Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
 // of positions / velocities / predicted to the public packed-float3 buffers).
-void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext,
+void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* predNext,
                         bool last, float* positionsOut, float* velocitiesOut, float* predictedOut,
                         const FrameParams* fp);
 
@@ -152,7 +152,7 @@ void launch_prepare_inputs(const FusedLaunch& L, const VtSDFCollider* colliders,
 
 // AoS import + pre-stabilisation SDF pass (frame dt) + PredictPositions of substep 0.
 void launch_begin_frame(const FusedLaunch& L, const float* positions, const float* velocities, const float* invMasses,
-                        float4* pos4, float4* vel4, float4* pred, const PreparedCollider* colliders,
+                        float4* pos4, float4* pred, const PreparedCollider* colliders,
                         const FrameParams* fp);
 
 // CollideParticles + ApplyDeltas + CollideSDF (substep dt): predIn -> predOut.
@@ -176,7 +176,7 @@ unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned c
 
 // Finalize of substep s fused with PredictPositions of substep s+1 (or, on the last substep, with the export
 // of positions / velocities / predicted to the public packed-float3 buffers).
-void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* vel4, float4* predNext,
+void launch_end_substep(const FusedLaunch& L, const float4* predIn, float4* pos4, float4* predNext,
                         bool last, float* positionsOut, float* velocitiesOut, float* predictedOut,
                         const FrameParams* fp);
 

@@ -1069,7 +1069,6 @@ void VtClothSolverGPU::ensureFusedResources()
 
     clk.lap("  (before allocations)");
     m_pos4.allocate(N);
-    m_vel4.allocate(N);
     // at least 2 MB each: the decomposed mode exports them over CUDA IPC and must not share a driver slab with other arrays
     m_predA.allocate(std::max<size_t>(N, 131072));
     m_predB.allocate(std::max<size_t>(N, 131072));
@@ -1152,7 +1151,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
     float4* other = m_predB;
     STAGE_BEGIN(t, "Solver_Predict");  // import + pre-stabilisation + predict(0)
     ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()),
-                       invMasses, m_pos4, m_vel4, cur, m_prepared, fp);
+                       invMasses, m_pos4, cur, m_prepared, fp);
     launches++;
     STAGE_END(t);
 
@@ -1204,7 +1203,7 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
 
         STAGE_BEGIN(t, "Solver_Finalize");  // + Predict of the next substep / export on the last one
         const bool last = substep == P.numSubsteps - 1;
-        ops.end_substep(L, cur, m_pos4, m_vel4, other, last, reinterpret_cast<float*>(positions.data()),
+        ops.end_substep(L, cur, m_pos4, other, last, reinterpret_cast<float*>(positions.data()),
                            reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
         launches++;
         if (!last) std::swap(cur, other);
@@ -1378,7 +1377,7 @@ void VtClothSolverGPU::ddFrameBegin(float frameTime)
     m_ddCur = m_predA;
     m_ddOther = m_predB;
     ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
-                    m_pos4, m_vel4, m_ddCur, m_prepared, m_frameParams);
+                    m_pos4, m_ddCur, m_prepared, m_frameParams);
     VT_CUDA(cudaGetLastError());
 }
 
@@ -1455,7 +1454,7 @@ void VtClothSolverGPU::ddSubstepEnd(int substep)
     const FusedOps ops = fused_ops(m_mathMode == VELVET_MATH_FAST);
     FusedLaunch L{m_stream, simParams.numParticles};
     const bool last = substep == simParams.numSubsteps - 1;
-    ops.end_substep(L, m_ddCur, m_pos4, m_vel4, m_ddOther, last, reinterpret_cast<float*>(positions.data()),
+    ops.end_substep(L, m_ddCur, m_pos4, m_ddOther, last, reinterpret_cast<float*>(positions.data()),
                     reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), m_frameParams);
     if (!last) std::swap(m_ddCur, m_ddOther);
     VT_CUDA(cudaGetLastError());
@@ -1607,7 +1606,7 @@ void VtClothSolverGPU::recordDDFrame()
     ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()), m_slotsDev,
                        (uint)(3 * attachSlotPositions.size()), fp);
     ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
-                    m_pos4, m_vel4, buf[cur], m_prepared, fp);
+                    m_pos4, buf[cur], m_prepared, fp);
     launches += 2;
     TilePlanDev sub = m_planDev;  // this rank's tile range of the shared plan
     sub.tiles = m_planDev.tiles + m_dd.tileBegin;
@@ -1657,7 +1656,7 @@ void VtClothSolverGPU::recordDDFrame()
         launches++;
         wait();
         const bool last = substep == P.numSubsteps - 1;
-        ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
+        ops.end_substep(L, buf[cur], m_pos4, buf[other], last, reinterpret_cast<float*>(positions.data()),
                         reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
         launches++;
         if (!last) std::swap(cur, other);
@@ -1676,7 +1675,7 @@ void VtClothSolverGPU::recordDDFrame()
 //   (boundary tiles first, peer stores from the epilogue, publish from the last boundary tile; the next launch waits for the
 //   neighbours' rows when it starts): no exchange launches between iterations;
 //   all-gather of the owned range (peer stores), then Finalize + Predict on every rank for every particle, which keeps
-//   pos4 / vel4 / the public buffers identical everywhere (collide reads pos4 of arbitrary neighbours).
+//   pos4 / the public buffers identical everywhere (collide reads pos4 of arbitrary neighbours).
 // The signal / wait pairs are the "I have stopped reading the buffer you are about to write" handshakes.
 void VtClothSolverGPU::recordDDStripFrame(Stage* t)
 {
@@ -1719,7 +1718,7 @@ void VtClothSolverGPU::recordDDStripFrame(Stage* t)
     ops.prepare_inputs(L, m_collidersDev, m_prepared, reinterpret_cast<const float*>(attachSlotPositions.data()), m_slotsDev,
                        (uint)(3 * attachSlotPositions.size()), fp);
     ops.begin_frame(L, reinterpret_cast<const float*>(positions.data()), reinterpret_cast<const float*>(velocities.data()), invMasses,
-                    m_pos4, m_vel4, buf[cur], m_prepared, fp);
+                    m_pos4, buf[cur], m_prepared, fp);
     launches += 2;
     STAGE_END(t);
     const int maxBit = (int)std::ceil(std::log2((double)H.tableSize()));
@@ -1788,7 +1787,7 @@ void VtClothSolverGPU::recordDDStripFrame(Stage* t)
         STAGE_END(t);
         STAGE_BEGIN(t, "DD_Finalize(replicated)");
         const bool last = substep == P.numSubsteps - 1;
-        ops.end_substep(L, buf[cur], m_pos4, m_vel4, buf[other], last, reinterpret_cast<float*>(positions.data()),
+        ops.end_substep(L, buf[cur], m_pos4, buf[other], last, reinterpret_cast<float*>(positions.data()),
                         reinterpret_cast<float*>(velocities.data()), reinterpret_cast<float*>(predicted.data()), fp);
         launches++;
         STAGE_END(t);

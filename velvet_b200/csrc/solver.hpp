@@ -307,7 +307,7 @@ private:
     cudaGraphExec_t m_graphExec = nullptr;
     int m_graphLaunches = 0;
 
-    DeviceBuffer<float4> m_pos4, m_vel4, m_predA, m_predB, m_init4, m_sorted;
+    DeviceBuffer<float4> m_pos4, m_predA, m_predB, m_init4, m_sorted;
     DeviceBuffer<uint> m_keysAlt, m_valsAlt;
     DeviceBuffer<VtSDFCollider> m_collidersDev;  // stream-ordered device copy of the UpdateColliders block
     DeviceBuffer<PreparedCollider> m_prepared;
