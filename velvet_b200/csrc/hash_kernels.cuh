@@ -244,6 +244,10 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles,
     const unsigned* __restrict__ ownedSlots, const unsigned numThreads)
 {
+    // the particle's 27 bucket keys, [bucket][thread] (conflict-free): phase 1 computes them with compile-time cell offsets,
+    // phase 2 reads back the ones it visits -- recomputing a key there (runtime cell offset: two divisions, three selects, the
+    // modulo) was 11 % of the kernel's instructions, and the key registers it kept alive cost a CTA of occupancy (48 -> 40)
+    __shared__ unsigned s_key[27 * CN_THREADS];
     const unsigned ti = blockIdx.x * CN_THREADS + threadIdx.x;
     if (ti >= numThreads) return;
     const unsigned t = ownedSlots ? __ldg(ownedSlots + ti) : ti;  // decomposed mode: only the slots of owned particles
@@ -259,14 +263,6 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     const int hx0 = (int)((unsigned)(ix - 1) * 92837111u), hx1 = (int)((unsigned)ix * 92837111u), hx2 = (int)((unsigned)(ix + 1) * 92837111u);
     const int hy0 = (int)((unsigned)(iy - 1) * 689287499u), hy1 = (int)((unsigned)iy * 689287499u), hy2 = (int)((unsigned)(iy + 1) * 689287499u);
     const int hz0 = (int)((unsigned)(iz - 1) * 283923481u), hz1 = (int)((unsigned)iz * 283923481u), hz2 = (int)((unsigned)(iz + 1) * 283923481u);
-    auto key_of = [&](int b) {
-        const int a = b / 9, m = (b / 3) % 3, c = b % 3;
-        const int hx = a == 0 ? hx0 : a == 1 ? hx1 : hx2;
-        const int hy = m == 0 ? hy0 : m == 1 ? hy1 : hy2;
-        const int hz = c == 0 ? hz0 : c == 1 ? hz1 : hz2;
-        return tableBase + hash_key_fast(hx, hy, hz, fm);
-    };
-
     // phase 1: which of the 27 buckets (x, y, z traversal order = bit order) are non-empty; 27 independent loads in flight
     unsigned mask = 0;
 #pragma unroll
@@ -274,7 +270,9 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
         const int hx = (b / 9) == 0 ? hx0 : (b / 9) == 1 ? hx1 : hx2;
         const int hy = ((b / 3) % 3) == 0 ? hy0 : ((b / 3) % 3) == 1 ? hy1 : hy2;
         const int hz = (b % 3) == 0 ? hz0 : (b % 3) == 1 ? hz1 : hz2;
-        if (__ldg(cellStart + tableBase + hash_key_fast(hx, hy, hz, fm)) != 0xffffffffu) mask |= 1u << b;
+        const unsigned key = tableBase + hash_key_fast(hx, hy, hz, fm);
+        s_key[b * CN_THREADS + threadIdx.x] = key;
+        if (__ldg(cellStart + key) != 0xffffffffu) mask |= 1u << b;
     }
 
     // phase 2: walk the non-empty buckets in traversal order
@@ -289,7 +287,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     auto fetch_range = [&](unsigned& first, unsigned& last) {
         first = last = 0;
         if (mask) {
-            const unsigned key = key_of(__ffs(mask) - 1);
+            const unsigned key = s_key[(__ffs(mask) - 1) * CN_THREADS + threadIdx.x];
             mask &= mask - 1;
             first = __ldg(cellStart + key);
             last = __ldg(cellEnd + key);
