@@ -608,6 +608,7 @@ void VtClothSolverGPU::GenerateGridClothOnDevice(int R, int base, const float* v
     const size_t nv = (size_t)(R + 1) * (R + 1);
     if ((size_t)base + nv > positions.size() || indices.size() < (size_t)6 * R * R)
         throw Error(VELVET_ERR_STATE, "GenerateGridClothOnDevice: the cloth is not registered (AddCloth first)");
+    VT_CUDA(cudaSetDevice(m_device));
     quiesce();
     SetupClock clk;
     cudaStream_t st = m_stream;
