@@ -163,3 +163,36 @@ def test_grid_cloths_are_recognised_from_their_constraint_pattern():
     ok, tiles, rest, why = _grid_check([n, (R2 + 1) ** 2], np.r_[si, s2[0]], np.r_[sl, s2[1]], np.r_[bi, s2[2].astype(np.uint32)], np.r_[ba, s2[3]])
     assert ok and tiles == 4 + 1, why
     assert np.array_equal(rest[:n], expect)
+
+
+def test_grid_tile_shape_follows_the_cloth_side():
+    """grid_plan.cpp: 15 x 15 owned particles per tile, or 14 x 16 when that needs at least 5 % fewer tiles (a side of 64:
+    5 x 4 instead of 5 x 5; a side of 32: 3 x 2 instead of 3 x 3); one shape for all the cloths of a solver."""
+    import numpy as np
+    from oracle import o1
+
+    def lists(R, off):
+        s = o1.O1Solver(o1.default_params())
+        v, idx = o1.generate_cloth_mesh(R)
+        s.cloth_object_start(R, v, idx, o1.transform_matrix((0, 1.5, 1.0), (90, 0, 0), (1, 1, 1)), [])
+        return (s.buffer("stretchIndices").copy() + off, s.buffer("stretchLengths").copy(),
+                (s.buffer("bendIndices").copy() + off).astype(np.uint32), s.buffer("bendAngles").copy())
+
+    def tiles(sides):
+        si, sl, bi, ba, counts, off = [], [], [], [], [], 0
+        for side in sides:
+            a, b, c, d = lists(side - 1, off)
+            si.append(a); sl.append(b); bi.append(c); ba.append(d)
+            counts.append(side * side)
+            off += side * side
+        ok, n, _, why = _grid_check(counts, np.concatenate(si), np.concatenate(sl), np.concatenate(bi), np.concatenate(ba))
+        assert ok, why
+        return n
+
+    square = lambda s: (-(-s // 15)) ** 2
+    rect = lambda s: -(-s // 14) * -(-s // 16)
+    assert tiles([64]) == rect(64) == 20 and square(64) == 25
+    assert tiles([32]) == rect(32) == 6
+    assert tiles([21]) == square(21) == 4          # no gain: the square shape stays
+    assert tiles([128]) == square(128) == 81        # 80 rectangular tiles are less than 5 % fewer
+    assert tiles([64, 21]) == rect(64) + rect(21)   # one shape per solver: 24 tiles against 29
