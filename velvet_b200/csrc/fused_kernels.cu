@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <utility>
 
 #include "hash_kernels.cuh"
@@ -1230,9 +1231,24 @@ int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, con
     // (with sortedHashForCells the cell table is built in the same launch: cellStart was cleared by launch_hash_particles)
     reorder_sorted_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, particleIndex, pred, init4, n, hp.cellSpacing,
                                                          const_cast<unsigned*>(cellStart), const_cast<unsigned*>(cellEnd), sortedHashForCells);
+    // bucket keys through shared memory up to VT_WALK_SMEM_KEYS_MAX particles (VELVET_WALK_KEYS=smem|regs overrides: A/B runs)
+    static const int keysMode = [] {
+        const char* e = getenv("VELVET_WALK_KEYS");
+        return e && !strcmp(e, "smem") ? 1 : e && !strcmp(e, "regs") ? 2 : 0;
+    }();
+    const bool smemKeys = keysMode == 1 || (keysMode == 0 && n <= VT_WALK_SMEM_KEYS_MAX);
+    const FastMod fm = make_fastmod((unsigned)hp.tableSize);
+    auto walk = [&](unsigned threads, const unsigned* slots) {
+        const unsigned grid = (threads + CN_THREADS - 1) / CN_THREADS;
+        if (smemKeys)
+            cache_neighbors_sorted_kernel<true><<<grid, CN_THREADS, 0, L.stream>>>(neighbors, cellStart, cellEnd, sorted, hp, fm, inst.particles,
+                                                                                   slots, threads);
+        else
+            cache_neighbors_sorted_kernel<false><<<grid, CN_THREADS, 0, L.stream>>>(neighbors, cellStart, cellEnd, sorted, hp, fm,
+                                                                                    inst.particles, slots, threads);
+    };
     if (!ownedMask) {
-        cache_neighbors_sorted_kernel<<<(n + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
-            neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, nullptr, n);
+        walk(n, nullptr);
         return 2;
     }
     // decomposed mode: compact the owned slots (scratch behind the sorted records: a counter + numOwned slot indices)
@@ -1240,9 +1256,7 @@ int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, con
     unsigned* slots = counter + 4;
     VT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), L.stream));
     compact_owned_slots_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, ownedMask, n, slots, counter);
-    if (numOwned)
-        cache_neighbors_sorted_kernel<<<(numOwned + CN_THREADS - 1) / CN_THREADS, CN_THREADS, 0, L.stream>>>(
-            neighbors, cellStart, cellEnd, sorted, hp, make_fastmod((unsigned)hp.tableSize), inst.particles, slots, numOwned);
+    if (numOwned) walk(numOwned, slots);
     return 4;
 }
 

@@ -49,6 +49,7 @@ struct GridPlanDev {
     unsigned tileX, tileY;  // owned particles per tile (grid_plan.hpp): 15 x 15, or 14 x 16
 };
 
+constexpr unsigned VT_WALK_SMEM_KEYS_MAX = 3u << 20;  // particles up to which the candidate walk keeps its bucket keys in shared memory
 constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)
 constexpr int VT_MAX_TILE = 512;           // particles (= threads) per Jacobi tile, upper bound
 

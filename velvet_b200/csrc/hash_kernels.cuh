@@ -239,6 +239,9 @@ static __global__ void __launch_bounds__(256) compact_owned_slots_kernel(const S
     if (owned) slots[base + __popc(ballot & ((1u << lane) - 1u))] = t;
 }
 
+// SMEM_KEYS: see s_key below (the better trade up to a few million particles; beyond, the walk is bound by misses of the
+// candidate records and the shared-memory carve-out costs more L1 than the saved instructions are worth)
+template <bool SMEM_KEYS>
 static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kernel(
     unsigned* __restrict__ neighbors, const unsigned* __restrict__ cellStart, const unsigned* __restrict__ cellEnd,
     const SortedParticle* __restrict__ sorted, VtHashParams hp, FastMod fm, unsigned instanceParticles,
@@ -247,7 +250,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     // the particle's 27 bucket keys, [bucket][thread] (conflict-free): phase 1 computes them with compile-time cell offsets,
     // phase 2 reads back the ones it visits -- recomputing a key there (runtime cell offset: two divisions, three selects, the
     // modulo) was 11 % of the kernel's instructions, and the key registers it kept alive cost a CTA of occupancy (48 -> 40)
-    __shared__ unsigned s_key[27 * CN_THREADS];
+    __shared__ unsigned s_key[SMEM_KEYS ? 27 * CN_THREADS : 1];
     const unsigned ti = blockIdx.x * CN_THREADS + threadIdx.x;
     if (ti >= numThreads) return;
     const unsigned t = ownedSlots ? __ldg(ownedSlots + ti) : ti;  // decomposed mode: only the slots of owned particles
@@ -263,6 +266,13 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     const int hx0 = (int)((unsigned)(ix - 1) * 92837111u), hx1 = (int)((unsigned)ix * 92837111u), hx2 = (int)((unsigned)(ix + 1) * 92837111u);
     const int hy0 = (int)((unsigned)(iy - 1) * 689287499u), hy1 = (int)((unsigned)iy * 689287499u), hy2 = (int)((unsigned)(iy + 1) * 689287499u);
     const int hz0 = (int)((unsigned)(iz - 1) * 283923481u), hz1 = (int)((unsigned)iz * 283923481u), hz2 = (int)((unsigned)(iz + 1) * 283923481u);
+    auto key_of = [&](int b) {  // !SMEM_KEYS: the key of bucket b, recomputed
+        const int a = b / 9, m = (b / 3) % 3, c = b % 3;
+        const int hx = a == 0 ? hx0 : a == 1 ? hx1 : hx2;
+        const int hy = m == 0 ? hy0 : m == 1 ? hy1 : hy2;
+        const int hz = c == 0 ? hz0 : c == 1 ? hz1 : hz2;
+        return tableBase + hash_key_fast(hx, hy, hz, fm);
+    };
     // phase 1: which of the 27 buckets (x, y, z traversal order = bit order) are non-empty; 27 independent loads in flight
     unsigned mask = 0;
 #pragma unroll
@@ -271,7 +281,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
         const int hy = ((b / 3) % 3) == 0 ? hy0 : ((b / 3) % 3) == 1 ? hy1 : hy2;
         const int hz = (b % 3) == 0 ? hz0 : (b % 3) == 1 ? hz1 : hz2;
         const unsigned key = tableBase + hash_key_fast(hx, hy, hz, fm);
-        s_key[b * CN_THREADS + threadIdx.x] = key;
+        if (SMEM_KEYS) s_key[b * CN_THREADS + threadIdx.x] = key;
         if (__ldg(cellStart + key) != 0xffffffffu) mask |= 1u << b;
     }
 
@@ -287,7 +297,7 @@ static __global__ void __launch_bounds__(CN_THREADS) cache_neighbors_sorted_kern
     auto fetch_range = [&](unsigned& first, unsigned& last) {
         first = last = 0;
         if (mask) {
-            const unsigned key = s_key[(__ffs(mask) - 1) * CN_THREADS + threadIdx.x];
+            const unsigned key = SMEM_KEYS ? s_key[(__ffs(mask) - 1) * CN_THREADS + threadIdx.x] : key_of(__ffs(mask) - 1);
             mask &= mask - 1;
             first = __ldg(cellStart + key);
             last = __ldg(cellEnd + key);
