@@ -229,3 +229,30 @@ def test_fused_hash_at_headline_size_matches_reference_kernel_digests():
     tab = valid_prefix_table(g.download("neighbors"), n, 64)
     assert np.array_equal(tab[:, gold["sample"]], gold["sample_neighbors"])
     assert sha(tab) == str(gold["neighbors"])
+
+
+def test_band_ordered_candidate_walk_builds_the_same_lists(monkeypatch):
+    """Cloths of more than 3 M particles walk their sorted slots band by band (bands of 2^18 consecutive particle indices,
+    hash_kernels.cuh: band_slots_kernel) so that the candidates of a band stay in L2.  Forced here at a small size, with
+    bands that do and do not divide the particle count: lists and frames must equal the unbanded walk's bit for bit."""
+    import velvet_b200 as vb
+    from util import gpu_params
+
+    def run(band):
+        if band is None:
+            monkeypatch.delenv("VELVET_WALK_BAND", raising=False)
+        else:
+            monkeypatch.setenv("VELVET_WALK_BAND", str(band))
+        g = vb.build_scene(90, gpu_params(numSubsteps=3, numIterations=4))
+        g.UpdateColliders(vb.sphere_plane_colliders())
+        for _ in range(10):
+            g.Simulate()
+        out = (g.download("neighbors").copy(), g.download("positions").copy(), g.download("cellStart").copy())
+        g.close()
+        return out
+
+    ref = run(0)
+    for band in (1000, 4096, 8281, 100000):   # 91 * 91 = 8281 particles: 9 bands, 3 bands (the last one partial), 1 band, 1 oversized band
+        got = run(band)
+        for a, b, name in zip(ref, got, ("neighbors", "positions", "cellStart")):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (band, name)

@@ -1223,7 +1223,8 @@ void launch_cache_neighbors(const FusedLaunch& L, unsigned* neighbors, const uns
 int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, const unsigned* particleIndex,
                                   const unsigned* cellStart, const unsigned* cellEnd, const float4* pred,
                                   const float4* init4, float4* sortedScratch, VtHashParams hp, Instancing inst,
-                                  const unsigned char* ownedMask, unsigned numOwned, const unsigned* sortedHashForCells)
+                                  const unsigned char* ownedMask, unsigned numOwned, const unsigned* sortedHashForCells,
+                                  unsigned ownedBegin, unsigned bandParticles)
 {
     if (hp.tableSize <= 0) return 0;
     const unsigned n = L.numParticles;
@@ -1247,20 +1248,34 @@ int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, con
             cache_neighbors_sorted_kernel<false><<<grid, CN_THREADS, 0, L.stream>>>(neighbors, cellStart, cellEnd, sorted, hp, fm,
                                                                                     inst.particles, slots, threads);
     };
+    // scratch behind the sorted records: CN_MAX_BANDS counters + up to n slot indices
+    unsigned* counter = reinterpret_cast<unsigned*>(sorted + n);
+    unsigned* slots = counter + CN_MAX_BANDS;
+    // a contiguous index range of a large cloth (all of it, or the strip a rank owns): walked band by band (hash_kernels.cuh)
+    if (const char* e = getenv("VELVET_WALK_BAND")) bandParticles = (unsigned)atoi(e);  // particles per band, 0 = never (tests, A/B runs)
+    const bool contiguous = !ownedMask || ownedBegin != 0xffffffffu;
+    if (contiguous && bandParticles) {
+        const unsigned begin = ownedMask ? ownedBegin : 0u, count = ownedMask ? numOwned : n;
+        const unsigned numBands = (count + bandParticles - 1) / bandParticles;
+        if (count && numBands <= CN_MAX_BANDS) {
+            VT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned) * CN_MAX_BANDS, L.stream));
+            band_slots_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, n, begin, count, bandParticles, numBands, slots, counter);
+            walk(count, slots);
+            return 4;
+        }
+    }
     if (!ownedMask) {
         walk(n, nullptr);
         return 2;
     }
-    // decomposed mode: compact the owned slots (scratch behind the sorted records: a counter + numOwned slot indices)
-    unsigned* counter = reinterpret_cast<unsigned*>(sorted + n);
-    unsigned* slots = counter + 4;
+    // decomposed mode: compact the owned slots
     VT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), L.stream));
     compact_owned_slots_kernel<<<pgrid(n), PB, 0, L.stream>>>(sorted, ownedMask, n, slots, counter);
     if (numOwned) walk(numOwned, slots);
     return 4;
 }
 
-size_t cache_neighbors_scratch_float4(size_t n) { return 2 * n + (n + 4 + 3) / 4 + 1; }  // sorted records + counter + owned slots
+size_t cache_neighbors_scratch_float4(size_t n) { return 2 * n + (n + CN_MAX_BANDS + 3) / 4 + 1; }  // sorted records + counters + slots
 
 // plain device-side copy (read-back staging): a kernel rather than cudaMemcpyAsync because the source is managed memory,
 // for which the driver's copy path is not stream-fast

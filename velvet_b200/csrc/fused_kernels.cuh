@@ -49,6 +49,7 @@ struct GridPlanDev {
     unsigned tileX, tileY;  // owned particles per tile (grid_plan.hpp): 15 x 15, or 14 x 16
 };
 
+constexpr unsigned VT_WALK_BAND_PARTICLES = 1u << 18;  // candidate walk of a grid cloth with more particles than VT_WALK_SMEM_KEYS_MAX: band size
 constexpr unsigned VT_WALK_SMEM_KEYS_MAX = 3u << 20;  // particles up to which the candidate walk keeps its bucket keys in shared memory
 constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)
 constexpr int VT_MAX_TILE = 512;           // particles (= threads) per Jacobi tile, upper bound
@@ -132,7 +133,9 @@ int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, con
                                   Instancing inst,  // hp.tableSize = rows per instance
                                   const unsigned char* ownedMask = nullptr,  // decomposed mode: lists of the owned particles only ...
                                   unsigned numOwned = 0,                     // ... exactly this many of them
-                                  const unsigned* sortedHashForCells = nullptr);  // also run FindCellStart (no launch_find_cell_start then)
+                                  const unsigned* sortedHashForCells = nullptr,  // also run FindCellStart (no launch_find_cell_start then)
+                                  unsigned ownedBegin = 0xffffffffu,  // the owned particles are the index range [ownedBegin, +numOwned)
+                                  unsigned bandParticles = 0);        // > 0: walk a contiguous range in bands of this many indices
 size_t cache_neighbors_scratch_float4(size_t numParticles);
 void launch_copy_words(cudaStream_t stream, const void* src, void* dst, size_t words);
 void launch_pack_float4(const FusedLaunch& L, const float* packed3, float4* out, unsigned n);

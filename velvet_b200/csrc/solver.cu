@@ -595,6 +595,12 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
     invalidate();
 }
 
+// Band size of the candidate walk: ids of a grid cloth are row-major, so index bands are compact pieces of cloth (hash_kernels.cuh)
+unsigned VtClothSolverGPU::walkBandParticles() const
+{
+    return (m_gridUsable && !m_instanced && simParams.numParticles > VT_WALK_SMEM_KEYS_MAX) ? VT_WALK_BAND_PARTICLES : 0u;
+}
+
 bool VtClothSolverGPU::deviceRegistration()
 {
     const char* e = getenv("VELVET_HOST_GENERATE");
@@ -1176,7 +1182,8 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             hp.tableSize = H.tableSize() / (int)m_instancing.count;  // rows per instance
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, cur,
-                                                                         m_init4, m_sorted, hp, m_instancing, nullptr, 0, H.particleHash)) {
+                                                                         m_init4, m_sorted, hp, m_instancing, nullptr, 0, H.particleHash,
+                                                                         0xffffffffu, walkBandParticles())) {
                 launches += nl;
             } else {
                 exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);
@@ -1742,7 +1749,7 @@ void VtClothSolverGPU::recordDDStripFrame(Stage* t)
             VtHashParams hp = H.MakeParams(N, P.particleDiameter);
             if (const int nl = exact_math::launch_cache_neighbors_sorted(L, H.neighbors, H.particleIndex, H.cellStart, H.cellEnd, buf[cur],
                                                                          m_init4, m_sorted, hp, m_instancing, m_ddStripMask, count,
-                                                                         H.particleHash)) {
+                                                                         H.particleHash, begin, walkBandParticles())) {
                 launches += nl;
             } else {
                 exact_math::launch_find_cell_start(L, H.cellStart, H.cellEnd, H.particleHash);

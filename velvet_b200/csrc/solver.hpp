@@ -262,6 +262,7 @@ private:
     };
     std::vector<GeneratedCloth> m_generated;
     bool generatedListsIntact() const;
+    unsigned walkBandParticles() const;
     bool buildGridPlanOnDevice(uint planN, cudaStream_t st);
     DeviceBuffer<input::GrabState> m_grab;
     DeviceBuffer<int> m_setupFlags;  // [0] mesh index out of range, [1] bending quads differ from the grid pattern
