@@ -598,7 +598,7 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
 // Band size of the candidate walk: ids of a grid cloth are row-major, so index bands are compact pieces of cloth (hash_kernels.cuh)
 unsigned VtClothSolverGPU::walkBandParticles() const
 {
-    return (m_gridUsable && !m_instanced && simParams.numParticles > VT_WALK_SMEM_KEYS_MAX) ? VT_WALK_BAND_PARTICLES : 0u;
+    return (m_gridUsable && !m_instanced && simParams.numParticles > VT_WALK_BAND_MIN_PARTICLES) ? VT_WALK_BAND_PARTICLES : 0u;
 }
 
 bool VtClothSolverGPU::deviceRegistration()
