@@ -1237,7 +1237,8 @@ int launch_cache_neighbors_sorted(const FusedLaunch& L, unsigned* neighbors, con
         const char* e = getenv("VELVET_WALK_KEYS");
         return e && !strcmp(e, "smem") ? 1 : e && !strcmp(e, "regs") ? 2 : 0;
     }();
-    const bool smemKeys = keysMode == 1 || (keysMode == 0 && n <= VT_WALK_SMEM_KEYS_MAX);
+    // (batched instances sort instance by instance: what counts for the locality of the walk is the size of one instance)
+    const bool smemKeys = keysMode == 1 || (keysMode == 0 && (inst.count > 1 ? inst.particles : n) <= VT_WALK_SMEM_KEYS_MAX);
     const FastMod fm = make_fastmod((unsigned)hp.tableSize);
     auto walk = [&](unsigned threads, const unsigned* slots) {
         const unsigned grid = (threads + CN_THREADS - 1) / CN_THREADS;
