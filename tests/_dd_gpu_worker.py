@@ -42,8 +42,12 @@ dd = DecomposedCloth(dd_solver, local, transport=transport)
 ok = True
 worst = 0.0
 checksum = 0.0
+walk_band = os.environ.get("VELVET_DD_WALK_BAND")  # force the band-ordered candidate walk in the decomposed solver only
 for f in range(frames):
+    if walk_band:
+        os.environ["VELVET_WALK_BAND"] = walk_band
     dd.Simulate()
+    os.environ.pop("VELVET_WALK_BAND", None)
     b = dd_solver.download("positions")
     checksum = float(np.sum(b.astype(np.float64)))
     if have_ref:

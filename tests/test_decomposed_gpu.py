@@ -25,14 +25,19 @@ def _ngpus():
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport,walk_band", [("peer", None), ("nccl", None), ("peer", 5000)])
 @pytest.mark.parametrize("resolution", [63, 255])
-def test_decomposed_cloth_is_bit_identical_to_single_gpu(tmp_path, resolution, transport):
+def test_decomposed_cloth_is_bit_identical_to_single_gpu(tmp_path, resolution, transport, walk_band):
+    """walk_band: the band-ordered candidate walk of the owned strip (what a cloth of more than 1.5 M particles uses), forced
+    at this size in the decomposed ranks only -- the single-GPU solver they are compared with walks unbanded."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     world = min(_ngpus(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "_dd_gpu_worker.py"), str(tmp_path), str(resolution), "4", "0", transport]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ)
+    if walk_band is not None:
+        env["VELVET_DD_WALK_BAND"] = str(walk_band)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     outs = [json.load(open(tmp_path / f"dd_gpu{k}.json")) for k in range(world)]
     for o in outs:
