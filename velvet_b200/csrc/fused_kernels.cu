@@ -665,9 +665,9 @@ __device__ __noinline__ GridBendOut grid_bend_slow(float4 p0, float4 p1, float4 
 // BX x BY bundles per tile = (BX - 1) x (BY - 1) owned particles: 16 x 16, or 15 x 17 (grid_plan.hpp: the cloth side decides)
 template <int BX, int BY>
 __global__ void __launch_bounds__(256, VT_GRID_BLOCKS)
-iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ predOutAll, const GridPlanDev plan,
+iterate_grid_kernel(float4* __restrict__ predA, float4* __restrict__ predB, const GridPlanDev plan,
                     const float* __restrict__ attachSlotsAll, const FrameParams* __restrict__ fp, const Instancing inst,
-                    const unsigned totalWork, const ddpeer::StripArgs strip)
+                    const unsigned totalWork, const ddpeer::StripArgs strip, const unsigned iterations, unsigned* __restrict__ gridBarrier)
 {
     vt_pdl_trigger();  // the next kernel may set itself up while this one runs
     constexpr unsigned NT = 256;
@@ -686,8 +686,7 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
     const bool live = BX * BY == (int)NT || tid < (unsigned)(BX * BY);  // 15 x 17 leaves the last thread without a bundle
     const int by = live ? (int)(tid % (unsigned)BY) : 0, bx = live ? (int)(tid / (unsigned)BY) : 0;
     const unsigned stride = gridDim.x;
-    unsigned w = blockIdx.x;
-    if (w >= totalWork) return;
+    if (blockIdx.x >= totalWork) return;  // (never with more than one iteration per launch: the grid is at most totalWork)
     if (tid < plan.numCloths) s_cloth[tid] = plan.cloths[tid];
     // vertices outside the cloth are never staged: whatever their entries hold must at least be finite
     for (unsigned i = tid; i < 2 * GRID_V * GRID_V + 2 * NT; i += NT) s_mem[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -720,6 +719,8 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         __syncthreads();
     }
 
+    const float4* predInAll = predA;  // input / output of the iteration in progress
+    float4* predOutAll = predB;
     // work item -> first particle of its cloth (instance included), grid side, tile origin.  One thread does this (an integer
     // division and a table walk) two tiles ahead and leaves the result in shared memory for the others.
     auto locate = [&](unsigned item) {
@@ -770,7 +771,7 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         const bool inX = live && (unsigned)gx < (unsigned)t.side, inY = (unsigned)gy < (unsigned)t.side;
         const bool inX1 = (unsigned)(gx + 1) < (unsigned)t.side, inY1 = (unsigned)(gy + 1) < (unsigned)t.side;
         const int idx = gx * t.side + gy;
-        const float4* src = predInAll + t.base + idx;
+        const float4* src = predInAll + t.base + idx;  // (predInAll: this iteration's input, set by the loop below)
         const unsigned dst = spAddr + buf * SP_BYTES;
         if (inX && inY) {
             cp16(dst, src);
@@ -784,6 +785,14 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         }
     };
 
+    // Several Jacobi iterations per launch (`iterations` > 1; a single cloth or batch without a strip exchange): the CTAs of the
+    // launch are all resident (the grid is one wave), so an iteration ends at a grid-wide barrier instead of a kernel
+    // boundary -- a launch and its drain cost ~5 us of the 36 us an iteration takes at 1M particles, the barrier ~2.
+    // Iteration `it` reads predA and writes predB when it is even, the other way round when it is odd.
+    for (unsigned it = 0; it < iterations; it++) {
+    predInAll = (it & 1u) ? predB : predA;
+    predOutAll = (it & 1u) ? predA : predB;
+    unsigned w = blockIdx.x;
     // ring of three tile coordinates: tile k + 2 is written while k and k + 1 are still being read
     if (tid == 0) {
         s_tile[0] = locate(w);
@@ -974,6 +983,21 @@ iterate_grid_kernel(const float4* __restrict__ predInAll, float4* __restrict__ p
         slotCur = slotNext;
     }
     cp_async_wait_all();
+    if (it + 1 < iterations) {  // grid-wide barrier: every CTA's results of this iteration are in memory before anyone reads them
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(gridBarrier, 1u);
+            const unsigned target = (it + 1u) * gridDim.x;
+            const long long t0 = clock64();
+            unsigned seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gridBarrier) : "memory");
+            } while (seen < target && clock64() - t0 < (1ll << 32));  // (~2 s: a launch that is not fully resident must not hang the device)
+        }
+        __syncthreads();
+    }
+    }  // iterations
     if (strip.enabled && tid == 0 && atomicAdd(&strip.ctl->exits, 1u) == gridDim.x - 1) {  // last block out completes the launch
         strip.ctl->exits = 0;
         strip.ctl->seq = stripSeq + 1;
@@ -1144,8 +1168,9 @@ unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned c
     return (unsigned)(sms * perSm);
 }
 
-void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
-                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst, const ddpeer::StripArgs* strip)
+void launch_iterate_grid(const FusedLaunch& L, float4* predIn, float4* predOut, const GridPlanDev& plan,
+                         const float* attachSlotPositions, const FrameParams* fp, Instancing inst, const ddpeer::StripArgs* strip,
+                         unsigned iterations, unsigned* gridBarrier)
 {
     ddpeer::StripArgs a{};
     unsigned total = plan.numTiles * inst.count;
@@ -1154,14 +1179,16 @@ void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* pre
         a.enabled = 1;
         total = (a.tileRowEnd - a.tileRowBegin) * plan.tilesY0;
     }
-    if (!total) return;
-    const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave
+    if (!total || !iterations) return;
+    if (iterations > 1 && (strip || !gridBarrier)) throw Error(VELVET_ERR_STATE, "iterate_grid: several iterations per launch need a barrier word and no strip");
+    const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave, all CTAs resident
+    if (iterations > 1) VT_CUDA(cudaMemsetAsync(gridBarrier, 0, sizeof(unsigned), L.stream));
     if (plan.tileX == (unsigned)GRID_TILE_RX && plan.tileY == (unsigned)GRID_TILE_RY && !strip)
         launch_pdl(iterate_grid_kernel<GRID_TILE_RX + 1, GRID_TILE_RY + 1>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut,
-                   plan, attachSlotPositions, fp, inst, total, a);
+                   plan, attachSlotPositions, fp, inst, total, a, iterations, gridBarrier);
     else if (plan.tileX == (unsigned)GRID_TILE && plan.tileY == (unsigned)GRID_TILE)
         launch_pdl(iterate_grid_kernel<GRID_B, GRID_B>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut, plan,
-                   attachSlotPositions, fp, inst, total, a);
+                   attachSlotPositions, fp, inst, total, a, iterations, gridBarrier);
     else
         throw Error(VELVET_ERR_STATE, "iterate_grid: no kernel for this tile shape");
 }

@@ -103,9 +103,12 @@ void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
 // The same iteration for grid cloths without index records (iterate_grid_kernel): bit-identical to launch_iterate.
-void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
+// iterations > 1 (no strip): that many Jacobi iterations in ONE launch, separated by grid-wide barriers on *gridBarrier; the
+// result is in predOut when `iterations` is odd, in predIn when it is even (both arrays are overwritten along the way)
+void launch_iterate_grid(const FusedLaunch& L, float4* predIn, float4* predOut, const GridPlanDev& plan,
                          const float* attachSlotPositions, const FrameParams* fp, Instancing inst,
-                         const ddpeer::StripArgs* strip = nullptr);  // strip: this rank's rows of a decomposed cloth (dd_peer.cuh)
+                         const ddpeer::StripArgs* strip = nullptr,  // strip: this rank's rows of a decomposed cloth (dd_peer.cuh)
+                         unsigned iterations = 1, unsigned* gridBarrier = nullptr);
 unsigned configure_iterate_grid_kernel();  // returns resident CTAs on the device
 unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 
@@ -174,9 +177,12 @@ void launch_iterate(const FusedLaunch& L, const float4* predIn, float4* predOut,
                     const float* attachSlotPositions, const FrameParams* fp, Instancing inst);
 size_t iterate_smem_bytes(const TilePlanDev& plan);
 // The same iteration for grid cloths without index records (iterate_grid_kernel): bit-identical to launch_iterate.
-void launch_iterate_grid(const FusedLaunch& L, const float4* predIn, float4* predOut, const GridPlanDev& plan,
+// iterations > 1 (no strip): that many Jacobi iterations in ONE launch, separated by grid-wide barriers on *gridBarrier; the
+// result is in predOut when `iterations` is odd, in predIn when it is even (both arrays are overwritten along the way)
+void launch_iterate_grid(const FusedLaunch& L, float4* predIn, float4* predOut, const GridPlanDev& plan,
                          const float* attachSlotPositions, const FrameParams* fp, Instancing inst,
-                         const ddpeer::StripArgs* strip = nullptr);  // strip: this rank's rows of a decomposed cloth (dd_peer.cuh)
+                         const ddpeer::StripArgs* strip = nullptr,  // strip: this rank's rows of a decomposed cloth (dd_peer.cuh)
+                         unsigned iterations = 1, unsigned* gridBarrier = nullptr);
 unsigned configure_iterate_grid_kernel();  // returns resident CTAs on the device
 unsigned configure_iterate_kernel(size_t smemBytes, unsigned threads, unsigned ctaThreads);  // opt in to > 48 KB smem; returns resident CTAs on the device
 

@@ -596,6 +596,13 @@ void VtClothSolverGPU::AddClothInstances(int R, const float* vertices, const uin
 }
 
 // Band size of the candidate walk: ids of a grid cloth are row-major, so index bands are compact pieces of cloth (hash_kernels.cuh)
+// 0 / 1: one Jacobi iteration per launch; otherwise all iterations of a substep in one launch (VELVET_GRID_MULTI=0 for A/B runs)
+unsigned VtClothSolverGPU::gridIterationsPerLaunch() const
+{
+    const char* e = getenv("VELVET_GRID_MULTI");
+    return (e && e[0] == '0') ? 1u : 2u;
+}
+
 unsigned VtClothSolverGPU::walkBandParticles() const
 {
     return (m_gridUsable && !m_instanced && simParams.numParticles > VT_WALK_BAND_MIN_PARTICLES) ? VT_WALK_BAND_PARTICLES : 0u;
@@ -1080,6 +1087,7 @@ void VtClothSolverGPU::ensureFusedResources()
     m_predA.allocate(std::max<size_t>(N, 131072));
     m_predB.allocate(std::max<size_t>(N, 131072));
     m_init4.allocate(N);
+    m_gridBarrier.allocate(4);
     m_sorted.allocate(exact_math::cache_neighbors_scratch_float4(N));
     m_keysAlt.allocate(N);
     m_valsAlt.allocate(N);
@@ -1199,13 +1207,20 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
         STAGE_END(t);
 
         STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
-        for (int iteration = 0; iteration < P.numIterations; iteration++) {
-            if (m_gridUsable)
-                ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing, nullptr);
-            else
-                ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp, m_instancing);
+        if (m_gridUsable && gridIterationsPerLaunch() > 1 && P.numIterations > 1) {
+            // all iterations of the substep in one launch of the (one-wave, fully resident) grid kernel, grid barriers in between
+            ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing, nullptr, (unsigned)P.numIterations, m_gridBarrier.data());
             launches++;
-            std::swap(cur, other);
+            if (P.numIterations & 1) std::swap(cur, other);
+        } else {
+            for (int iteration = 0; iteration < P.numIterations; iteration++) {
+                if (m_gridUsable)
+                    ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing, nullptr, 1u, nullptr);
+                else
+                    ops.iterate(L, cur, other, m_planDev, m_slotsDev, fp, m_instancing);
+                launches++;
+                std::swap(cur, other);
+            }
         }
         STAGE_END(t);
 
@@ -1776,7 +1791,7 @@ void VtClothSolverGPU::recordDDStripFrame(Stage* t)
             // Nobody reads those rows of that buffer meanwhile: iterations only read the rows next to their own strip, and a
             // neighbour has published (i.e. finished reading them) before this launch passes its wait.
             A.gatherAll = iteration == P.numIterations - 1 ? 1 : 0;
-            ops.iterate_grid(L, buf[cur], buf[other], m_gridDev, m_slotsDev, fp, m_instancing, &A);
+            ops.iterate_grid(L, buf[cur], buf[other], m_gridDev, m_slotsDev, fp, m_instancing, &A, 1u, nullptr);
             launches++;
             std::swap(cur, other);
         }

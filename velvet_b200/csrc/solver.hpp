@@ -263,6 +263,8 @@ private:
     std::vector<GeneratedCloth> m_generated;
     bool generatedListsIntact() const;
     unsigned walkBandParticles() const;
+    unsigned gridIterationsPerLaunch() const;
+    DeviceBuffer<unsigned> m_gridBarrier;  // arrival counter of the grid-wide barriers of a multi-iteration launch
     bool buildGridPlanOnDevice(uint planN, cudaStream_t st);
     DeviceBuffer<input::GrabState> m_grab;
     DeviceBuffer<int> m_setupFlags;  // [0] mesh index out of range, [1] bending quads differ from the grid pattern
