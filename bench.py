@@ -525,9 +525,14 @@ def velvet_main(args, rank, world, local_rank):
     del nb
     rebuilds = len([s for s in range(SUBSTEPS) if s % p.interleavedHash == 0])
     alg = algorithmic_bytes(N, S, B, A, rebuilds, nbar)
-    iter_launch_ms = stages.get("Solver_Iterate", 0.0) / (SUBSTEPS * ITERATIONS)
+    # the grid kernel runs all iterations of a substep in ONE launch (grid-wide barriers in between): a launch is then
+    # `iters_per_launch` iterations, with that many times the algorithmic bytes of one iteration
+    frame_launches = int(g.lastLaunchCount)
+    iters_per_launch = ITERATIONS if (iterate_kernel.startswith("iterate_grid") and frame_launches < SUBSTEPS * ITERATIONS) else 1
+    iteration_ms = stages.get("Solver_Iterate", 0.0) / (SUBSTEPS * ITERATIONS)
+    iter_launch_ms = iteration_ms * iters_per_launch
     peak, peak_src = measured_peak_gbs()
-    achieved = alg["iterate_per_launch"] / (iter_launch_ms * 1e-3) / 1e9 if iter_launch_ms > 0 else 0.0
+    achieved = alg["iterate_per_launch"] * iters_per_launch / (iter_launch_ms * 1e-3) / 1e9 if iter_launch_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:  # static: one `ncu --set full` capture of this kernel on this workload, committed with its summary under profiles/
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -539,10 +544,11 @@ def velvet_main(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": iterate_kernel + " (SolveStretch+SolveAttach+SolveBending+ApplyDeltas fused)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": ("static, not measured in this run: " + str(traffic_src)) if traffic is not None else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["iterate_per_launch"],
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["iterate_per_launch"] * iters_per_launch,
                 "algorithmic_bytes_per_particle": alg["per_particle_iter"], "launch_ms": iter_launch_ms,
+                "iterations_per_launch": iters_per_launch, "iteration_ms": iteration_ms,
                 "how": f"CUDA events per stage on the solver stream, un-graphed pass over the middle frames of the timed region, "
-                       f"mean of {SUBSTEPS * ITERATIONS} launches x {stage_frames} frames",
+                       f"mean of {SUBSTEPS * ITERATIONS // iters_per_launch} launches x {stage_frames} frames",
                 "share_of_frame": stages.get("Solver_Iterate", 0.0) / max(stages.get("Solver_Total", 1e-9), 1e-9),
                 "frame": {"algorithmic_bytes": alg["frame"], "achieved": frame_gbs, "frac": frame_gbs / peak}}
 
@@ -561,7 +567,7 @@ def velvet_main(args, rank, world, local_rank):
     restart(W + max(0, args.steps // 2 - 1))
     ostage = g.SimulateTimed()
     other = {"math": other_name, "ms_per_step": oms, "value": N * SUBSTEPS / (oms * 1e-3),
-             "iterate_launch_ms": ostage.get("Solver_Iterate", 0.0) / (SUBSTEPS * ITERATIONS)}
+             "iteration_ms": ostage.get("Solver_Iterate", 0.0) / (SUBSTEPS * ITERATIONS)}
     g.SetMathMode(math_mode)
 
     cpu_baseline = None

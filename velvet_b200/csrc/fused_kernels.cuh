@@ -53,6 +53,7 @@ struct GridPlanDev {
 // (measured: no gain at 1.0 M particles, -23 % at 2.1 M, -26 % at 3.0 M, -31 % at 4.2 M, -23 % at 16.7 M)
 constexpr unsigned VT_WALK_BAND_PARTICLES = 1u << 18, VT_WALK_BAND_MIN_PARTICLES = 3u << 19;
 constexpr unsigned VT_WALK_SMEM_KEYS_MAX = 4u << 20;  // particles up to which the candidate walk keeps its bucket keys in shared memory
+constexpr unsigned VT_GRID_MAX_ITERATIONS_PER_LAUNCH = 64;  // more Jacobi iterations than this per substep: one launch each
 constexpr unsigned VT_MAX_COLLIDERS = 64;  // staged per block in shared memory (196 B each)
 constexpr int VT_MAX_TILE = 512;           // particles (= threads) per Jacobi tile, upper bound
 

@@ -1207,8 +1207,10 @@ void VtClothSolverGPU::recordFusedFrame(Stage* t)
         STAGE_END(t);
 
         STAGE_BEGIN(t, "Solver_Iterate");  // SolveStretch + SolveAttach + SolveBending + ApplyDeltas
-        if (m_gridUsable && gridIterationsPerLaunch() > 1 && P.numIterations > 1) {
+        if (m_gridUsable && gridIterationsPerLaunch() > 1 && P.numIterations > 1 && (uint)P.numIterations <= VT_GRID_MAX_ITERATIONS_PER_LAUNCH &&
+            (size_t)m_gridDev.numTiles * m_instancing.count >= 2 * (size_t)m_gridDev.residentCtas) {
             // all iterations of the substep in one launch of the (one-wave, fully resident) grid kernel, grid barriers in between
+            // (with less than a few tiles per CTA a kernel boundary is the cheaper barrier: 256^2 0.526 against 0.545 ms per frame)
             ops.iterate_grid(L, cur, other, m_gridDev, m_slotsDev, fp, m_instancing, nullptr, (unsigned)P.numIterations, m_gridBarrier.data());
             launches++;
             if (P.numIterations & 1) std::swap(cur, other);
