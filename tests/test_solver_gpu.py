@@ -633,3 +633,34 @@ def test_nonzero_rest_angles_uploaded_after_registration(iterate_kernel_param):
         g2.Simulate()
         o2.simulate()
     assert_fused_parity(g2, o2, TOL_60)
+
+
+def test_two_solvers_running_concurrently_on_one_device():
+    """A cloth with several tiles per CTA runs the ten Jacobi iterations of a substep in ONE launch with grid-wide barriers in
+    between (solver.cu: recordFusedFrame).  Such a launch is cooperative: two solvers whose frames overlap on the device (each
+    has its own stream) must neither dead-lock nor disturb each other's results."""
+    p = gpu_params(numSubsteps=3, numIterations=6)
+
+    def make(height):
+        g = vb.build_scene(479, p, position=(0, height, 1.0))  # 480 x 480 particles = 1024 tiles: multi-iteration launches
+        g.UpdateColliders(vb.sphere_plane_colliders())
+        return g
+
+    a, b = make(1.5), make(1.55)
+    for _ in range(6):
+        a.Simulate(sync=False)
+        b.Simulate(sync=False)
+    a.Synchronize()
+    b.Synchronize()
+    # the iterations really were fused into one launch per substep: 19 launches per frame (2 + one rebuild of 7 + 3 x 3 + normals);
+    # with one launch per iteration it would be 34
+    if a.iterateKernel == vb.ITERATE_GRID:
+        assert a.lastLaunchCount < 25, a.lastLaunchCount
+    ra, rb = make(1.5), make(1.55)
+    for _ in range(6):
+        ra.Simulate()
+    for _ in range(6):
+        rb.Simulate()
+    for name in ("positions", "velocities", "normals"):
+        assert np.array_equal(a.download(name), ra.download(name)), name
+        assert np.array_equal(b.download(name), rb.download(name)), name

@@ -56,7 +56,17 @@ inline bool pdl_enabled()
     return on;
 }
 template <class... KArgs, class... Args>
+void launch_kernel_ex(bool cooperative, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args);
+// cooperative: the grid synchronises inside the kernel (grid-wide barriers), so the driver must place ALL its CTAs at once --
+// with a plain launch two such grids on one device (two solvers on their own streams) could each hold part of the SMs and
+// wait for the other for ever.  A cooperative launch is not combined with programmatic dependent launch.
+template <class... KArgs, class... Args>
 void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    launch_kernel_ex(false, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+template <class... KArgs, class... Args>
+void launch_kernel_ex(bool cooperative, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -64,10 +74,16 @@ void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (cooperative) {
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.numAttrs = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
     VT_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
@@ -1183,12 +1199,13 @@ void launch_iterate_grid(const FusedLaunch& L, float4* predIn, float4* predOut, 
     if (iterations > 1 && (strip || !gridBarrier)) throw Error(VELVET_ERR_STATE, "iterate_grid: several iterations per launch need a barrier word and no strip");
     const unsigned grid = total < plan.residentCtas ? total : plan.residentCtas;  // persistent: one wave, all CTAs resident
     if (iterations > 1) VT_CUDA(cudaMemsetAsync(gridBarrier, 0, sizeof(unsigned), L.stream));
+    const bool coop = iterations > 1;  // grid-wide barriers inside: every CTA must be resident
     if (plan.tileX == (unsigned)GRID_TILE_RX && plan.tileY == (unsigned)GRID_TILE_RY && !strip)
-        launch_pdl(iterate_grid_kernel<GRID_TILE_RX + 1, GRID_TILE_RY + 1>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut,
-                   plan, attachSlotPositions, fp, inst, total, a, iterations, gridBarrier);
+        launch_kernel_ex(coop, iterate_grid_kernel<GRID_TILE_RX + 1, GRID_TILE_RY + 1>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream,
+                         predIn, predOut, plan, attachSlotPositions, fp, inst, total, a, iterations, gridBarrier);
     else if (plan.tileX == (unsigned)GRID_TILE && plan.tileY == (unsigned)GRID_TILE)
-        launch_pdl(iterate_grid_kernel<GRID_B, GRID_B>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut, plan,
-                   attachSlotPositions, fp, inst, total, a, iterations, gridBarrier);
+        launch_kernel_ex(coop, iterate_grid_kernel<GRID_B, GRID_B>, dim3(grid), dim3(256), GRID_SMEM_BYTES, L.stream, predIn, predOut, plan,
+                         attachSlotPositions, fp, inst, total, a, iterations, gridBarrier);
     else
         throw Error(VELVET_ERR_STATE, "iterate_grid: no kernel for this tile shape");
 }
